@@ -1,0 +1,199 @@
+/* smalfit.h -- C-ABI of libsmalfit (B200 / sm_100a).
+ *
+ * Drop-in boundary for the SMALify fitting hot path.  The reference has no native
+ * interface (it is pure Python on torch + PyTorch3D); each entry point below names
+ * the reference Python surface it replaces (paths relative to the SMALify checkout).
+ * The Python binding a maintainer would add is in INTEGRATION.md and
+ * smalify_b200/_cabi.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative SMALFIT_E* code; the message
+ *     is available from smalfit_last_error().  Nothing throws across the ABI.
+ *   - "dev" pointers are CUDA device pointers on the handle's device, "host"
+ *     pointers are ordinary (ideally pinned) host memory.
+ *   - work is enqueued on the cudaStream_t passed as `void* stream` (NULL = legacy
+ *     default stream); the caller keeps every buffer alive until that work is done.
+ *   - a handle is bound to one device and is not re-entrant; one handle per GPU.
+ *   - frames are addressed as a contiguous range [frame0, frame0 + n_frames) of the
+ *     sequence the handle was sized for.
+ */
+#ifndef SMALFIT_H_
+#define SMALFIT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMALFIT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SMALFIT_API __attribute__((visibility("default")))
+#else
+#define SMALFIT_API
+#endif
+
+#define SMALFIT_OK 0
+#define SMALFIT_EINVAL (-1)   /* bad argument */
+#define SMALFIT_ECUDA (-2)    /* CUDA runtime error */
+#define SMALFIT_ENOMEM (-3)
+#define SMALFIT_ESTATE (-4)   /* call order (e.g. targets not set) */
+
+#define SMALFIT_N_JOINTS 35
+#define SMALFIT_N_POSE 34
+#define SMALFIT_N_BETAS 20
+#define SMALFIT_N_LOGSCALE 6
+#define SMALFIT_N_KEYPOINTS 25
+#define SMALFIT_N_MODEL_JOINTS 41
+
+/* indices into the loss_terms[8] output (the `objs` dict of SMALFitter.forward,
+ * smal_fitter/smal_fitter.py:138-175, plus the temporal sum and the total) */
+#define SMALFIT_L_JOINT 0
+#define SMALFIT_L_SIL 1
+#define SMALFIT_L_BETAS 2
+#define SMALFIT_L_POSE 3
+#define SMALFIT_L_LIMIT 4     /* always 0: disabled in the reference (smal_fitter.py:146-151) */
+#define SMALFIT_L_SPLAY 5
+#define SMALFIT_L_TEMPORAL 6
+#define SMALFIT_L_TOTAL 7
+
+typedef struct smalfit_ctx* smalfit_t;
+
+/* Model constants (HOST pointers, copied at create).  Replaces what
+ * SMAL.__init__ (smal_model/smal_torch.py:24-96), Prior.__init__
+ * (smal_fitter/priors/pose_prior_35.py:51-92) and the shape-prior block of
+ * SMALFitter.__init__ (smal_fitter/smal_fitter.py:48-72) keep on the device.
+ * Sparse tables are the ones smalify_b200/model_io.py::build_tables derives. */
+typedef struct {
+    int32_t n_verts, n_faces;
+    const float* v_template;     /* [V*3] */
+    const float* shapedirs;      /* [20 * V*3] */
+    const int32_t* faces;        /* [F*3] */
+    const int32_t* parents;      /* [35], root -1, parents precede children */
+    const int32_t* scale_axis;   /* [35*3] log-scale index per joint axis or -1 */
+    /* skinning weights: ELL by vertex and CSC by joint */
+    const int32_t* skin_joint;   /* [V*8] */
+    const float* skin_weight;    /* [V*8], 0-padded */
+    const int32_t* skinT_ptr;    /* [36] */
+    const int32_t* skinT_vert;
+    const float* skinT_weight;
+    /* joint regressor: rest joints (35) by joint / by vertex */
+    const int32_t* jreg_ptr;     /* [36] */
+    const int32_t* jreg_vert;
+    const float* jreg_weight;
+    const int32_t* jregT_ptr;    /* [V+1] */
+    const int32_t* jregT_joint;
+    const float* jregT_weight;
+    /* model joints (35 regressed + 6 picked vertices) by joint / by vertex */
+    const int32_t* mj_ptr;       /* [42] */
+    const int32_t* mj_vert;
+    const float* mj_weight;
+    const int32_t* mjT_ptr;      /* [V+1] */
+    const int32_t* mjT_joint;
+    const float* mjT_weight;
+    /* vertex -> incident (face*4 + corner) */
+    const int32_t* v2f_ptr;      /* [V+1] */
+    const int32_t* v2f_fc;
+    const int32_t* keypoint_joint;   /* [25] model joint per keypoint (config.py:77-88) */
+    /* priors */
+    const float* pose_mean;      /* [105] */
+    const float* pose_prec;      /* [105*105] row-major 'pic' */
+    const float* pose_use;       /* [105] */
+    int32_t shape_dim;           /* 26 (unity prior: betas + log scales) or 20 */
+    const float* shape_mean;     /* [shape_dim] */
+    const float* shape_prec;     /* [shape_dim*shape_dim] row-major */
+} smalfit_model_t;
+
+/* The five trainable tensors of SMALFitter (smal_fitter.py:58,61,83,86,89), as dev
+ * pointers.  Rotations are indexed by absolute frame id. */
+typedef struct {
+    float* betas;             /* [n_shapes*20]  (n_shapes = 1: shared, as the reference) */
+    float* log_beta_scales;   /* [n_shapes*6] */
+    float* global_rotation;   /* [N*3] */
+    float* joint_rotations;   /* [N*34*3] */
+    float* trans;             /* [N*3] */
+} smalfit_tensors_t;
+
+/* ---- lifecycle --------------------------------------------------------- */
+SMALFIT_API int smalfit_abi_version(void);
+
+/* Replaces SMALFitter.__init__'s device setup (SMAL(...) + Renderer(...),
+ * smal_fitter.py:101-102).  max_frames = N frames of the sequence, image_size = S. */
+SMALFIT_API int smalfit_create(const smalfit_model_t* model, int device, int max_frames, int image_size,
+                   smalfit_t* out);
+SMALFIT_API void smalfit_destroy(smalfit_t h);
+SMALFIT_API const char* smalfit_last_error(smalfit_t h);   /* h may be NULL: last create error */
+
+/* ---- targets (self.sil_imgs / target_joints / target_visibility,
+ *      smal_fitter.py:28-29,118-120) ------------------------------------- */
+/* sil: [n*S*S] uint8 {0,1}; joints: [n*25*2] float (row,col); visibility: [n*25] uint8.
+ * from_host != 0: pointers are host memory, copied H2D on `stream` (this is the copy
+ * SMALFitter.forward repeats every call); 0: device pointers, copied D2D. */
+SMALFIT_API int smalfit_set_targets(smalfit_t h, int frame0, int n_frames, const uint8_t* sil,
+                        const float* joints, const uint8_t* visibility, int from_host, void* stream);
+/* only the visibility rows (optimize_to_joints.py:98-110 rewrites them per stage) */
+SMALFIT_API int smalfit_set_visibility(smalfit_t h, int frame0, int n_frames, const uint8_t* visibility,
+                           int from_host, void* stream);
+/* rotation masks global_mask[3], rotation_mask[34*3] (smal_fitter.py:92,97); host ptrs */
+SMALFIT_API int smalfit_set_masks(smalfit_t h, const float* global_mask, const float* rotation_mask);
+/* frames_per_window[i] = number of frames in the window that frame i belongs to
+ * (the B of every mean() in SMALFitter.forward); host pointer, N entries. Default N. */
+SMALFIT_API int smalfit_set_windows(smalfit_t h, const int32_t* frames_per_window, int n_frames);
+
+/* Extension (not in the reference): one shape (betas, log_beta_scales) per frame and one
+ * window per frame, for batches of independent images.  params.betas is then [N*20]. */
+SMALFIT_API int smalfit_set_per_frame_shapes(smalfit_t h, int enable);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* One SMALFitter.forward(batch_range, weights, stage_id) + its backward
+ * (smal_fitter.py:107-175 and the autograd pass of optimize_to_joints.py:136) for
+ * frames [frame0, frame0+n_frames):
+ *   weights[6] = (w_j2d, w_reproj, w_betas, w_pose, w_limit, w_splay)
+ *   grads     : dL/d(each tensor), ASSIGNED (not accumulated) for the frames of the
+ *               range (betas / log_beta_scales: whole tensor); a NULL member skips it
+ *   loss_terms: dev float[8], see SMALFIT_L_*
+ *   prior_windows: how many windows this call stands for in the shape-prior term
+ *               (1 for a single forward; n_windows when a whole epoch is fused; 0 on the
+ *               ranks that must not count the shared-shape prior when frames are sharded) */
+SMALFIT_API int smalfit_loss_grad(smalfit_t h, const smalfit_tensors_t* params, int frame0, int n_frames,
+                      const float weights[6], int prior_windows, const smalfit_tensors_t* grads,
+                      float* loss_terms, void* stream);
+
+/* SMALFitter.get_temporal(w_temp) (smal_fitter.py:177-190) over frames [0,N) and its
+ * gradient ADDED into grads.{global_rotation,joint_rotations,trans}; terms = dev
+ * float[3] (joint, global, trans) as the reference returns them. */
+SMALFIT_API int smalfit_temporal(smalfit_t h, const smalfit_tensors_t* params, int n_frames, float w_temp,
+                     const smalfit_tensors_t* grads, float* terms, void* stream);
+
+/* torch.optim.Adam(lr, betas=(0.5,0.999), eps=1e-8).step() (optimize_to_joints.py:96,137)
+ * on the tensors whose `train` flag is set; state m/v are caller-owned dev tensors of
+ * the same layout (zeroed by the caller at the start of a stage).  step >= 1 uses that
+ * step count; step == 0 uses a device-side counter (incremented by the call, reset by
+ * smalfit_adam_reset) so that the call can be captured in a CUDA graph. */
+SMALFIT_API int smalfit_adam_step(smalfit_t h, const smalfit_tensors_t* params, const smalfit_tensors_t* grads,
+                      const smalfit_tensors_t* exp_avg, const smalfit_tensors_t* exp_avg_sq,
+                      int n_frames, const int32_t train[5], float lr, float beta1, float beta2,
+                      float eps, int step, void* stream);
+
+SMALFIT_API int smalfit_adam_reset(smalfit_t h, void* stream);
+
+/* ---- read-outs (Renderer.forward outputs, p3d_renderer.py:61-74) ------- */
+/* soft silhouettes [n*S*S] float and projected keypoints [n*25*2] (row,col) for the
+ * given frames; either output may be NULL.  No gradients. */
+SMALFIT_API int smalfit_render(smalfit_t h, const smalfit_tensors_t* params, int frame0, int n_frames,
+                   float* silhouettes, float* keypoints, void* stream);
+/* posed vertices [n*V*3] (SMAL.__call__ verts + trans, smal_fitter.py:129) */
+SMALFIT_API int smalfit_vertices(smalfit_t h, const smalfit_tensors_t* params, int frame0, int n_frames,
+                     float* verts, void* stream);
+
+/* ---- diagnostics ------------------------------------------------------- */
+/* counters[0] = pixels whose fragment count exceeded the K=100 cap (last call)
+ * counters[1] = pixels whose fragment count exceeded the selection buffer (inexact!)
+ * counters[2] = raster kernel launches since create, counters[3] = all kernel launches */
+SMALFIT_API int smalfit_counters(smalfit_t h, int64_t counters[4], void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMALFIT_H_ */

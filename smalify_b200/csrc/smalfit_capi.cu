@@ -1,0 +1,427 @@
+// smalfit_capi.cu -- the C-ABI of libsmalfit (see include/smalfit.h).
+// Owns the device copy of the model constants and the step workspace; every entry
+// point only enqueues kernels / async copies on the caller's stream.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/smalfit.h"
+#include "smalfit_kernels.cuh"
+
+using namespace smf;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevPool {                 // every allocation of a handle, freed together
+    std::vector<void*> ptrs;
+    cudaError_t err = cudaSuccess;
+    template <typename T>
+    T* alloc(size_t n, bool zero = false) {
+        void* p = nullptr;
+        if (err != cudaSuccess) return nullptr;
+        err = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
+        if (err != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        if (zero) err = cudaMemset(p, 0, (n ? n : 1) * sizeof(T));
+        return static_cast<T*>(p);
+    }
+    template <typename T>
+    T* upload(const T* host, size_t n) {
+        T* p = alloc<T>(n);
+        if (p && n) err = cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice);
+        return p;
+    }
+    void release() {
+        for (void* p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+};
+
+}  // namespace
+
+struct smalfit_ctx {
+    int device = 0;
+    int N = 0, S = 0;
+    int n_sm = 0, raster_ctas = 0;
+    ModelDev m{};
+    Workspace w{};
+    RasterScratch sc{};
+    float* ndc_soa = nullptr;
+    AdamState* adam_state = nullptr;
+    // mutable target buffers (Workspace holds const views)
+    uint8_t* sil = nullptr; float* kp_target = nullptr; uint8_t* vis = nullptr;
+    float* tile_tsum = nullptr; float* inv_window = nullptr; float* gmask = nullptr; float* rmask = nullptr;
+    bool targets_set = false;
+    DevPool pool;
+    std::string error;
+    long long n_raster_launches = 0, n_launches = 0;
+};
+
+namespace {
+
+int fail(smalfit_t h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->error = buf; else g_create_error = buf;
+    return code;
+}
+
+int check_cuda(smalfit_t h, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return SMALFIT_OK;
+    return fail(h, SMALFIT_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int check_launch(smalfit_t h, const char* what) { return check_cuda(h, cudaGetLastError(), what); }
+
+Params to_params(const smalfit_tensors_t* t) {
+    Params p;
+    p.betas = t->betas; p.logscale = t->log_beta_scales; p.glob = t->global_rotation;
+    p.joint = t->joint_rotations; p.trans = t->trans;
+    return p;
+}
+Grads to_grads(const smalfit_tensors_t* t) {
+    Grads g{};
+    if (t) { g.betas = t->betas; g.logscale = t->log_beta_scales; g.glob = t->global_rotation; g.joint = t->joint_rotations; g.trans = t->trans; }
+    return g;
+}
+
+bool range_ok(smalfit_t h, int frame0, int n) { return frame0 >= 0 && n > 0 && frame0 + n <= h->N; }
+
+}  // namespace
+
+extern "C" {
+
+int smalfit_abi_version(void) { return SMALFIT_ABI_VERSION; }
+
+const char* smalfit_last_error(smalfit_t h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int image_size, smalfit_t* out) {
+    if (!md || !out || max_frames <= 0 || image_size <= 0 || image_size > 4096)
+        return fail(nullptr, SMALFIT_EINVAL, "smalfit_create: bad arguments");
+    if (md->n_verts <= 0 || md->n_verts > 65535 || md->n_faces <= 0 || md->n_faces > 65504)
+        return fail(nullptr, SMALFIT_EINVAL, "smalfit_create: mesh size out of range (V=%d F=%d)", md->n_verts, md->n_faces);
+    if (md->shape_dim != 26 && md->shape_dim != 20)
+        return fail(nullptr, SMALFIT_EINVAL, "smalfit_create: shape_dim must be 26 or 20");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, SMALFIT_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, SMALFIT_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(nullptr, SMALFIT_ECUDA, "libsmalfit is built for sm_100a; device %d is sm_%d%d", device, prop.major, prop.minor);
+
+    smalfit_ctx* h = new smalfit_ctx();
+    h->device = device; h->N = max_frames; h->S = image_size; h->n_sm = prop.multiProcessorCount;
+    h->raster_ctas = 2 * h->n_sm;
+    const int V = md->n_verts, F = md->n_faces;
+    ModelDev& m = h->m;
+    m.V = V; m.F = F; m.Fp = (F + 31) / 32 * 32; m.Vp = (V + 3) / 4 * 4;
+    DevPool& P = h->pool;
+
+    // ---- skeleton tables ----
+    SkeletonConst sk{};
+    int depth[NJ];
+    for (int j = 0; j < NJ; ++j) {
+        sk.parents[j] = md->parents[j];
+        if (j > 0 && (md->parents[j] < 0 || md->parents[j] >= j)) { delete h; return fail(nullptr, SMALFIT_EINVAL, "parents must precede children"); }
+        depth[j] = (j == 0) ? 0 : depth[md->parents[j]] + 1;
+        for (int a = 0; a < 3; ++a) sk.scale_axis[j * 3 + a] = md->scale_axis[j * 3 + a];
+    }
+    int maxd = 0;
+    for (int j = 0; j < NJ; ++j) maxd = depth[j] > maxd ? depth[j] : maxd;
+    if (maxd + 1 > MAX_LEVELS) { delete h; return fail(nullptr, SMALFIT_EINVAL, "kinematic tree too deep"); }
+    sk.n_levels = maxd + 1;
+    int pos = 0;
+    for (int d = 0; d <= maxd; ++d) {
+        sk.level_start[d] = pos;
+        for (int j = 0; j < NJ; ++j) if (depth[j] == d) sk.joint_order[pos++] = j;
+    }
+    sk.level_start[maxd + 1] = pos;
+    pos = 0;
+    for (int p = 0; p < NJ; ++p) {
+        sk.child_ptr[p] = pos;
+        for (int j = 1; j < NJ; ++j) if (md->parents[j] == p) sk.child_idx[pos++] = j;
+    }
+    sk.child_ptr[NJ] = pos;
+    for (int k = 0; k < NKP; ++k) sk.kp_joint[k] = md->keypoint_joint[k];
+    upload_skeleton(sk);
+
+    // ---- model constants ----
+    m.v_template = P.upload(md->v_template, (size_t)V * 3);
+    m.shapedirs = P.upload(md->shapedirs, (size_t)NBETA * V * 3);
+    std::vector<ushort4> f4(m.Fp, make_ushort4(0, 0, 0, 0));
+    for (int f = 0; f < F; ++f) {
+        const int a = md->faces[f * 3], b = md->faces[f * 3 + 1], c = md->faces[f * 3 + 2];
+        if (a < 0 || a >= V || b < 0 || b >= V || c < 0 || c >= V) { P.release(); delete h; return fail(nullptr, SMALFIT_EINVAL, "face index out of range"); }
+        f4[f] = make_ushort4((unsigned short)a, (unsigned short)b, (unsigned short)c, 1);
+    }
+    m.faces4 = P.upload(f4.data(), f4.size());
+    m.skin_joint = P.upload(md->skin_joint, (size_t)V * MAXINF);
+    m.skin_weight = P.upload(md->skin_weight, (size_t)V * MAXINF);
+    m.skinT_ptr = P.upload(md->skinT_ptr, NJ + 1);
+    m.skinT_vert = P.upload(md->skinT_vert, md->skinT_ptr[NJ]);
+    m.skinT_weight = P.upload(md->skinT_weight, md->skinT_ptr[NJ]);
+    m.jreg_ptr = P.upload(md->jreg_ptr, NJ + 1);
+    m.jreg_vert = P.upload(md->jreg_vert, md->jreg_ptr[NJ]);
+    m.jreg_weight = P.upload(md->jreg_weight, md->jreg_ptr[NJ]);
+    m.jregT_ptr = P.upload(md->jregT_ptr, V + 1);
+    m.jregT_joint = P.upload(md->jregT_joint, md->jregT_ptr[V]);
+    m.jregT_weight = P.upload(md->jregT_weight, md->jregT_ptr[V]);
+    m.mj_ptr = P.upload(md->mj_ptr, NMJ + 1);
+    m.mj_vert = P.upload(md->mj_vert, md->mj_ptr[NMJ]);
+    m.mj_weight = P.upload(md->mj_weight, md->mj_ptr[NMJ]);
+    m.mjT_ptr = P.upload(md->mjT_ptr, V + 1);
+    m.mjT_joint = P.upload(md->mjT_joint, md->mjT_ptr[V]);
+    m.mjT_weight = P.upload(md->mjT_weight, md->mjT_ptr[V]);
+    m.v2f_ptr = P.upload(md->v2f_ptr, V + 1);
+    m.v2f_fc = P.upload(md->v2f_fc, md->v2f_ptr[V]);
+    m.pose_mean = P.upload(md->pose_mean, NJ * 3);
+    m.pose_prec = P.upload(md->pose_prec, (size_t)NJ * 3 * NJ * 3);
+    m.pose_use = P.upload(md->pose_use, NJ * 3);
+    m.shape_dim = md->shape_dim;
+    m.shape_mean = P.upload(md->shape_mean, md->shape_dim);
+    m.shape_prec = P.upload(md->shape_prec, (size_t)md->shape_dim * md->shape_dim);
+
+    // ---- workspace ----
+    Workspace& w = h->w;
+    const size_t N = max_frames, SS = (size_t)image_size * image_size;
+    w.N = max_frames; w.S = image_size;
+    w.tiles_x = (image_size + TILE_W - 1) / TILE_W; w.tiles_y = (image_size + TILE_H - 1) / TILE_H;
+    const size_t tiles = (size_t)w.tiles_x * w.tiles_y;
+    w.n_shapes = 1;
+    const int n_blocks = (V * 3 + 255) / 256;
+    w.v_shaped = P.alloc<float>(N * V * 3);          // sized for per-frame shapes too
+    w.ndc = P.alloc<float4>(N * m.Vp);
+    h->ndc_soa = P.alloc<float>(N * 3 * m.Vp);
+    w.gjoint = P.alloc<float>(N * NMJ * 3, true);
+    w.kp_proj = P.alloc<float>(N * NKP * 2, true);
+    w.face_rect = P.alloc<uint2>(N * m.Fp);
+    w.frame_bounds = P.alloc<int4>(N);
+    w.pix = P.alloc<uint2>(N * SS, true);
+    w.pix_tfid = P.alloc<uint16_t>(N * SS, true);
+    w.tile_l1 = P.alloc<float>(N * tiles, true);
+    w.face_grad = P.alloc<float>(N * m.Fp * 8, true);
+    w.dvs = P.alloc<float>(N * V * 3, true);
+    w.gJ = P.alloc<float>(N * NJ * 3, true);
+    w.gls = P.alloc<float>(N * NLS, true);
+    w.frame_loss = P.alloc<float>(N * 4, true);
+    w.beta_partial = P.alloc<float>(N * n_blocks * NBETA, true);
+    h->sil = P.alloc<uint8_t>(N * SS, true);
+    h->kp_target = P.alloc<float>(N * NKP * 2, true);
+    h->vis = P.alloc<uint8_t>(N * NKP, true);
+    h->tile_tsum = P.alloc<float>(N * tiles, true);
+    std::vector<float> ones(N > 102 ? N : 102, 1.0f);
+    std::vector<float> invw(N, 1.0f / (float)N);
+    h->inv_window = P.upload(invw.data(), N);
+    h->gmask = P.upload(ones.data(), 3);
+    h->rmask = P.upload(ones.data(), (NJ - 1) * 3);
+    w.sil = h->sil; w.kp_target = h->kp_target; w.vis = h->vis; w.tile_tsum = h->tile_tsum;
+    w.inv_window = h->inv_window; w.gmask = h->gmask; w.rmask = h->rmask;
+    const size_t n_warps = (size_t)h->raster_ctas * RAST_WARPS;
+    w.sl_fid = P.alloc<uint16_t>(n_warps * m.Fp);
+    w.sl_mask = P.alloc<uint32_t>(n_warps * m.Fp);
+    h->sc.key = P.alloc<unsigned>(n_warps * m.Fp);
+    h->sc.m = P.alloc<float>(n_warps * m.Fp);
+    h->sc.fid = P.alloc<unsigned short>(n_warps * m.Fp);
+    h->adam_state = P.alloc<AdamState>(1, true);
+    w.work_counter = P.alloc<unsigned int>(1, true);
+    w.counters = P.alloc<unsigned long long>(4, true);
+    if (P.err != cudaSuccess) {
+        const cudaError_t pe = P.err;
+        P.release();
+        delete h;
+        return fail(nullptr, pe == cudaErrorMemoryAllocation ? SMALFIT_ENOMEM : SMALFIT_ECUDA,
+                    "smalfit_create: device allocation/upload failed: %s", cudaGetErrorString(pe));
+    }
+    e = configure_kernels(m);
+    if (e != cudaSuccess) { P.release(); delete h; return fail(nullptr, SMALFIT_ECUDA, "kernel configuration: %s", cudaGetErrorString(e)); }
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { P.release(); delete h; return fail(nullptr, SMALFIT_ECUDA, "smalfit_create: %s", cudaGetErrorString(e)); }
+    *out = h;
+    return SMALFIT_OK;
+}
+
+void smalfit_destroy(smalfit_t h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    h->pool.release();
+    delete h;
+}
+
+int smalfit_set_per_frame_shapes(smalfit_t h, int enable) {
+    if (!h) return SMALFIT_EINVAL;
+    h->w.n_shapes = enable ? h->N : 1;
+    return SMALFIT_OK;
+}
+
+int smalfit_set_targets(smalfit_t h, int frame0, int n, const uint8_t* sil, const float* joints,
+                        const uint8_t* visibility, int from_host, void* stream) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!range_ok(h, frame0, n) || !sil || !joints || !visibility) return fail(h, SMALFIT_EINVAL, "smalfit_set_targets: bad arguments");
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const cudaMemcpyKind kind = from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const size_t SS = (size_t)h->S * h->S;
+    cudaError_t e = cudaMemcpyAsync(h->sil + frame0 * SS, sil, n * SS, kind, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->kp_target + (size_t)frame0 * NKP * 2, joints, (size_t)n * NKP * 2 * sizeof(float), kind, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->vis + (size_t)frame0 * NKP, visibility, (size_t)n * NKP, kind, st);
+    if (e != cudaSuccess) return check_cuda(h, e, "smalfit_set_targets copy");
+    launch_tile_tsum(h->w, frame0, n, h->tile_tsum, st);
+    h->n_launches += 1;
+    h->targets_set = true;
+    return check_launch(h, "tile_tsum");
+}
+
+int smalfit_set_visibility(smalfit_t h, int frame0, int n, const uint8_t* visibility, int from_host, void* stream) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!range_ok(h, frame0, n) || !visibility) return fail(h, SMALFIT_EINVAL, "smalfit_set_visibility: bad arguments");
+    cudaSetDevice(h->device);
+    const cudaMemcpyKind kind = from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    return check_cuda(h, cudaMemcpyAsync(h->vis + (size_t)frame0 * NKP, visibility, (size_t)n * NKP, kind, (cudaStream_t)stream),
+                      "smalfit_set_visibility copy");
+}
+
+int smalfit_set_masks(smalfit_t h, const float* global_mask, const float* rotation_mask) {
+    if (!h || !global_mask || !rotation_mask) return SMALFIT_EINVAL;
+    cudaSetDevice(h->device);
+    cudaError_t e = cudaMemcpy(h->gmask, global_mask, 3 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->rmask, rotation_mask, (NJ - 1) * 3 * sizeof(float), cudaMemcpyHostToDevice);
+    return check_cuda(h, e, "smalfit_set_masks");
+}
+
+int smalfit_set_windows(smalfit_t h, const int32_t* fpw, int n) {
+    if (!h || !fpw || n <= 0 || n > h->N) return fail(h, SMALFIT_EINVAL, "smalfit_set_windows: bad arguments");
+    std::vector<float> inv(n);
+    for (int i = 0; i < n; ++i) {
+        if (fpw[i] <= 0) return fail(h, SMALFIT_EINVAL, "smalfit_set_windows: window size must be positive");
+        inv[i] = 1.0f / (float)fpw[i];
+    }
+    cudaSetDevice(h->device);
+    return check_cuda(h, cudaMemcpy(h->inv_window, inv.data(), n * sizeof(float), cudaMemcpyHostToDevice), "smalfit_set_windows");
+}
+
+static int run_forward(smalfit_t h, const Params& p, int frame0, int n, Weights wt, bool raster, float* alpha_out,
+                       float* verts_out, cudaStream_t st) {
+    launch_shape_forward(h->m, h->w, p, st);
+    launch_frame_forward(h->m, h->w, p, frame0, n, wt, verts_out, st);
+    h->n_launches += 2;
+    if (raster) {
+        launch_face_rects(h->m, h->w, frame0, n, st);
+        launch_raster_forward(h->m, h->w, h->sc, h->ndc_soa, frame0, n, wt, alpha_out, h->raster_ctas, st);
+        h->n_launches += 3;
+        h->n_raster_launches += 1;
+    }
+    return check_launch(h, "forward kernels");
+}
+
+int smalfit_loss_grad(smalfit_t h, const smalfit_tensors_t* params, int frame0, int n, const float weights[6],
+                      int prior_windows, const smalfit_tensors_t* grads, float* loss_terms, void* stream) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!params || !weights || !range_ok(h, frame0, n)) return fail(h, SMALFIT_EINVAL, "smalfit_loss_grad: bad arguments");
+    if (!params->betas || !params->log_beta_scales || !params->global_rotation || !params->joint_rotations || !params->trans)
+        return fail(h, SMALFIT_EINVAL, "smalfit_loss_grad: NULL parameter tensor");
+    if (!h->targets_set) return fail(h, SMALFIT_ESTATE, "smalfit_loss_grad: call smalfit_set_targets first");
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Weights wt{weights[0], weights[1], weights[2], weights[3], weights[4], weights[5]};
+    const Params p = to_params(params);
+    const Grads g = to_grads(grads);
+    const bool raster = wt.sil > 0.f;
+    int rc = run_forward(h, p, frame0, n, wt, raster, nullptr, nullptr, st);
+    if (rc) return rc;
+    if (raster) { launch_raster_backward(h->m, h->w, frame0, n, st); h->n_launches += 1; h->n_raster_launches += 1; }
+    launch_frame_backward(h->m, h->w, p, g, frame0, n, wt, st);
+    launch_shape_backward(h->m, h->w, p, g, frame0, n, wt, prior_windows < 0 ? 0 : prior_windows, loss_terms, st);
+    h->n_launches += 3;
+    return check_launch(h, "backward kernels");
+}
+
+int smalfit_temporal(smalfit_t h, const smalfit_tensors_t* params, int n_frames, float w_temp,
+                     const smalfit_tensors_t* grads, float* terms, void* stream) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!params || n_frames <= 0 || n_frames > h->N) return fail(h, SMALFIT_EINVAL, "smalfit_temporal: bad arguments");
+    cudaSetDevice(h->device);
+    launch_temporal(h->w, to_params(params), to_grads(grads), n_frames, w_temp, terms, (cudaStream_t)stream);
+    h->n_launches += 1;
+    return check_launch(h, "temporal kernel");
+}
+
+int smalfit_adam_step(smalfit_t h, const smalfit_tensors_t* params, const smalfit_tensors_t* grads,
+                      const smalfit_tensors_t* exp_avg, const smalfit_tensors_t* exp_avg_sq, int n_frames,
+                      const int32_t train[5], float lr, float beta1, float beta2, float eps, int step, void* stream) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !train || step < 0 || n_frames <= 0 || n_frames > h->N)
+        return fail(h, SMALFIT_EINVAL, "smalfit_adam_step: bad arguments");
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ns = h->w.n_shapes;
+    float* P5[5] = {params->betas, params->log_beta_scales, params->global_rotation, params->joint_rotations, params->trans};
+    float* G5[5] = {grads->betas, grads->log_beta_scales, grads->global_rotation, grads->joint_rotations, grads->trans};
+    float* M5[5] = {exp_avg->betas, exp_avg->log_beta_scales, exp_avg->global_rotation, exp_avg->joint_rotations, exp_avg->trans};
+    float* V5[5] = {exp_avg_sq->betas, exp_avg_sq->log_beta_scales, exp_avg_sq->global_rotation, exp_avg_sq->joint_rotations, exp_avg_sq->trans};
+    const int len[5] = {ns * NBETA, ns * NLS, n_frames * 3, n_frames * (NJ - 1) * 3, n_frames * 3};
+    launch_adam_tick(h->adam_state, beta1, beta2, step, st);
+    h->n_launches += 1;
+    for (int i = 0; i < 5; ++i) {
+        if (!train[i]) continue;
+        if (!P5[i] || !G5[i] || !M5[i] || !V5[i]) return fail(h, SMALFIT_EINVAL, "smalfit_adam_step: NULL tensor %d", i);
+        launch_adam(P5[i], G5[i], M5[i], V5[i], len[i], lr, beta1, beta2, eps, h->adam_state, st);
+        h->n_launches += 1;
+    }
+    return check_launch(h, "adam kernel");
+}
+
+int smalfit_adam_reset(smalfit_t h, void* stream) {
+    if (!h) return SMALFIT_EINVAL;
+    cudaSetDevice(h->device);
+    return check_cuda(h, cudaMemsetAsync(h->adam_state, 0, sizeof(AdamState), (cudaStream_t)stream), "smalfit_adam_reset");
+}
+
+int smalfit_render(smalfit_t h, const smalfit_tensors_t* params, int frame0, int n, float* silhouettes,
+                   float* keypoints, void* stream) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!params || !range_ok(h, frame0, n)) return fail(h, SMALFIT_EINVAL, "smalfit_render: bad arguments");
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Weights wt{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int rc = run_forward(h, to_params(params), frame0, n, wt, silhouettes != nullptr, silhouettes, nullptr, st);
+    if (rc) return rc;
+    if (keypoints)
+        rc = check_cuda(h, cudaMemcpyAsync(keypoints, h->w.kp_proj + (size_t)frame0 * NKP * 2, (size_t)n * NKP * 2 * sizeof(float),
+                                           cudaMemcpyDeviceToDevice, st), "smalfit_render keypoints");
+    return rc;
+}
+
+int smalfit_vertices(smalfit_t h, const smalfit_tensors_t* params, int frame0, int n, float* verts, void* stream) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!params || !verts || !range_ok(h, frame0, n)) return fail(h, SMALFIT_EINVAL, "smalfit_vertices: bad arguments");
+    cudaSetDevice(h->device);
+    const Weights wt{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    return run_forward(h, to_params(params), frame0, n, wt, false, nullptr, verts, (cudaStream_t)stream);
+}
+
+int smalfit_counters(smalfit_t h, int64_t counters[4], void* stream) {
+    if (!h || !counters) return SMALFIT_EINVAL;
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long host[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(host, h->w.counters, sizeof(host), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->w.counters, 0, 2 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return check_cuda(h, e, "smalfit_counters");
+    counters[0] = (int64_t)host[0]; counters[1] = (int64_t)host[1];
+    counters[2] = h->n_raster_launches; counters[3] = h->n_launches;
+    return SMALFIT_OK;
+}
+
+}  // extern "C"

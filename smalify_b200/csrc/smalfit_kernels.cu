@@ -1,0 +1,1028 @@
+// smalfit_kernels.cu -- sm_100a kernels of the SMAL fitting hot path.
+//
+// One optimisation step over a window of frames is this kernel sequence
+// (all on one stream, no host synchronisation, no allocation):
+//
+//   shape_forward      v_shaped = v_template + betas . shapedirs              (smal_torch.py:115)
+//   frame_forward      per frame: rest joints, Rodrigues, kinematic chain, sparse LBS,
+//                      camera, 41 model joints, keypoint projection + loss     (smal_torch.py:125-184,
+//                      and dL/d(joints)                                         smal_fitter.py:129-144)
+//   face_rects         per face: validity + conservative pixel rectangle
+//   raster_forward     soft silhouette (PyTorch3D 0.2.5 semantics, exact K=100 nearest-z
+//                      rule) fused with the L1 silhouette loss                 (p3d_renderer.py:26-39,66;
+//                      writes per pixel (coef, z-threshold) for the backward    smal_fitter.py:172-173)
+//   raster_backward    face-parallel analytic backward -> per-face xy gradients (RasterizeMeshesBackward)
+//   frame_backward     per frame: face->vertex gather, camera^T, LBS^T, chain^T, Rodrigues^T,
+//                      pose prior + splay (value and gradient)                 (smal_fitter.py:153-160)
+//   shape_backward     cross-frame reduction -> dL/dbetas, dL/dlog_beta_scales, shape prior,
+//                      loss_terms[8]                                            (smal_fitter.py:162-175)
+//   temporal / adam    get_temporal + Adam                                      (smal_fitter.py:177-190,
+//                                                                               optimize_to_joints.py:96,137)
+#include "smalfit_kernels.cuh"
+
+namespace smf {
+
+__constant__ SkeletonConst c_sk;
+
+void upload_skeleton(const SkeletonConst& sk) { cudaMemcpyToSymbol(c_sk, &sk, sizeof(SkeletonConst)); }
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_prod(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+// block sum of one float per thread (blockDim.x multiple of 32, <= 1024); result valid in all threads
+__device__ float block_sum(float v, float* red /* >= 33 floats */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        float t = (lane < nw) ? red[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// ---------------------------------------------------------------------------
+// shape_forward: v_shaped[slot][i] = v_template[i] + sum_k betas[slot][k] shapedirs[k][i]
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) shape_forward_kernel(ModelDev m, Workspace w, Params p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = blockIdx.y;
+    __shared__ float sb[NBETA];
+    if (threadIdx.x < NBETA) sb[threadIdx.x] = p.betas[slot * NBETA + threadIdx.x];
+    __syncthreads();
+    const int n = m.V * 3;
+    if (i >= n) return;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < NBETA; ++k) acc = fmaf(sb[k], m.shapedirs[(size_t)k * n + i], acc);
+    w.v_shaped[(size_t)slot * n + i] = m.v_template[i] + acc;
+}
+
+void launch_shape_forward(const ModelDev& m, const Workspace& w, const Params& p, cudaStream_t st) {
+    dim3 grid((m.V * 3 + 255) / 256, w.n_shapes);
+    shape_forward_kernel<<<grid, 256, 0, st>>>(m, w, p);
+}
+
+// ---------------------------------------------------------------------------
+// shared-memory layout of the per-frame kernels
+// ---------------------------------------------------------------------------
+struct FrameSmem {
+    float R[NJ * 9], Rw[NJ * 9], s[NJ * 3], t[NJ * 3], J[NJ * 3], G[NJ * 9], off[NJ * 3];
+    float theta[NJ * 3], ls[NLS], tr[3];
+    float mj[NMJ * 3];      // model joints (world, with trans)
+    float gj[NMJ * 3];      // dL/d(model joints)
+    float gkp[NKP * 3];
+    float red[40];
+    // backward only
+    float Gb[NJ * 9], offb[NJ * 3], tb[NJ * 3], Rwb[NJ * 9], sb[NJ * 3], Jb[NJ * 3], Rb[NJ * 9];
+    float thg[NJ * 3], res[NJ * 3];
+};
+
+__device__ __forceinline__ ChainFwd chain_of(FrameSmem& S) {
+    ChainFwd c;
+    c.R = S.R; c.Rw = S.Rw; c.s = S.s; c.t = S.t; c.J = S.J; c.G = S.G; c.off = S.off;
+    return c;
+}
+
+// Loads the frame's parameters and runs rest-joint regression, Rodrigues and the chain.
+// Ends with a __syncthreads(); afterwards S.G / S.off hold the skinning transforms.
+__device__ void frame_pose_forward(FrameSmem& S, const ModelDev& m, const Workspace& w, const Params& p,
+                                   int fr, int slot) {
+    const int tid = threadIdx.x;
+    const float* vs = w.v_shaped + (size_t)slot * m.V * 3;
+    if (tid < NJ * 3) {
+        S.theta[tid] = (tid < 3) ? p.glob[fr * 3 + tid] * w.gmask[tid]
+                                 : p.joint[(size_t)fr * (NJ - 1) * 3 + (tid - 3)] * w.rmask[tid - 3];
+        const int j = tid / 3, c = tid - j * 3;
+        float acc = 0.f;
+        for (int e = m.jreg_ptr[j]; e < m.jreg_ptr[j + 1]; ++e) acc = fmaf(m.jreg_weight[e], vs[m.jreg_vert[e] * 3 + c], acc);
+        S.J[tid] = acc;
+    }
+    if (tid < NLS) S.ls[tid] = p.logscale[slot * NLS + tid];
+    if (tid < 3) S.tr[tid] = p.trans[fr * 3 + tid];
+    __syncthreads();
+    if (tid < NJ) {
+        rodrigues_fwd(S.theta + 3 * tid, S.R + 9 * tid);
+        chain_scale(tid, S.ls, c_sk.scale_axis, S.s);
+    }
+    __syncthreads();
+    ChainFwd c = chain_of(S);
+    for (int lev = 0; lev < c_sk.n_levels; ++lev) {
+        const int a = c_sk.level_start[lev], b = c_sk.level_start[lev + 1];
+        if (tid < b - a) {
+            const int i = c_sk.joint_order[a + tid];
+            chain_fwd_joint(c, i, c_sk.parents[i]);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// frame_forward
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(FRAME_THREADS)
+frame_forward_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, float* verts_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FrameSmem& S = *reinterpret_cast<FrameSmem*>(smem_raw);
+    float* vw = reinterpret_cast<float*>(smem_raw + sizeof(FrameSmem));     // [V*3] world verts, no trans
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int fr = frame0 + blockIdx.x;
+    const int slot = (w.n_shapes == 1) ? 0 : fr;
+    const float* vs = w.v_shaped + (size_t)slot * m.V * 3;
+
+    if (tid == 0) w.frame_bounds[fr] = make_int4(1 << 30, -1, 1 << 30, -1);
+    frame_pose_forward(S, m, w, p, fr, slot);
+
+    // sparse linear-blend skinning + camera
+    float4* ndc = w.ndc + (size_t)fr * m.Vp;
+    for (int v = tid; v < m.V; v += FRAME_THREADS) {
+        const float x = vs[v * 3 + 0], y = vs[v * 3 + 1], z = vs[v * 3 + 2];
+        float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXINF; ++k) {
+            const float wk = m.skin_weight[v * MAXINF + k];
+            if (wk != 0.f) {
+                const int j = m.skin_joint[v * MAXINF + k];
+                const float* G = S.G + j * 9;
+                const float* o = S.off + j * 3;
+                ax = fmaf(wk, G[0] * x + G[1] * y + G[2] * z + o[0], ax);
+                ay = fmaf(wk, G[3] * x + G[4] * y + G[5] * z + o[1], ay);
+                az = fmaf(wk, G[6] * x + G[7] * y + G[8] * z + o[2], az);
+            }
+        }
+        vw[v * 3 + 0] = ax; vw[v * 3 + 1] = ay; vw[v * 3 + 2] = az;
+        const float X = ax + S.tr[0], Y = ay + S.tr[1], Z = az + S.tr[2];
+        float xn, yn, zv;
+        camera_fwd(X, Y, Z, xn, yn, zv);
+        ndc[v] = make_float4(xn, yn, zv, 0.f);
+        if (verts_out) {
+            float* o = verts_out + ((size_t)blockIdx.x * m.V + v) * 3;
+            o[0] = X; o[1] = Y; o[2] = Z;
+        }
+    }
+    for (int v = m.V + tid; v < m.Vp; v += FRAME_THREADS) ndc[v] = make_float4(0.f, 0.f, -1.f, 0.f);
+    __syncthreads();
+
+    // 41 model joints: regressed from the posed vertices (+ trans), smal_torch.py:171-184
+    for (int j = wid; j < NMJ; j += FRAME_THREADS / 32) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int e = m.mj_ptr[j] + lane; e < m.mj_ptr[j + 1]; e += 32) {
+            const float wk = m.mj_weight[e];
+            const int v = m.mj_vert[e];
+            a0 = fmaf(wk, vw[v * 3 + 0], a0); a1 = fmaf(wk, vw[v * 3 + 1], a1); a2 = fmaf(wk, vw[v * 3 + 2], a2);
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+        if (lane == 0) { S.mj[j * 3 + 0] = a0 + S.tr[0]; S.mj[j * 3 + 1] = a1 + S.tr[1]; S.mj[j * 3 + 2] = a2 + S.tr[2]; }
+    }
+    __syncthreads();
+
+    // keypoint projection + masked MSE (smal_fitter.py:140-144) and its gradient
+    float lk = 0.f;
+    if (tid < NKP) {
+        const int j = c_sk.kp_joint[tid];
+        float xn, yn, zv, row, col;
+        camera_fwd(S.mj[j * 3 + 0], S.mj[j * 3 + 1], S.mj[j * 3 + 2], xn, yn, zv);
+        const float half = 0.5f * (float)(w.S - 1);
+        screen_fwd(xn, yn, half, row, col);
+        w.kp_proj[(size_t)fr * NKP * 2 + tid * 2 + 0] = row;
+        w.kp_proj[(size_t)fr * NKP * 2 + tid * 2 + 1] = col;
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        if (wt.j2d > 0.f && w.vis[(size_t)fr * NKP + tid] != 0) {
+            const float dr = row - w.kp_target[(size_t)fr * NKP * 2 + tid * 2 + 0];
+            const float dc = col - w.kp_target[(size_t)fr * NKP * 2 + tid * 2 + 1];
+            const float scale = wt.j2d * w.inv_window[fr] * (1.f / (float)(NKP * 2));
+            lk = scale * (dr * dr + dc * dc);
+            const float gyn = -half * 2.f * scale * dr, gxn = -half * 2.f * scale * dc;
+            camera_bwd(xn, yn, zv, gxn, gyn, g0, g1, g2);
+        }
+        S.gkp[tid * 3 + 0] = g0; S.gkp[tid * 3 + 1] = g1; S.gkp[tid * 3 + 2] = g2;
+    }
+    const float lsum = block_sum(lk, S.red);
+    if (tid < NMJ) {
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        for (int k = 0; k < NKP; ++k)
+            if (c_sk.kp_joint[k] == tid) { g0 += S.gkp[k * 3]; g1 += S.gkp[k * 3 + 1]; g2 += S.gkp[k * 3 + 2]; }
+        float* gj = w.gjoint + (size_t)fr * NMJ * 3 + tid * 3;
+        gj[0] = g0; gj[1] = g1; gj[2] = g2;
+    }
+    if (tid == 0) w.frame_loss[fr * 4 + 0] = lsum;
+}
+
+void launch_frame_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n,
+                          Weights wt, float* verts_out, cudaStream_t st) {
+    const size_t smem = sizeof(FrameSmem) + (size_t)m.V * 3 * sizeof(float);
+    frame_forward_kernel<<<n, FRAME_THREADS, smem, st>>>(m, w, p, frame0, wt, verts_out);
+}
+
+// ---------------------------------------------------------------------------
+// face_rects: per (frame, face) pixel rectangle of the blur-expanded bbox
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ FaceSetup load_face(const float4* ndc, ushort4 f4) {
+    const float4 a = ndc[f4.x], b = ndc[f4.y], c = ndc[f4.z];
+    FaceSetup fs = face_setup(a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z);
+    if (f4.w == 0) fs.valid = 0.f;
+    return fs;
+}
+
+__global__ void __launch_bounds__(256) face_rect_kernel(ModelDev m, Workspace w, int frame0) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int fr = frame0 + blockIdx.y;
+    int c0 = 0xFFFF, c1 = 0, r0 = 0xFFFF, r1 = 0;
+    bool ok = false;
+    if (f < m.Fp) {
+        const FaceSetup fs = load_face(w.ndc + (size_t)fr * m.Vp, m.faces4[f]);
+        int a, b, c, d;
+        ok = face_pixel_rect(fs, w.S, a, b, c, d);
+        if (ok) { c0 = a; c1 = b; r0 = c; r1 = d; }
+        w.face_rect[(size_t)fr * m.Fp + f] = make_uint2((unsigned)c0 | ((unsigned)c1 << 16), (unsigned)r0 | ((unsigned)r1 << 16));
+    }
+    // frame bounds: warp-reduce then one atomic per warp
+    int mc0 = ok ? c0 : (1 << 30), mc1 = ok ? c1 : -1, mr0 = ok ? r0 : (1 << 30), mr1 = ok ? r1 : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mc0 = min(mc0, __shfl_xor_sync(0xffffffffu, mc0, o));
+        mc1 = max(mc1, __shfl_xor_sync(0xffffffffu, mc1, o));
+        mr0 = min(mr0, __shfl_xor_sync(0xffffffffu, mr0, o));
+        mr1 = max(mr1, __shfl_xor_sync(0xffffffffu, mr1, o));
+    }
+    if ((threadIdx.x & 31) == 0 && mc1 >= 0) {
+        int* fb = reinterpret_cast<int*>(w.frame_bounds + fr);
+        atomicMin(fb + 0, mc0); atomicMax(fb + 1, mc1); atomicMin(fb + 2, mr0); atomicMax(fb + 3, mr1);
+    }
+}
+
+void launch_face_rects(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st) {
+    dim3 grid((m.Fp + 255) / 256, n);
+    face_rect_kernel<<<grid, 256, 0, st>>>(m, w, frame0);
+}
+
+// ---------------------------------------------------------------------------
+// TMA (1-D bulk copy) + mbarrier helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    for (int it = 0; it < (1 << 24); ++it)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();      // a lost TMA would otherwise hang the GPU
+}
+
+// ---------------------------------------------------------------------------
+// raster_forward
+//
+// Persistent CTAs (8 warps) pull (frame, 16x16 tile) items.  The frame's NDC vertices
+// (x[], y[], z[] as three 15.6 KB arrays) are staged into shared memory with one TMA
+// bulk copy per array and reused for consecutive tiles of the same frame.  Each warp
+// owns an 8x4 pixel region of the tile:
+//   A. scan all face rectangles (coalesced), keep the faces touching the region together
+//      with the 32-bit mask of region pixels inside their rectangle  -> sub-list
+//   B. for each of the 32 pixels: compact the sub-list faces whose bit is set into a
+//      queue; every 32 queued faces are evaluated one per lane (vertices gathered from
+//      shared memory); fragments are appended to the warp's (key, m, face) buffer
+//   C. n <= K: product of all m.  n > K: exact K-th order statistic of (pz, face id) by
+//      warp-cooperative bisection on the key bits, product over the selected set
+//   D. lane q finishes pixel q: alpha, L1 term, coef = dL/dalpha * P / sigma, threshold
+// ---------------------------------------------------------------------------
+struct RasterWarpSmem {
+    unsigned key[KCAP];
+    float mval[KCAP];
+    unsigned short fid[KCAP];
+    unsigned short queue[64];
+};
+
+struct KeyStore {           // fragment buffer: shared memory first, global spill beyond KCAP
+    RasterWarpSmem* s;
+    unsigned* gkey; float* gm; unsigned short* gfid;
+    __device__ __forceinline__ void put(int i, unsigned k, float mv, unsigned short f) const {
+        if (i < KCAP) { s->key[i] = k; s->mval[i] = mv; s->fid[i] = f; }
+        else { gkey[i - KCAP] = k; gm[i - KCAP] = mv; gfid[i - KCAP] = f; }
+    }
+    __device__ __forceinline__ unsigned key(int i) const { return i < KCAP ? s->key[i] : gkey[i - KCAP]; }
+    __device__ __forceinline__ float m(int i) const { return i < KCAP ? s->mval[i] : gm[i - KCAP]; }
+    __device__ __forceinline__ unsigned short f(int i) const { return i < KCAP ? s->fid[i] : gfid[i - KCAP]; }
+};
+
+__device__ __forceinline__ int warp_count_le(const KeyStore& ks, int n, unsigned t, int lane) {
+    int c = 0;
+    for (int i = lane; i < n; i += 32) c += (ks.key(i) <= t) ? 1 : 0;
+    return __reduce_add_sync(0xffffffffu, c);
+}
+
+// Exact K nearest by (key, face id).  Returns the product of m over the selected set and the
+// threshold (tkey, tfid): selected <=> key < tkey || (key == tkey && fid <= tfid).
+__device__ float select_k_nearest(const KeyStore& ks, int n, int lane, unsigned& tkey, unsigned& tfid) {
+    unsigned lo = 0xffffffffu, hi = 0u;
+    for (int i = lane; i < n; i += 32) { const unsigned k = ks.key(i); lo = min(lo, k); hi = max(hi, k); }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    // smallest t with count(key <= t) >= K; stop early when a split of exactly K is found
+    bool exact = false;
+    unsigned t = hi;
+    while (lo < hi) {
+        const unsigned mid = lo + ((hi - lo) >> 1);
+        const int c = warp_count_le(ks, n, mid, lane);
+        if (c == RAST_K) { t = mid; exact = true; break; }
+        if (c > RAST_K) hi = mid; else lo = mid + 1;
+    }
+    unsigned tf = 0xffffu;
+    if (!exact) {
+        t = lo;
+        int clt = 0, cle = 0;
+        for (int i = lane; i < n; i += 32) { const unsigned k = ks.key(i); clt += (k < t); cle += (k <= t); }
+        clt = __reduce_add_sync(0xffffffffu, clt);
+        cle = __reduce_add_sync(0xffffffffu, cle);
+        if (cle > RAST_K) {
+            // ties on pz at the cut: keep the (K - clt) lowest face ids among key == t
+            const int need = RAST_K - clt;
+            unsigned flo = 0u, fhi = 0xffffu;
+            while (flo < fhi) {
+                const unsigned mid = flo + ((fhi - flo) >> 1);
+                int c = 0;
+                for (int i = lane; i < n; i += 32) c += (ks.key(i) == t && ks.f(i) <= mid) ? 1 : 0;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c >= need) fhi = mid; else flo = mid + 1;
+            }
+            tf = flo;
+        }
+    }
+    float prod = 1.f;
+    for (int i = lane; i < n; i += 32) {
+        const unsigned k = ks.key(i);
+        if (k < t || (k == t && (unsigned)ks.f(i) <= tf)) prod *= ks.m(i);
+    }
+    tkey = t; tfid = tf;
+    return warp_prod(prod);
+}
+
+__global__ void __launch_bounds__(RAST_THREADS, 2)
+raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int n_frames, Weights wt,
+                      const float* ndc_soa /* [N][3][Vp] */, float* alpha_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* vx = reinterpret_cast<float*>(smem_raw);
+    float* vy = vx + m.Vp;
+    float* vz = vy + m.Vp;
+    RasterWarpSmem* wsm_all = reinterpret_cast<RasterWarpSmem*>(vz + m.Vp);
+    __shared__ unsigned long long bar;
+    __shared__ unsigned s_item;
+    __shared__ float s_l1[RAST_WARPS];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    RasterWarpSmem& wsm = wsm_all[wid];
+    const int gwarp = blockIdx.x * RAST_WARPS + wid;
+    unsigned short* sl_fid = w.sl_fid + (size_t)gwarp * m.Fp;
+    unsigned* sl_mask = w.sl_mask + (size_t)gwarp * m.Fp;
+    KeyStore ks;
+    ks.s = &wsm;
+    ks.gkey = sc.key + (size_t)gwarp * m.Fp; ks.gm = sc.m + (size_t)gwarp * m.Fp; ks.gfid = sc.fid + (size_t)gwarp * m.Fp;
+
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    unsigned parity = 0;
+    int cached_frame = -1;
+
+    const int S = w.S;
+    const float inv_s = 1.f / (float)S;
+    const int tiles = w.tiles_x * w.tiles_y;
+    const int n_items = n_frames * tiles;
+    const unsigned ltmask = lanemask_lt();
+    unsigned long long n_capped = 0, n_spilled = 0;
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(w.work_counter, 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= (unsigned)n_items) break;
+        const int fr = frame0 + (int)(item / tiles);
+        const int tile = (int)(item % tiles);
+        const int tx = tile % w.tiles_x, ty = tile / w.tiles_x;
+        const int4 fb = w.frame_bounds[fr];
+        const int tx0 = tx * TILE_W, ty0 = ty * TILE_H;
+        const bool tile_empty = (fb.y < tx0) || (fb.x > tx0 + TILE_W - 1) || (fb.w < ty0) || (fb.z > ty0 + TILE_H - 1);
+        if (tile_empty) {
+            // no face touches the tile: alpha = 0 everywhere, |alpha - T| = T
+            if (tid == 0) w.tile_l1[(size_t)fr * tiles + tile] = w.tile_tsum[(size_t)fr * tiles + tile];
+            if (alpha_out) {
+                const int x = tx0 + (tid & 15), y = ty0 + (tid >> 4);
+                if (x < S && y < S) alpha_out[((size_t)(fr - frame0) * S + y) * S + x] = 0.f;
+            }
+            __syncthreads();      // s_item is rewritten next iteration
+            continue;
+        }
+        if (fr != cached_frame) {
+            // all warps are past the previous frame's vertices (barrier above)
+            if (tid == 0) {
+                const unsigned bytes = (unsigned)(m.Vp * sizeof(float));
+                const float* src = ndc_soa + (size_t)fr * 3 * m.Vp;
+                mbar_expect_tx(&bar, 3 * bytes);
+                tma_load_1d(vx, src, bytes, &bar);
+                tma_load_1d(vy, src + m.Vp, bytes, &bar);
+                tma_load_1d(vz, src + 2 * m.Vp, bytes, &bar);
+            }
+            mbar_wait(&bar, parity);
+            parity ^= 1u;
+            cached_frame = fr;
+        }
+
+        // ---- this warp's 8x4 region ------------------------------------------------
+        const int x0 = tx0 + (wid & 1) * REGION_W, y0 = ty0 + (wid >> 1) * REGION_H;
+        const uint2* rects = w.face_rect + (size_t)fr * m.Fp;
+        int L = 0;
+        for (int base = 0; base < m.Fp; base += 32) {
+            const uint2 r = rects[base + lane];
+            const int c0 = (int)(r.x & 0xffffu), c1 = (int)(r.x >> 16), r0 = (int)(r.y & 0xffffu), r1 = (int)(r.y >> 16);
+            const bool ov = (c0 <= x0 + REGION_W - 1) && (c1 >= x0) && (r0 <= y0 + REGION_H - 1) && (r1 >= y0);
+            const unsigned bal = __ballot_sync(0xffffffffu, ov);
+            if (ov) {
+                const int a = max(c0 - x0, 0), b = min(c1 - x0, REGION_W - 1);
+                const unsigned cm = ((1u << (b + 1)) - 1u) & ~((1u << a) - 1u);       // 8-bit column mask
+                const int ra = max(r0 - y0, 0), rb = min(r1 - y0, REGION_H - 1);
+                unsigned mk = 0u;
+                for (int rr = ra; rr <= rb; ++rr) mk |= cm << (8 * rr);
+                const int pos = L + __popc(bal & ltmask);
+                sl_fid[pos] = (unsigned short)(base + lane);
+                sl_mask[pos] = mk;
+            }
+            L += __popc(bal);
+        }
+        __syncwarp();
+
+        float myP = 1.f;
+        unsigned myTkey = 0xffffffffu, myTfid = 0xffffu;
+        int myN = 0;
+        if (L > 0) {
+            for (int q = 0; q < 32; ++q) {
+                const float px = pix_to_ndc(x0 + (q & 7), inv_s), py = pix_to_ndc(y0 + (q >> 3), inv_s);
+                int n = 0, qhead = 0, qn = 0;
+                for (int base = 0; base < L || qn > 0; base += 32) {
+                    if (base < L) {
+                        const int idx = base + lane;
+                        const bool pass = (idx < L) && ((sl_mask[idx] >> q) & 1u);
+                        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                        if (pass) wsm.queue[(qhead + qn + __popc(bal & ltmask)) & 63] = sl_fid[idx];
+                        qn += __popc(bal);
+                        __syncwarp();
+                    }
+                    if (qn >= 32 || (base + 32 >= L && qn > 0)) {
+                        const int cnt = min(qn, 32);
+                        bool valid = false;
+                        unsigned key = 0u; float mv = 1.f; unsigned short fidx = 0;
+                        if (lane < cnt) {
+                            fidx = wsm.queue[(qhead + lane) & 63];
+                            const ushort4 f4 = m.faces4[fidx];
+                            const FaceSetup fs = face_setup(vx[f4.x], vy[f4.x], vz[f4.x], vx[f4.y], vy[f4.y], vz[f4.y],
+                                                            vx[f4.z], vy[f4.z], vz[f4.z]);
+                            Fragment frag;
+                            valid = (f4.w != 0) && face_eval(fs, px, py, frag);
+                            if (valid) {
+                                float pp;
+                                frag_prob(frag.sd, pp, mv);
+                                key = __float_as_uint(frag.pz + 0.f);
+                            }
+                        }
+                        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+                        if (valid) ks.put(n + __popc(bal & ltmask), key, mv, fidx);
+                        n += __popc(bal);
+                        qhead = (qhead + cnt) & 63;
+                        qn -= cnt;
+                        __syncwarp();
+                    }
+                }
+                float P = 1.f;
+                unsigned tk = 0xffffffffu, tf = 0xffffu;
+                if (n > RAST_K) {
+                    P = select_k_nearest(ks, n, lane, tk, tf);
+                    if (lane == 0) { ++n_capped; if (n > KCAP) ++n_spilled; }
+                } else if (n > 0) {
+                    float pr = 1.f;
+                    for (int i = lane; i < n; i += 32) pr *= wsm.mval[i];
+                    P = warp_prod(pr);
+                }
+                if (lane == q) { myP = P; myTkey = tk; myTfid = tf; myN = n; }
+                __syncwarp();
+            }
+        }
+
+        // ---- epilogue: lane = pixel -------------------------------------------------
+        {
+            const int x = x0 + (lane & 7), y = y0 + (lane >> 3);
+            float l1 = 0.f;
+            if (x < S && y < S) {
+                const size_t pi = ((size_t)fr * S + y) * S + x;
+                const float alpha = 1.f - myP;
+                const float T = (float)w.sil[pi];
+                const float d = alpha - T;
+                l1 = fabsf(d);
+                float coef = 0.f;
+                if (myN > 0 && myP >= P_SKIP && d != 0.f) {
+                    const float ga = wt.sil * w.inv_window[fr] * inv_s * inv_s * (d > 0.f ? 1.f : -1.f);
+                    coef = ga * myP * (1.f / RAST_SIGMA);
+                }
+                w.pix[pi] = make_uint2(__float_as_uint(coef), myTkey);
+                if (myTkey != 0xffffffffu) w.pix_tfid[pi] = (unsigned short)myTfid;
+                if (alpha_out) alpha_out[((size_t)(fr - frame0) * S + y) * S + x] = alpha;
+            }
+            l1 = warp_sum(l1);
+            if (lane == 0) s_l1[wid] = l1;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int i = 0; i < RAST_WARPS; ++i) t += s_l1[i];
+            w.tile_l1[(size_t)fr * tiles + tile] = t;
+        }
+    }
+    if (lane == 0 && (n_capped | n_spilled)) {
+        atomicAdd(w.counters + 0, n_capped);
+        atomicAdd(w.counters + 1, n_spilled);
+    }
+}
+
+size_t raster_smem_bytes(const ModelDev& m) {
+    return (size_t)3 * m.Vp * sizeof(float) + (size_t)RAST_WARPS * sizeof(RasterWarpSmem);
+}
+
+// SoA copy of the NDC vertices for the TMA loads (x[], y[], z[] per frame)
+__global__ void __launch_bounds__(256) ndc_soa_kernel(ModelDev m, Workspace w, int frame0, float* soa) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int fr = frame0 + blockIdx.y;
+    if (v >= m.Vp) return;
+    const float4 a = w.ndc[(size_t)fr * m.Vp + v];
+    float* o = soa + (size_t)fr * 3 * m.Vp;
+    o[v] = a.x; o[m.Vp + v] = a.y; o[2 * m.Vp + v] = a.z;
+}
+
+void launch_raster_forward(const ModelDev& m, const Workspace& w, const RasterScratch& sc, float* ndc_soa,
+                              int frame0, int n, Weights wt, float* alpha_out, int n_ctas, cudaStream_t st) {
+    dim3 g((m.Vp + 255) / 256, n);
+    ndc_soa_kernel<<<g, 256, 0, st>>>(m, w, frame0, ndc_soa);
+    cudaMemsetAsync(w.work_counter, 0, sizeof(unsigned), st);
+    raster_forward_kernel<<<n_ctas, RAST_THREADS, raster_smem_bytes(m), st>>>(m, w, sc, frame0, n, wt, ndc_soa, alpha_out);
+}
+
+// ---------------------------------------------------------------------------
+// raster_backward: one warp per (frame, face); lanes sweep the face's pixel rectangle
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) raster_backward_kernel(ModelDev m, Workspace w, int frame0) {
+    const int lane = threadIdx.x & 31;
+    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int fr = frame0 + blockIdx.y;
+    if (f >= m.Fp) return;
+    const FaceSetup fs = load_face(w.ndc + (size_t)fr * m.Vp, m.faces4[f]);
+    float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int c0, c1, r0, r1;
+    if (face_pixel_rect(fs, w.S, c0, c1, r0, r1)) {
+        const int S = w.S;
+        const float inv_s = 1.f / (float)S;
+        const int wd = c1 - c0 + 1, npx = wd * (r1 - r0 + 1);
+        const float inv_w = 1.f / (float)wd;
+        const uint2* pix = w.pix + (size_t)fr * S * S;
+        for (int i = lane; i < npx; i += 32) {
+            const int rr = (int)(((float)i + 0.5f) * inv_w);
+            const int cc = i - rr * wd;
+            const int x = c0 + cc, y = r0 + rr;
+            const uint2 pr = pix[(size_t)y * S + x];
+            const float coef = __uint_as_float(pr.x);
+            if (coef == 0.f) continue;
+            Fragment frag;
+            if (!face_eval(fs, pix_to_ndc(x, inv_s), pix_to_ndc(y, inv_s), frag)) continue;
+            const unsigned key = __float_as_uint(frag.pz + 0.f);
+            if (key > pr.y) continue;
+            if (key == pr.y && (unsigned)f > (unsigned)w.pix_tfid[((size_t)fr * S + y) * S + x]) continue;
+            float p, mv;
+            frag_prob(frag.sd, p, mv);
+            frag_grad(frag, -coef * p, g);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g[k] = warp_sum(g[k]);
+    }
+    if (lane == 0) {
+        float4* o = reinterpret_cast<float4*>(w.face_grad + ((size_t)fr * m.Fp + f) * 8);
+        o[0] = make_float4(g[0], g[1], g[2], g[3]);
+        o[1] = make_float4(g[4], g[5], 0.f, 0.f);
+    }
+}
+
+void launch_raster_backward(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st) {
+    dim3 grid((m.Fp + 7) / 8, n);
+    raster_backward_kernel<<<grid, 256, 0, st>>>(m, w, frame0);
+}
+
+// ---------------------------------------------------------------------------
+// frame_backward
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(FRAME_THREADS)
+frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, Weights wt) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FrameSmem& S = *reinterpret_cast<FrameSmem*>(smem_raw);
+    float* gw = reinterpret_cast<float*>(smem_raw + sizeof(FrameSmem));     // [V*3] dL/d(world verts)
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int fr = frame0 + blockIdx.x;
+    const int slot = (w.n_shapes == 1) ? 0 : fr;
+    const float* vs = w.v_shaped + (size_t)slot * m.V * 3;
+    const bool use_sil = wt.sil > 0.f;
+
+    frame_pose_forward(S, m, w, p, fr, slot);
+    if (tid < NMJ * 3) S.gj[tid] = w.gjoint[(size_t)fr * NMJ * 3 + tid];
+    __syncthreads();
+
+    // 1. vertex gradients: face -> vertex gather, camera^T, keypoint regressor^T, LBS^T (v_shaped part)
+    const float4* ndc = w.ndc + (size_t)fr * m.Vp;
+    const float* fg = w.face_grad + (size_t)fr * m.Fp * 8;
+    float* dvs = w.dvs + (size_t)fr * m.V * 3;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int v = tid; v < m.V; v += FRAME_THREADS) {
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        if (use_sil) {
+            float gx = 0.f, gy = 0.f;
+            for (int e = m.v2f_ptr[v]; e < m.v2f_ptr[v + 1]; ++e) {
+                const int fc = m.v2f_fc[e];
+                const float2 q = *reinterpret_cast<const float2*>(fg + (size_t)(fc >> 2) * 8 + (fc & 3) * 2);
+                gx += q.x; gy += q.y;
+            }
+            const float4 nd = ndc[v];
+            camera_bwd(nd.x, nd.y, nd.z, gx, gy, g0, g1, g2);
+        }
+        t0 += g0; t1 += g1; t2 += g2;
+        for (int e = m.mjT_ptr[v]; e < m.mjT_ptr[v + 1]; ++e) {
+            const float wk = m.mjT_weight[e];
+            const int j = m.mjT_joint[e];
+            g0 = fmaf(wk, S.gj[j * 3 + 0], g0); g1 = fmaf(wk, S.gj[j * 3 + 1], g1); g2 = fmaf(wk, S.gj[j * 3 + 2], g2);
+        }
+        gw[v * 3 + 0] = g0; gw[v * 3 + 1] = g1; gw[v * 3 + 2] = g2;
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXINF; ++k) {
+            const float wk = m.skin_weight[v * MAXINF + k];
+            if (wk != 0.f) {
+                const float* G = S.G + m.skin_joint[v * MAXINF + k] * 9;
+                d0 = fmaf(wk, G[0] * g0 + G[3] * g1 + G[6] * g2, d0);
+                d1 = fmaf(wk, G[1] * g0 + G[4] * g1 + G[7] * g2, d1);
+                d2 = fmaf(wk, G[2] * g0 + G[5] * g1 + G[8] * g2, d2);
+            }
+        }
+        dvs[v * 3 + 0] = d0; dvs[v * 3 + 1] = d1; dvs[v * 3 + 2] = d2;
+    }
+    // dL/dtrans = sum_v (raster part) + sum_j dL/djoint_j   (verts + trans, joints + trans)
+    t0 = block_sum(t0, S.red); t1 = block_sum(t1, S.red); t2 = block_sum(t2, S.red);
+    if (tid == 0) {
+        float a0 = t0, a1 = t1, a2 = t2;
+        for (int j = 0; j < NMJ; ++j) { a0 += S.gj[j * 3]; a1 += S.gj[j * 3 + 1]; a2 += S.gj[j * 3 + 2]; }
+        if (g.trans) { g.trans[fr * 3 + 0] = a0; g.trans[fr * 3 + 1] = a1; g.trans[fr * 3 + 2] = a2; }
+    }
+    __syncthreads();
+
+    // 2. per joint: dL/dG_j = sum_v w gw_v vs_v^T, dL/doff_j = sum_v w gw_v
+    for (int j = wid; j < NJ; j += FRAME_THREADS / 32) {
+        float a[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) a[k] = 0.f;
+        for (int e = m.skinT_ptr[j] + lane; e < m.skinT_ptr[j + 1]; e += 32) {
+            const int v = m.skinT_vert[e];
+            const float wk = m.skinT_weight[e];
+            const float gx = wk * gw[v * 3], gy = wk * gw[v * 3 + 1], gz = wk * gw[v * 3 + 2];
+            const float x = vs[v * 3], y = vs[v * 3 + 1], z = vs[v * 3 + 2];
+            a[0] = fmaf(gx, x, a[0]); a[1] = fmaf(gx, y, a[1]); a[2] = fmaf(gx, z, a[2]);
+            a[3] = fmaf(gy, x, a[3]); a[4] = fmaf(gy, y, a[4]); a[5] = fmaf(gy, z, a[5]);
+            a[6] = fmaf(gz, x, a[6]); a[7] = fmaf(gz, y, a[7]); a[8] = fmaf(gz, z, a[8]);
+            a[9] += gx; a[10] += gy; a[11] += gz;
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) a[k] = warp_sum(a[k]);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) S.Gb[j * 9 + k] = a[k];
+            S.offb[j * 3] = a[9]; S.offb[j * 3 + 1] = a[10]; S.offb[j * 3 + 2] = a[11];
+        }
+    }
+    __syncthreads();
+
+    // 3. chain backward: local layer, then parents pull their children level by level
+    ChainFwd c = chain_of(S);
+    ChainBwd b;
+    b.Gb = S.Gb; b.offb = S.offb; b.tb = S.tb; b.Rwb = S.Rwb; b.sb = S.sb; b.Jb = S.Jb; b.Rb = S.Rb;
+    if (tid < NJ) chain_bwd_local(c, b, tid);
+    __syncthreads();
+    for (int lev = c_sk.n_levels - 1; lev >= 0; --lev) {
+        const int a0 = c_sk.level_start[lev], a1 = c_sk.level_start[lev + 1];
+        if (tid < a1 - a0) {
+            const int pj = c_sk.joint_order[a0 + tid];
+            for (int e = c_sk.child_ptr[pj]; e < c_sk.child_ptr[pj + 1]; ++e) chain_bwd_push(c, b, c_sk.child_idx[e], pj);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) chain_bwd_push(c, b, 0, -1);
+    __syncthreads();
+
+    // 4. Rodrigues^T, log-scale gradient, rest-joint gradient
+    if (tid < NJ) {
+        float thb[3] = {0.f, 0.f, 0.f};
+        rodrigues_bwd(S.theta + 3 * tid, S.Rb + 9 * tid, thb);
+        S.thg[tid * 3] = thb[0]; S.thg[tid * 3 + 1] = thb[1]; S.thg[tid * 3 + 2] = thb[2];
+    }
+    if (tid >= 64 && tid < 64 + NLS) {
+        const int k = tid - 64;
+        float a = 0.f;
+        for (int i = 0; i < NJ * 3; ++i)
+            if (c_sk.scale_axis[i] == k) a += S.sb[i] * S.s[i];
+        w.gls[fr * NLS + k] = a;
+    }
+    if (tid >= 96 && tid < 96 + NJ * 3) w.gJ[(size_t)fr * NJ * 3 + (tid - 96)] = S.Jb[tid - 96];
+    __syncthreads();
+
+    // 5. pose prior (smal_fitter.py:153-157, pose_prior_35.py:112-124) and splay (:159-160)
+    float lpose = 0.f, lsplay = 0.f;
+    const float invw = w.inv_window[fr];
+    if (wt.pose > 0.f) {
+        if (tid < NJ * 3) {
+            float a = 0.f;
+            for (int i = 0; i < NJ * 3; ++i) a = fmaf(S.theta[i] - m.pose_mean[i], m.pose_prec[i * (NJ * 3) + tid], a);
+            a *= m.pose_use[tid];
+            S.res[tid] = a;
+            lpose = a * a;
+        }
+        __syncthreads();
+        const float cp = wt.pose * invw * (1.f / (float)(NJ * 3));
+        if (tid < NJ * 3) {
+            float a = 0.f;
+            for (int k = 0; k < NJ * 3; ++k) a = fmaf(m.pose_prec[tid * (NJ * 3) + k], S.res[k] * m.pose_use[k], a);
+            S.thg[tid] += 2.f * cp * a;
+        }
+        lpose *= cp;
+    }
+    if (wt.splay > 0.f && tid >= 3 && tid < NJ * 3) {
+        const int c3 = tid % 3;
+        if (c3 != 1) {
+            const float q = S.theta[tid];
+            lsplay = wt.splay * q * q;
+            S.thg[tid] += 2.f * wt.splay * q;
+        }
+    }
+    lpose = block_sum(lpose, S.red);
+    lsplay = block_sum(lsplay, S.red);
+    if (tid == 0) { w.frame_loss[fr * 4 + 1] = lpose; w.frame_loss[fr * 4 + 2] = lsplay; }
+    if (tid < 3) { if (g.glob) g.glob[fr * 3 + tid] = S.thg[tid] * w.gmask[tid]; }
+    else if (tid < NJ * 3) { if (g.joint) g.joint[(size_t)fr * (NJ - 1) * 3 + (tid - 3)] = S.thg[tid] * w.rmask[tid - 3]; }
+}
+
+void launch_frame_backward(const ModelDev& m, const Workspace& w, const Params& p, const Grads& g,
+                           int frame0, int n, Weights wt, cudaStream_t st) {
+    const size_t smem = sizeof(FrameSmem) + (size_t)m.V * 3 * sizeof(float);
+    frame_backward_kernel<<<n, FRAME_THREADS, smem, st>>>(m, w, p, g, frame0, wt);
+}
+
+// ---------------------------------------------------------------------------
+// shape_backward: dL/dbetas = shapedirs . (sum_frames dvs + Jreg . sum_frames gJ), then finalize
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+shape_backward_kernel(ModelDev m, Workspace w, int frame0, int n_frames, int n_blocks) {
+    __shared__ float red[8][NBETA];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int slot = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + tid;
+    const int n = m.V * 3;
+    const int fa = (w.n_shapes == 1) ? frame0 : slot, fb = (w.n_shapes == 1) ? frame0 + n_frames : slot + 1;
+    float gsum = 0.f;
+    if (i < n) {
+        for (int fr = fa; fr < fb; ++fr) gsum += w.dvs[(size_t)fr * n + i];
+        const int v = i / 3, c = i - v * 3;
+        for (int e = m.jregT_ptr[v]; e < m.jregT_ptr[v + 1]; ++e) {
+            const int j = m.jregT_joint[e];
+            float gj = 0.f;
+            for (int fr = fa; fr < fb; ++fr) gj += w.gJ[(size_t)fr * NJ * 3 + j * 3 + c];
+            gsum = fmaf(m.jregT_weight[e], gj, gsum);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NBETA; ++k) {
+        float v = (i < n) ? m.shapedirs[(size_t)k * n + i] * gsum : 0.f;
+        v = warp_sum(v);
+        if (lane == 0) red[wid][k] = v;
+    }
+    __syncthreads();
+    if (tid < NBETA) {
+        float t = 0.f;
+        for (int q = 0; q < 8; ++q) t += red[q][tid];
+        w.beta_partial[((size_t)slot * n_blocks + blockIdx.x) * NBETA + tid] = t;
+    }
+}
+
+// one CTA: reduce partials, add the shape prior (smal_fitter.py:162-171), sum the loss terms
+__global__ void __launch_bounds__(256)
+finalize_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, int n_frames, Weights wt,
+                int prior_windows, int n_blocks, float* loss_terms) {
+    __shared__ float red[40];
+    __shared__ float diff[32], res[32];
+    const int tid = threadIdx.x;
+    const int tiles = w.tiles_x * w.tiles_y;
+    // loss terms: fixed-order sums over the frames of the range
+    float lk = 0.f, lp = 0.f, lsp = 0.f, lsil = 0.f;
+    for (int f = tid; f < n_frames; f += blockDim.x) {
+        const int fr = frame0 + f;
+        lk += w.frame_loss[fr * 4 + 0];
+        lp += w.frame_loss[fr * 4 + 1];
+        lsp += w.frame_loss[fr * 4 + 2];
+        if (wt.sil > 0.f) {
+            float t = 0.f;
+            for (int q = 0; q < tiles; ++q) t += w.tile_l1[(size_t)fr * tiles + q];
+            lsil += t * wt.sil * w.inv_window[fr] / ((float)w.S * (float)w.S);
+        }
+    }
+    lk = block_sum(lk, red); lp = block_sum(lp, red); lsp = block_sum(lsp, red); lsil = block_sum(lsil, red);
+
+    float lbetas = 0.f;
+    for (int slot = 0; slot < w.n_shapes; ++slot) {
+        const int D = m.shape_dim;
+        // shared shapes: every window contributes w_betas * mean(res^2); per-frame shapes: one window each
+        const float pw = (w.n_shapes == 1) ? (float)prior_windows : 1.f;
+        const bool in_range = (w.n_shapes == 1) || (slot >= frame0 && slot < frame0 + n_frames);
+        if (wt.betas > 0.f && in_range) {
+            if (tid < D) diff[tid] = ((tid < NBETA) ? p.betas[slot * NBETA + tid] : p.logscale[slot * NLS + tid - NBETA]) - m.shape_mean[tid];
+            __syncthreads();
+            if (tid < D) {
+                float a = 0.f;
+                for (int i = 0; i < D; ++i) a = fmaf(diff[i], m.shape_prec[i * D + tid], a);
+                res[tid] = a;
+            }
+            __syncthreads();
+        }
+        const float cb = wt.betas * pw / (float)D;
+        float pg = 0.f;
+        if (wt.betas > 0.f && in_range && tid < D) {
+            float a = 0.f;
+            for (int k = 0; k < D; ++k) a = fmaf(m.shape_prec[tid * D + k], res[k], a);
+            pg = 2.f * cb * a;
+            lbetas += cb * res[tid] * res[tid];
+        }
+        if (in_range) {
+            if (tid < NBETA && g.betas) {
+                float t = 0.f;
+                for (int q = 0; q < n_blocks; ++q) t += w.beta_partial[((size_t)slot * n_blocks + q) * NBETA + tid];
+                g.betas[slot * NBETA + tid] = t + pg;
+            }
+            if (tid >= 32 && tid < 32 + NLS && g.logscale) {
+                const int k = tid - 32;
+                const int fa = (w.n_shapes == 1) ? frame0 : slot, fb = (w.n_shapes == 1) ? frame0 + n_frames : slot + 1;
+                float t = 0.f;
+                for (int fr = fa; fr < fb; ++fr) t += w.gls[fr * NLS + k];
+                // prior gradient of the log-scale entries lives at index 20+k of the 26-d residual
+                float pgl = 0.f;
+                if (wt.betas > 0.f && D > NBETA) {
+                    float a = 0.f;
+                    for (int kk = 0; kk < D; ++kk) a = fmaf(m.shape_prec[(NBETA + k) * D + kk], res[kk], a);
+                    pgl = 2.f * cb * a;
+                }
+                g.logscale[slot * NLS + k] = t + pgl;
+            }
+        }
+        __syncthreads();
+    }
+    lbetas = block_sum(lbetas, red);
+    if (tid == 0 && loss_terms) {
+        loss_terms[0] = lk; loss_terms[1] = lsil; loss_terms[2] = lbetas; loss_terms[3] = lp;
+        loss_terms[4] = 0.f; loss_terms[5] = lsp; loss_terms[6] = 0.f;
+        loss_terms[7] = lk + lsil + lbetas + lp + lsp;
+    }
+}
+
+void launch_shape_backward(const ModelDev& m, const Workspace& w, const Params& p, const Grads& g,
+                           int frame0, int n, Weights wt, int prior_windows, float* loss_terms, cudaStream_t st) {
+    const int n_blocks = (m.V * 3 + 255) / 256;
+    dim3 grid(n_blocks, w.n_shapes);
+    shape_backward_kernel<<<grid, 256, 0, st>>>(m, w, frame0, n, n_blocks);
+    finalize_kernel<<<1, 256, 0, st>>>(m, w, p, g, frame0, n, wt, prior_windows, n_blocks, loss_terms);
+}
+
+// ---------------------------------------------------------------------------
+// temporal term (smal_fitter.py:177-190): value (joint, global, trans) and gradient (added)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) temporal_kernel(Workspace w, Params p, Grads g, int N, float w_temp, float* terms) {
+    __shared__ float red[40];
+    const int tid = threadIdx.x;
+    float lj = 0.f, lg = 0.f, lt = 0.f;
+    const int per = 3 + (NJ - 1) * 3 + 3;    // 108 values per frame: glob(3) joint(102) trans(3)
+    for (int idx = tid; idx < N * per; idx += blockDim.x) {
+        const int fr = idx / per, k = idx - fr * per;
+        const float* src; float* dst; float mask; float norm; int stride, off;
+        if (k < 3) { src = p.glob; dst = g.glob; stride = 3; off = k; mask = w.gmask[k]; norm = 1.f / 3.f; }
+        else if (k < 3 + (NJ - 1) * 3) { src = p.joint; dst = g.joint; stride = (NJ - 1) * 3; off = k - 3; mask = w.rmask[off]; norm = 1.f / (float)((NJ - 1) * 3); }
+        else { src = p.trans; dst = g.trans; stride = 3; off = k - 3 - (NJ - 1) * 3; mask = 1.f; norm = 1.f / 3.f; }
+        const float cur = src[(size_t)fr * stride + off] * mask;
+        float grad = 0.f;
+        if (fr + 1 < N) {
+            const float d = cur - src[(size_t)(fr + 1) * stride + off] * mask;
+            const float l = w_temp * norm * d * d;
+            if (k < 3) lg += l; else if (k < 3 + (NJ - 1) * 3) lj += l; else lt += l;
+            grad += 2.f * w_temp * norm * d;
+        }
+        if (fr > 0) {
+            const float d = src[(size_t)(fr - 1) * stride + off] * mask - cur;
+            grad -= 2.f * w_temp * norm * d;
+        }
+        if (dst) dst[(size_t)fr * stride + off] += grad * mask;
+    }
+    lj = block_sum(lj, red); lg = block_sum(lg, red); lt = block_sum(lt, red);
+    if (tid == 0 && terms) { terms[0] = lj; terms[1] = lg; terms[2] = lt; }
+}
+
+void launch_temporal(const Workspace& w, const Params& p, const Grads& g, int N, float w_temp, float* terms, cudaStream_t st) {
+    temporal_kernel<<<1, 256, 0, st>>>(w, p, g, N, w_temp, terms);
+}
+
+// ---------------------------------------------------------------------------
+// Adam (torch.optim.Adam semantics, no weight decay / amsgrad).  The step count and the
+// bias corrections live on the device so that a whole step can sit in a CUDA graph.
+// ---------------------------------------------------------------------------
+__global__ void adam_tick_kernel(AdamState* s, float b1, float b2, int host_step) {
+    const int step = (host_step > 0) ? host_step : s->step + 1;
+    s->step = step;
+    s->bc1 = 1.f - powf(b1, (float)step);
+    s->bc2_sqrt = sqrtf(1.f - powf(b2, (float)step));
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* p, const float* g, float* m, float* v, int n, float lr,
+                                                   float b1, float b2, float eps, const AdamState* s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float bc1 = s->bc1, bc2_sqrt = s->bc2_sqrt;
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+}
+
+void launch_adam_tick(AdamState* s, float b1, float b2, int host_step, cudaStream_t st) {
+    adam_tick_kernel<<<1, 1, 0, st>>>(s, b1, b2, host_step);
+}
+
+void launch_adam(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2, float eps,
+                 const AdamState* s, cudaStream_t st) {
+    if (n <= 0) return;
+    adam_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, s);
+}
+
+// ---------------------------------------------------------------------------
+// per-tile sums of the target mask (loss of tiles no face touches)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tile_tsum_kernel(Workspace w, int frame0, float* out) {
+    __shared__ float red[40];
+    const int tile = blockIdx.x, fr = frame0 + blockIdx.y;
+    const int tx = tile % w.tiles_x, ty = tile / w.tiles_x;
+    const int x = tx * TILE_W + (threadIdx.x & 15), y = ty * TILE_H + (threadIdx.x >> 4);
+    float v = 0.f;
+    if (x < w.S && y < w.S) v = (float)w.sil[((size_t)fr * w.S + y) * w.S + x];
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) out[(size_t)fr * w.tiles_x * w.tiles_y + tile] = v;
+}
+
+void launch_tile_tsum(const Workspace& w, int frame0, int n, float* tile_tsum, cudaStream_t st) {
+    dim3 grid(w.tiles_x * w.tiles_y, n);
+    tile_tsum_kernel<<<grid, 256, 0, st>>>(w, frame0, tile_tsum);
+}
+
+cudaError_t configure_kernels(const ModelDev& m) {
+    const int frame_smem = (int)(sizeof(FrameSmem) + (size_t)m.V * 3 * sizeof(float));
+    cudaError_t e = cudaFuncSetAttribute(frame_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(frame_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(raster_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes(m));
+}
+
+}  // namespace smf

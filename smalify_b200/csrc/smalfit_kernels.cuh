@@ -1,0 +1,119 @@
+// smalfit_kernels.cuh -- kernel argument blocks shared by smalfit_kernels.cu and
+// smalfit_capi.cu.  Device pointers only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "smalfit_math.cuh"
+
+namespace smf {
+
+constexpr int FRAME_THREADS = 256;
+constexpr int RAST_WARPS = 8;               // warps per raster-forward CTA
+constexpr int RAST_THREADS = RAST_WARPS * 32;
+constexpr int REGION_W = 8, REGION_H = 4;   // pixels handled by one warp at a time
+constexpr int TILE_W = 16, TILE_H = 16;     // 8 regions per CTA work item
+constexpr int KCAP = 512;                   // fragment selection buffer per warp (shared memory part)
+constexpr int MAX_LEVELS = 16;
+constexpr float P_SKIP = 2.98023224e-8f;    // 2^-25: below this 1-P rounds to 1.0f in fp32
+
+struct ModelDev {
+    int V, F, Fp, Vp;
+    const float* v_template;
+    const float* shapedirs;
+    const ushort4* faces4;       // [Fp] (v0,v1,v2,valid) ; padding faces have valid = 0
+    const int* skin_joint; const float* skin_weight;
+    const int* skinT_ptr; const int* skinT_vert; const float* skinT_weight;
+    const int* jreg_ptr; const int* jreg_vert; const float* jreg_weight;
+    const int* jregT_ptr; const int* jregT_joint; const float* jregT_weight;
+    const int* mj_ptr; const int* mj_vert; const float* mj_weight;
+    const int* mjT_ptr; const int* mjT_joint; const float* mjT_weight;
+    const int* v2f_ptr; const int* v2f_fc;
+    const float* pose_mean; const float* pose_prec; const float* pose_use;
+    int shape_dim; const float* shape_mean; const float* shape_prec;
+};
+
+// small tables in __constant__ memory
+struct SkeletonConst {
+    int parents[NJ];
+    int scale_axis[NJ * 3];
+    int joint_order[NJ];
+    int level_start[MAX_LEVELS + 1];
+    int n_levels;
+    int child_ptr[NJ + 1];
+    int child_idx[NJ];
+    int kp_joint[NKP];
+};
+
+struct Params {                 // the five tensors (dev)
+    const float* betas; const float* logscale; const float* glob; const float* joint; const float* trans;
+};
+struct Grads {
+    float* betas; float* logscale; float* glob; float* joint; float* trans;
+};
+
+struct Workspace {
+    int N, S, tiles_x, tiles_y;
+    int n_shapes;
+    // per shape slot
+    float* v_shaped;            // [n_shapes][V*3]
+    // per frame (indexed by absolute frame id)
+    float4* ndc;                // [N][Vp]  (x_ndc, y_ndc, z_view, -)
+    float* gjoint;              // [N][41*3] dL/d(model joints) from the keypoint term
+    float* kp_proj;             // [N][25*2]
+    uint2* face_rect;           // [N][Fp]  (c0 | c1<<16, r0 | r1<<16), empty: c0 > c1
+    int4* frame_bounds;         // [N] pixel bounds (c0, c1, r0, r1) of all faces
+    uint2* pix;                 // [N][S*S] (float coef, u32 tkey)
+    uint16_t* pix_tfid;         // [N][S*S] tie face id (capped pixels only)
+    float* tile_l1;             // [N][tiles]
+    float* face_grad;           // [N][Fp][8] (gx0,gy0,gx1,gy1,gx2,gy2,-,-)
+    float* dvs;                 // [N][V*3]  per-frame dL/dv_shaped
+    float* gJ;                  // [N][105]  per-frame dL/dJ(rest joints)
+    float* gls;                 // [N][6]    per-frame dL/dlogscale
+    float* frame_loss;          // [N][4]    kp, pose, splay, (unused)
+    float* beta_partial;        // [n_shapes][n_blocks][20]
+    // targets
+    const uint8_t* sil;         // [N][S*S]
+    const float* kp_target;     // [N][25*2]
+    const uint8_t* vis;         // [N][25]
+    const float* tile_tsum;     // [N][tiles]
+    const float* inv_window;    // [N] 1 / frames_per_window
+    const float* gmask;         // [3]
+    const float* rmask;         // [102]
+    // raster scratch
+    uint16_t* sl_fid;           // [n_raster_warps][Fp]
+    uint32_t* sl_mask;          // [n_raster_warps][Fp]
+    unsigned int* work_counter; // [1]
+    unsigned long long* counters;   // [4]
+};
+
+struct Weights { float j2d, sil, betas, pose, limit, splay; };
+struct AdamState { int step; float bc1; float bc2_sqrt; int pad; };
+
+struct RasterScratch {      // global spill buffers for pixels with more than KCAP fragments, per resident warp
+    unsigned* key; float* m; unsigned short* fid;
+};
+
+// ---- launch wrappers (defined in smalfit_kernels.cu) ----------------------
+void upload_skeleton(const SkeletonConst& sk);
+cudaError_t configure_kernels(const ModelDev& m);
+size_t raster_smem_bytes(const ModelDev& m);
+void launch_shape_forward(const ModelDev& m, const Workspace& w, const Params& p, cudaStream_t st);
+void launch_frame_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n,
+                          Weights wt, float* verts_out, cudaStream_t st);
+void launch_face_rects(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st);
+void launch_raster_forward(const ModelDev& m, const Workspace& w, const RasterScratch& sc, float* ndc_soa,
+                           int frame0, int n, Weights wt, float* alpha_out, int n_ctas, cudaStream_t st);
+void launch_raster_backward(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st);
+void launch_frame_backward(const ModelDev& m, const Workspace& w, const Params& p, const Grads& g,
+                           int frame0, int n, Weights wt, cudaStream_t st);
+void launch_shape_backward(const ModelDev& m, const Workspace& w, const Params& p, const Grads& g,
+                           int frame0, int n, Weights wt, int prior_windows, float* loss_terms,
+                           cudaStream_t st);
+void launch_temporal(const Workspace& w, const Params& p, const Grads& g, int N, float w_temp,
+                     float* terms, cudaStream_t st);
+void launch_adam_tick(AdamState* s, float b1, float b2, int host_step, cudaStream_t st);
+void launch_adam(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2,
+                 float eps, const AdamState* s, cudaStream_t st);
+void launch_tile_tsum(const Workspace& w, int frame0, int n, float* tile_tsum, cudaStream_t st);
+
+}  // namespace smf

@@ -1,0 +1,369 @@
+// smalfit_math.cuh -- closed-form maths of the SMAL fitting path, shared by every
+// kernel.  Everything here is __host__ __device__ so tests/cpu_check can compile
+// the same functions with g++ and compare them with the oracle; the product only
+// ever runs them inside the CUDA kernels of smalfit_kernels.cu.
+//
+// Reference behaviour each block restates (paths in the SMALify checkout):
+//   rodrigues_*      smal_model/batch_lbs.py:33-52 (eps added per component inside the norm)
+//   chain_*          smal_model/batch_lbs.py:75-170 in the telescoped form
+//                    G_i = Rw_i diag(s_i),  t_i = t_p + Rw_p diag(s_p)(J_i - J_p),
+//                    A_i = [G_i | t_i - G_i J_i]   (S_parent^-1 cancels)
+//   camera_*         PyTorch3D 0.2.5 look_at_view_transform(2.7,0,0) + OpenGLPerspectiveCameras
+//                    as used at smal_fitter/p3d_renderer.py:22-23,67-68
+//   face_setup/eval  PyTorch3D 0.2.5 CheckPixelInsideFace / PointTriangleDistance{Forward,Backward}
+//                    (csrc/rasterize_meshes, csrc/utils/geometry_utils) as configured at
+//                    smal_fitter/p3d_renderer.py:26-39
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SMF_HD __host__ __device__ __forceinline__
+#else
+#define SMF_HD inline
+#endif
+
+namespace smf {
+
+constexpr int NJ = 35;            // joints incl. root
+constexpr int NMJ = 41;           // model joints (35 regressed + 6 picked vertices)
+constexpr int NKP = 25;           // annotated keypoints
+constexpr int NBETA = 20;
+constexpr int NLS = 6;
+constexpr int MAXINF = 8;         // skinning influences per vertex
+
+constexpr float CAM_DIST = 2.7f;
+constexpr float CAM_F = 1.7320508075688772f;         // 1/tan(30 deg)
+constexpr float RAST_SIGMA = 1e-4f;
+constexpr float RAST_BLUR = 9.210240366975849e-4f;   // log(1/1e-4 - 1) * 1e-4   (NDC^2)
+constexpr float RAST_BLUR_SQRT = 0.030348377826f;    // sqrt(RAST_BLUR)
+constexpr float RAST_EPS = 1e-8f;                    // PyTorch3D kEpsilon
+constexpr int RAST_K = 100;                          // faces_per_pixel
+constexpr float RODRIGUES_EPS = 1e-8f;
+
+// exact-rounding helpers: on the device these pin the operation order (no
+// re-contraction), on the host they are the plain operators.
+#if defined(__CUDA_ARCH__)
+SMF_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+SMF_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
+SMF_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+SMF_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+SMF_HD float fsat(float a) { return __saturatef(a); }
+#else
+SMF_HD float fmul(float a, float b) { return a * b; }
+SMF_HD float fsub(float a, float b) { return a - b; }
+SMF_HD float fadd(float a, float b) { return a + b; }
+SMF_HD float ffma(float a, float b, float c) { return fmaf(a, b, c); }
+SMF_HD float fsat(float a) { return a < 0.f ? 0.f : (a > 1.f ? 1.f : a); }
+#endif
+
+// ---------------------------------------------------------------------------
+// 3x3 helpers (row-major float[9])
+// ---------------------------------------------------------------------------
+SMF_HD void mat3_mul(const float* A, const float* B, float* C) {      // C = A B
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = A[i * 3 + 0] * B[0 * 3 + j] + A[i * 3 + 1] * B[1 * 3 + j] + A[i * 3 + 2] * B[2 * 3 + j];
+}
+SMF_HD void mat3_mul_bt(const float* A, const float* B, float* C) {   // C = A B^T
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = A[i * 3 + 0] * B[j * 3 + 0] + A[i * 3 + 1] * B[j * 3 + 1] + A[i * 3 + 2] * B[j * 3 + 2];
+}
+SMF_HD void mat3_mul_at(const float* A, const float* B, float* C) {   // C = A^T B
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = A[0 * 3 + i] * B[0 * 3 + j] + A[1 * 3 + i] * B[1 * 3 + j] + A[2 * 3 + i] * B[2 * 3 + j];
+}
+
+// ---------------------------------------------------------------------------
+// Rodrigues (batch_lbs.py:33-52)
+// ---------------------------------------------------------------------------
+SMF_HD void rodrigues_fwd(const float* th, float* R) {
+    const float ux = th[0] + RODRIGUES_EPS, uy = th[1] + RODRIGUES_EPS, uz = th[2] + RODRIGUES_EPS;
+    const float a = sqrtf(ux * ux + uy * uy + uz * uz);
+    const float rx = th[0] / a, ry = th[1] / a, rz = th[2] / a;
+    const float c = cosf(a), s = sinf(a), k = 1.f - c;
+    R[0] = c + k * rx * rx; R[1] = k * rx * ry - s * rz; R[2] = k * rx * rz + s * ry;
+    R[3] = k * ry * rx + s * rz; R[4] = c + k * ry * ry; R[5] = k * ry * rz - s * rx;
+    R[6] = k * rz * rx - s * ry; R[7] = k * rz * ry + s * rx; R[8] = c + k * rz * rz;
+}
+
+// thb += dL/dtheta given Rb = dL/dR, differentiating the expression above.
+SMF_HD void rodrigues_bwd(const float* th, const float* Rb, float* thb) {
+    const float u[3] = {th[0] + RODRIGUES_EPS, th[1] + RODRIGUES_EPS, th[2] + RODRIGUES_EPS};
+    const float a = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    const float ia = 1.f / a;
+    const float r[3] = {th[0] * ia, th[1] * ia, th[2] * ia};
+    const float c = cosf(a), s = sinf(a), k = 1.f - c;
+    // dR/da = -s I + s r r^T + c [r]x
+    float ab = 0.f;
+    ab += Rb[0] * (-s + s * r[0] * r[0]) + Rb[4] * (-s + s * r[1] * r[1]) + Rb[8] * (-s + s * r[2] * r[2]);
+    ab += s * (r[0] * r[1] * (Rb[1] + Rb[3]) + r[0] * r[2] * (Rb[2] + Rb[6]) + r[1] * r[2] * (Rb[5] + Rb[7]));
+    ab += c * (r[0] * (Rb[7] - Rb[5]) + r[1] * (Rb[2] - Rb[6]) + r[2] * (Rb[3] - Rb[1]));
+    // dR/dr_k = k (e_k r^T + r e_k^T) + s [e_k]x
+    float rb[3];
+    rb[0] = k * (Rb[0] * r[0] + Rb[1] * r[1] + Rb[2] * r[2] + Rb[0] * r[0] + Rb[3] * r[1] + Rb[6] * r[2]) + s * (Rb[7] - Rb[5]);
+    rb[1] = k * (Rb[3] * r[0] + Rb[4] * r[1] + Rb[5] * r[2] + Rb[1] * r[0] + Rb[4] * r[1] + Rb[7] * r[2]) + s * (Rb[2] - Rb[6]);
+    rb[2] = k * (Rb[6] * r[0] + Rb[7] * r[1] + Rb[8] * r[2] + Rb[2] * r[0] + Rb[5] * r[1] + Rb[8] * r[2]) + s * (Rb[3] - Rb[1]);
+    // r = th / a ,  a = |th + eps|
+    ab -= (rb[0] * th[0] + rb[1] * th[1] + rb[2] * th[2]) * ia * ia;
+    for (int i = 0; i < 3; ++i) thb[i] += rb[i] * ia + ab * u[i] * ia;
+}
+
+// ---------------------------------------------------------------------------
+// Kinematic chain.  Arrays are [NJ][..] floats, anywhere (shared / host memory).
+// ---------------------------------------------------------------------------
+struct ChainFwd {          // pointers into caller storage
+    float* R;    // [NJ*9] local rotations
+    float* Rw;   // [NJ*9] accumulated rotations
+    float* s;    // [NJ*3] per-axis scales
+    float* t;    // [NJ*3] posed joint positions
+    float* J;    // [NJ*3] rest joints
+    float* G;    // [NJ*9] Rw diag(s)
+    float* off;  // [NJ*3] t - G J
+};
+
+// scales of joint j from the 6 log-scales; scale_axis[j*3+a] in {-1,0..5}
+SMF_HD void chain_scale(int j, const float* ls, const int* scale_axis, float* s) {
+    for (int a = 0; a < 3; ++a) {
+        const int k = scale_axis[j * 3 + a];
+        s[j * 3 + a] = (k >= 0) ? expf(ls[k]) : 1.f;
+    }
+}
+
+// joint i given its parent p is done (root: p < 0)
+SMF_HD void chain_fwd_joint(const ChainFwd& c, int i, int p) {
+    float* Rw = c.Rw + i * 9;
+    if (p < 0) {
+        for (int k = 0; k < 9; ++k) Rw[k] = c.R[k];
+        for (int k = 0; k < 3; ++k) c.t[k] = c.J[k];
+    } else {
+        mat3_mul(c.Rw + p * 9, c.R + i * 9, Rw);
+        const float* Rp = c.Rw + p * 9;
+        const float* sp = c.s + p * 3;
+        const float d[3] = {sp[0] * (c.J[i * 3 + 0] - c.J[p * 3 + 0]),
+                            sp[1] * (c.J[i * 3 + 1] - c.J[p * 3 + 1]),
+                            sp[2] * (c.J[i * 3 + 2] - c.J[p * 3 + 2])};
+        for (int r = 0; r < 3; ++r)
+            c.t[i * 3 + r] = c.t[p * 3 + r] + Rp[r * 3 + 0] * d[0] + Rp[r * 3 + 1] * d[1] + Rp[r * 3 + 2] * d[2];
+    }
+    float* G = c.G + i * 9;
+    const float* si = c.s + i * 3;
+    for (int r = 0; r < 3; ++r)
+        for (int a = 0; a < 3; ++a) G[r * 3 + a] = Rw[r * 3 + a] * si[a];
+    for (int r = 0; r < 3; ++r)
+        c.off[i * 3 + r] = c.t[i * 3 + r] - (G[r * 3 + 0] * c.J[i * 3 + 0] + G[r * 3 + 1] * c.J[i * 3 + 1] + G[r * 3 + 2] * c.J[i * 3 + 2]);
+}
+
+struct ChainBwd {
+    float* Gb;    // [NJ*9] in: dL/dG from skinning
+    float* offb;  // [NJ*3] in: dL/doff from skinning
+    float* tb;    // [NJ*3] work: dL/dt
+    float* Rwb;   // [NJ*9] work: dL/dRw
+    float* sb;    // [NJ*3] out: dL/ds
+    float* Jb;    // [NJ*3] out: dL/dJ (rest joints)
+    float* Rb;    // [NJ*9] out: dL/dR (local)
+};
+
+// Step 1 (any order, per joint): fold the A_i = [G_i | t_i - G_i J_i] layer.
+// Initialises tb, Rwb, sb, Jb of joint i.
+SMF_HD void chain_bwd_local(const ChainFwd& c, const ChainBwd& b, int i) {
+    const float* G = c.G + i * 9;
+    const float* Rw = c.Rw + i * 9;
+    const float* si = c.s + i * 3;
+    const float* ob = b.offb + i * 3;
+    const float* Ji = c.J + i * 3;
+    for (int r = 0; r < 3; ++r) b.tb[i * 3 + r] = ob[r];
+    // off = t - G J :  Gb_eff = Gb - offb J^T ,  Jb = -G^T offb
+    float Ge[9];
+    for (int r = 0; r < 3; ++r)
+        for (int a = 0; a < 3; ++a) Ge[r * 3 + a] = b.Gb[i * 9 + r * 3 + a] - ob[r] * Ji[a];
+    for (int a = 0; a < 3; ++a)
+        b.Jb[i * 3 + a] = -(G[0 * 3 + a] * ob[0] + G[1 * 3 + a] * ob[1] + G[2 * 3 + a] * ob[2]);
+    // G = Rw diag(s)
+    for (int a = 0; a < 3; ++a) {
+        b.sb[i * 3 + a] = Rw[0 * 3 + a] * Ge[0 * 3 + a] + Rw[1 * 3 + a] * Ge[1 * 3 + a] + Rw[2 * 3 + a] * Ge[2 * 3 + a];
+        for (int r = 0; r < 3; ++r) b.Rwb[i * 9 + r * 3 + a] = Ge[r * 3 + a] * si[a];
+    }
+}
+
+// Step 2 (children before parents): push joint i's (complete) tb / Rwb to its parent p
+// and emit Rb_i.  Must be serialised per parent (the kernels pull per parent instead,
+// see chain_bwd_pull); kept for the serial host check.
+SMF_HD void chain_bwd_push(const ChainFwd& c, const ChainBwd& b, int i, int p) {
+    if (p < 0) {
+        for (int k = 0; k < 9; ++k) b.Rb[k] = b.Rwb[k];
+        for (int k = 0; k < 3; ++k) b.Jb[k] += b.tb[k];     // t_0 = J_0
+        return;
+    }
+    const float* Rp = c.Rw + p * 9;
+    const float* sp = c.s + p * 3;
+    const float* tbi = b.tb + i * 3;
+    float delta[3], RtT[3];
+    for (int a = 0; a < 3; ++a) {
+        delta[a] = c.J[i * 3 + a] - c.J[p * 3 + a];
+        RtT[a] = Rp[0 * 3 + a] * tbi[0] + Rp[1 * 3 + a] * tbi[1] + Rp[2 * 3 + a] * tbi[2];   // (Rw_p^T tb_i)_a
+    }
+    for (int r = 0; r < 3; ++r) {
+        b.tb[p * 3 + r] += tbi[r];
+        for (int a = 0; a < 3; ++a) b.Rwb[p * 9 + r * 3 + a] += tbi[r] * sp[a] * delta[a];
+    }
+    for (int a = 0; a < 3; ++a) {
+        b.sb[p * 3 + a] += RtT[a] * delta[a];
+        const float db = sp[a] * RtT[a];
+        b.Jb[i * 3 + a] += db;
+        b.Jb[p * 3 + a] -= db;
+    }
+    // Rw_i = Rw_p R_i
+    float tmp[9];
+    mat3_mul_bt(b.Rwb + i * 9, c.R + i * 9, tmp);             // Rwb_i R_i^T
+    for (int k = 0; k < 9; ++k) b.Rwb[p * 9 + k] += tmp[k];
+    mat3_mul_at(Rp, b.Rwb + i * 9, b.Rb + i * 9);             // Rw_p^T Rwb_i
+}
+
+// ---------------------------------------------------------------------------
+// Camera
+// ---------------------------------------------------------------------------
+SMF_HD void camera_fwd(float X, float Y, float Z, float& xn, float& yn, float& zv) {
+    zv = CAM_DIST - Z;
+    const float iz = 1.f / zv;
+    xn = -CAM_F * X * iz;
+    yn = CAM_F * Y * iz;
+}
+// (gx, gy) = dL/d(x_ndc, y_ndc) -> dL/d(X,Y,Z); z_view carries no gradient.
+SMF_HD void camera_bwd(float xn, float yn, float zv, float gx, float gy, float& gX, float& gY, float& gZ) {
+    const float iz = 1.f / zv;
+    gX = -CAM_F * iz * gx;
+    gY = CAM_F * iz * gy;
+    gZ = (xn * gx + yn * gy) * iz;
+}
+// keypoint pixel (row, col) from NDC, transform_points_screen with (S-1)/2
+SMF_HD void screen_fwd(float xn, float yn, float half, float& row, float& col) {
+    col = half * (1.f - xn);
+    row = half * (1.f - yn);
+}
+
+// pixel centre of the rasteriser (x is flipped: +X left, +Y up)
+SMF_HD float pix_to_ndc(int i, float inv_s) { return 1.f - (2.f * (float)i + 1.f) * inv_s; }
+
+// ---------------------------------------------------------------------------
+// Soft rasteriser: one face against one pixel
+// ---------------------------------------------------------------------------
+struct FaceSetup {         // 24 floats
+    float x0, y0, x1, y1, x2, y2;
+    float z0, z1, z2;
+    float rden;            // 1 / (area + eps)
+    float e01x, e01y, e02x, e02y, e12x, e12y;
+    float rl01, rl02, rl12;          // 1 / |edge|^2 (0 for a degenerate edge)
+    float bx0, bx1, by0, by1;        // blur-expanded bbox
+    float valid;                     // 0/1
+};
+
+SMF_HD FaceSetup face_setup(float x0, float y0, float z0, float x1, float y1, float z1, float x2, float y2, float z2) {
+    FaceSetup f;
+    f.x0 = x0; f.y0 = y0; f.x1 = x1; f.y1 = y1; f.x2 = x2; f.y2 = y2;
+    f.z0 = z0; f.z1 = z1; f.z2 = z2;
+    f.e01x = fsub(x1, x0); f.e01y = fsub(y1, y0);
+    f.e02x = fsub(x2, x0); f.e02y = fsub(y2, y0);
+    f.e12x = fsub(x2, x1); f.e12y = fsub(y2, y1);
+    // area = EdgeFunction(v2; v0, v1) = (x2-x0)(y1-y0) - (y2-y0)(x1-x0)
+    const float area = fsub(fmul(f.e02x, f.e01y), fmul(f.e02y, f.e01x));
+    const float zmax = fmaxf(z0, fmaxf(z1, z2));
+    const bool degenerate = (area <= RAST_EPS) && (area >= -RAST_EPS);
+    f.valid = (zmax >= 0.f && !degenerate) ? 1.f : 0.f;
+    f.rden = 1.f / fadd(area, RAST_EPS);
+    const float l01 = fadd(fmul(f.e01x, f.e01x), fmul(f.e01y, f.e01y));
+    const float l02 = fadd(fmul(f.e02x, f.e02x), fmul(f.e02y, f.e02y));
+    const float l12 = fadd(fmul(f.e12x, f.e12x), fmul(f.e12y, f.e12y));
+    f.rl01 = (l01 <= RAST_EPS) ? 0.f : 1.f / l01;
+    f.rl02 = (l02 <= RAST_EPS) ? 0.f : 1.f / l02;
+    f.rl12 = (l12 <= RAST_EPS) ? 0.f : 1.f / l12;
+    f.bx0 = fsub(fminf(x0, fminf(x1, x2)), RAST_BLUR_SQRT);
+    f.bx1 = fadd(fmaxf(x0, fmaxf(x1, x2)), RAST_BLUR_SQRT);
+    f.by0 = fsub(fminf(y0, fminf(y1, y2)), RAST_BLUR_SQRT);
+    f.by1 = fadd(fmaxf(y0, fmaxf(y1, y2)), RAST_BLUR_SQRT);
+    return f;
+}
+
+// Conservative pixel rectangle [c0,c1]x[r0,r1] (inclusive, clipped) containing every
+// pixel whose centre passes the bbox test; returns false if empty / face invalid.
+SMF_HD bool face_pixel_rect(const FaceSetup& f, int S, int& c0, int& c1, int& r0, int& r1) {
+    if (f.valid == 0.f) return false;
+    const float hs = 0.5f * (float)S;
+    // x(c) = 1 - (2c+1)/S in [bx0, bx1]  <=>  c in [ (1-bx1) S/2 - 1/2 , (1-bx0) S/2 - 1/2 ]
+    const float cl = (1.f - f.bx1) * hs - 0.5f, ch = (1.f - f.bx0) * hs - 0.5f;
+    const float rl = (1.f - f.by1) * hs - 0.5f, rh = (1.f - f.by0) * hs - 0.5f;
+    if (!(ch >= -0.02f) || !(cl <= (float)S - 0.98f) || !(rh >= -0.02f) || !(rl <= (float)S - 0.98f)) return false;
+    const float fS = (float)(S - 1);
+    c0 = (int)fminf(fmaxf(ceilf(cl - 0.01f), 0.f), fS);
+    c1 = (int)fminf(fmaxf(floorf(ch + 0.01f), 0.f), fS);
+    r0 = (int)fminf(fmaxf(ceilf(rl - 0.01f), 0.f), fS);
+    r1 = (int)fminf(fmaxf(floorf(rh + 0.01f), 0.f), fS);
+    return (c0 <= c1) && (r0 <= r1);
+}
+
+struct Fragment {
+    float pz;        // interpolated (unclipped barycentric) depth, >= 0
+    float sd;        // signed squared distance: <0 inside
+    int edge;        // closest edge: 0 = v0v1, 1 = v0v2, 2 = v1v2
+    float t;         // clamped parameter on that edge
+    float qx, qy;    // p_proj - p on that edge
+};
+
+// CheckPixelInsideFace.  Returns true when (face, pixel) yields a fragment.
+SMF_HD bool face_eval(const FaceSetup& f, float px, float py, Fragment& fr) {
+    if (f.valid == 0.f) return false;
+    if (px > f.bx1 || px < f.bx0 || py > f.by1 || py < f.by0) return false;
+    const float ax = fsub(px, f.x0), ay = fsub(py, f.y0);     // p - v0
+    const float bx = fsub(px, f.x1), by = fsub(py, f.y1);     // p - v1
+    const float cx = fsub(px, f.x2), cy = fsub(py, f.y2);     // p - v2
+    // barycentric numerators (edge functions)
+    const float n0 = fsub(fmul(bx, f.e12y), fmul(by, f.e12x));        // E(p; v1, v2)
+    const float n1 = fsub(fmul(cy, f.e02x), fmul(cx, f.e02y));        // E(p; v2, v0) = (p-v2) x (v0-v2)
+    const float n2 = fsub(fmul(ax, f.e01y), fmul(ay, f.e01x));        // E(p; v0, v1)
+    const float w0 = fmul(n0, f.rden), w1 = fmul(n1, f.rden), w2 = fmul(n2, f.rden);
+    const float pz = ffma(w2, f.z2, ffma(w1, f.z1, fmul(w0, f.z0)));
+    if (pz < 0.f) return false;
+    // squared distances to the three segments
+    const float t01 = (f.rl01 == 0.f) ? 1.f : fsat(fmul(fadd(fmul(f.e01x, ax), fmul(f.e01y, ay)), f.rl01));
+    const float q01x = fsub(fmul(t01, f.e01x), ax), q01y = fsub(fmul(t01, f.e01y), ay);
+    const float d01 = fadd(fmul(q01x, q01x), fmul(q01y, q01y));
+    const float t02 = (f.rl02 == 0.f) ? 1.f : fsat(fmul(fadd(fmul(f.e02x, ax), fmul(f.e02y, ay)), f.rl02));
+    const float q02x = fsub(fmul(t02, f.e02x), ax), q02y = fsub(fmul(t02, f.e02y), ay);
+    const float d02 = fadd(fmul(q02x, q02x), fmul(q02y, q02y));
+    const float t12 = (f.rl12 == 0.f) ? 1.f : fsat(fmul(fadd(fmul(f.e12x, bx), fmul(f.e12y, by)), f.rl12));
+    const float q12x = fsub(fmul(t12, f.e12x), bx), q12y = fsub(fmul(t12, f.e12y), by);
+    const float d12 = fadd(fmul(q12x, q12x), fmul(q12y, q12y));
+    // closest edge, ties 01 -> 02 -> 12 (PointTriangleDistanceBackward order)
+    int e; float d, t, qx, qy;
+    if (d01 <= d02 && d01 <= d12) { e = 0; d = d01; t = t01; qx = q01x; qy = q01y; }
+    else if (d02 <= d01 && d02 <= d12) { e = 1; d = d02; t = t02; qx = q02x; qy = q02y; }
+    else { e = 2; d = d12; t = t12; qx = q12x; qy = q12y; }
+    const bool inside = (w0 > 0.f) && (w1 > 0.f) && (w2 > 0.f);
+    if (!inside && d >= RAST_BLUR) return false;
+    fr.pz = pz; fr.sd = inside ? -d : d; fr.edge = e; fr.t = t; fr.qx = qx; fr.qy = qy;
+    return true;
+}
+
+// 1 - sigmoid(-sd/sigma) the way the reference forms it in fp32: p = sigmoid(x), m = 1 - p.
+SMF_HD void frag_prob(float sd, float& p, float& m) {
+#if defined(__CUDA_ARCH__)
+    p = __frcp_rn(1.f + __expf(sd * (1.f / RAST_SIGMA)));
+#else
+    p = 1.f / (1.f + expf(sd * (1.f / RAST_SIGMA)));
+#endif
+    m = 1.f - p;
+}
+
+// gradient of the signed distance w.r.t. the face's xy: g[0..5] += gs * d(sd)/d(x0,y0,x1,y1,x2,y2)
+SMF_HD void frag_grad(const Fragment& fr, float gs, float* g) {
+    const float gd = (fr.sd < 0.f) ? -gs : gs;            // d(sd)/d(d2) = inside ? -1 : 1
+    const float ga = gd * (1.f - fr.t) * 2.f, gb = gd * fr.t * 2.f;
+    int ia, ib;
+    if (fr.edge == 0) { ia = 0; ib = 2; } else if (fr.edge == 1) { ia = 0; ib = 4; } else { ia = 2; ib = 4; }
+    g[ia] += ga * fr.qx; g[ia + 1] += ga * fr.qy;
+    g[ib] += gb * fr.qx; g[ib + 1] += gb * fr.qy;
+}
+
+}  // namespace smf

@@ -1,0 +1,450 @@
+"""SMALFitter: drop-in for ``smal_fitter/smal_fitter.py::SMALFitter`` whose forward
+and backward run in libsmalfit's sm_100a kernels.
+
+Same constructor, parameters, attributes and ``forward`` / ``get_temporal`` /
+``load_checkpoint`` surface as the reference (smal_fitter.py:25-207); there is
+no torch autograd graph, PyTorch3D or CPU path inside: ``forward`` hands the raw
+device pointers of the five parameters through the C-ABI, the kernels compute
+the loss terms *and* the analytic gradients, and a ``torch.autograd.Function``
+shim deposits them when the caller runs ``loss.backward()``.
+
+``FusedFit`` (below) is the opt-in fast path: one call = one epoch of
+``optimize_to_joints.py:117-137`` (all windows + temporal + Adam [+ all-reduce])
+on flat device buffers, capturable in a CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import pickle as pkl
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi, constants as K, model_io
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _tensors(betas, lbs, glob, joint, trans) -> _cabi.Tensors:
+    s = _cabi.Tensors()
+    s.betas, s.log_beta_scales, s.global_rotation, s.joint_rotations, s.trans = (
+        t.data_ptr() if t is not None else None for t in (betas, lbs, glob, joint, trans))
+    return s
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _weights6(weights):
+    w = [float(x) for x in weights]
+    if len(w) != 6:
+        raise ValueError("weights must be (w_j2d, w_reproj, w_betas, w_pose, w_limit, w_splay)")
+    return (ctypes.c_float * 6)(*w)
+
+
+def _contiguous_range(batch_range):
+    br = [int(i) for i in batch_range]
+    if not br:
+        raise ValueError("empty batch_range")
+    if br != list(range(br[0], br[0] + len(br))):
+        raise ValueError("libsmalfit addresses frames as a contiguous range; got " + repr(br[:8]))
+    return br[0], len(br)
+
+
+class _LossGradFn(torch.autograd.Function):
+    """forward: launch the fused kernels (loss terms + analytic gradients into the
+    fitter's workspace); backward: scale the stashed gradients by grad_output."""
+
+    @staticmethod
+    def forward(ctx, fitter, frame0, n, weights, betas, lbs, glob, joint, trans):
+        terms = torch.empty(8, device=glob.device, dtype=torch.float32)
+        ws = fitter._grad_ws
+        lbs_dev = lbs if fitter.use_unity_prior else fitter._zero_logscale
+        params = _tensors(betas, lbs_dev, glob, joint, trans)
+        grads = _tensors(ws["betas"], ws["log_beta_scales"], ws["global_rotation"], ws["joint_rotations"], ws["trans"])
+        h = fitter._handle
+        h.check(h.lib.smalfit_loss_grad(h.h, ctypes.byref(params), frame0, n, _weights6(weights), 1,
+                                        ctypes.byref(grads), _ptr(terms), _stream(glob.device)), "smalfit_loss_grad")
+        ctx.fitter, ctx.frame0, ctx.n = fitter, frame0, n
+        # shared-shape gradients are overwritten by the next window: keep this window's copy
+        ctx.g_betas = ws["betas"].clone()
+        ctx.g_lbs = ws["log_beta_scales"].clone()
+        ctx.mark_non_differentiable(terms)
+        loss = terms[_cabi.L_TOTAL].clone()
+        ctx.terms = terms
+        return loss, terms
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_terms):
+        f, a, n = ctx.fitter, ctx.frame0, ctx.n
+        ws = f._grad_ws
+        need = ctx.needs_input_grad          # (fitter, frame0, n, weights, betas, lbs, glob, joint, trans)
+        out = [None, None, None, None]
+        out.append(grad_loss * ctx.g_betas if need[4] else None)
+        if need[5]:
+            out.append(grad_loss * ctx.g_lbs if f.use_unity_prior else torch.zeros_like(f.log_beta_scales))
+        else:
+            out.append(None)
+        for idx, key in ((6, "global_rotation"), (7, "joint_rotations"), (8, "trans")):
+            if need[idx]:
+                g = torch.zeros_like(ws[key])
+                g[a:a + n] = grad_loss * ws[key][a:a + n]
+                out.append(g)
+            else:
+                out.append(None)
+        return tuple(out)
+
+
+class _TemporalFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fitter, w_temp, glob, joint, trans):
+        dev = glob.device
+        terms = torch.empty(3, device=dev, dtype=torch.float32)
+        g = {k: torch.zeros_like(v) for k, v in (("g", glob), ("j", joint), ("t", trans))}
+        params = _tensors(fitter.betas, fitter._lbs_dev(), glob, joint, trans)
+        grads = _tensors(None, None, g["g"], g["j"], g["t"])
+        h = fitter._handle
+        h.check(h.lib.smalfit_temporal(h.h, ctypes.byref(params), fitter.num_images, float(w_temp),
+                                       ctypes.byref(grads), _ptr(terms), _stream(dev)), "smalfit_temporal")
+        ctx.g = g
+        return terms[0].clone(), terms[1].clone(), terms[2].clone()
+
+    @staticmethod
+    def backward(ctx, gj, gg, gt):
+        # the kernel returns the gradient of (joint + global + trans); the three terms touch
+        # disjoint tensors, so each upstream factor applies to its own tensor
+        g = ctx.g
+        return None, None, gg * g["g"], gj * g["j"], gt * g["t"]
+
+
+class SMALFitter(nn.Module):
+    """See module docstring.  ``data_batch = (rgb (N,3,S,S), sil (N,1,S,S), joints (N,25,2) (row,col),
+    visibility (N,25))`` as produced by the reference loaders (data_loader.py:60-69)."""
+
+    def __init__(self, device, data_batch, batch_size, shape_family, use_unity_prior,
+                 constants: model_io.SmalConstants | None = None, data_root: str | None = None,
+                 resident_targets: bool = True):
+        super().__init__()
+        self.rgb_imgs, self.sil_imgs, self.target_joints, self.target_visibility = data_batch
+        self.target_visibility = self.target_visibility.long()
+        if self.rgb_imgs is not None:
+            assert self.rgb_imgs.max() <= 1.0 and self.rgb_imgs.min() >= 0.0, "RGB Image range is incorrect"
+
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _cabi.SmalfitError("SMALFitter (B200) needs a CUDA device: the fitting path has no CPU implementation")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_images = int(self.sil_imgs.shape[0])
+        self.image_size = int(self.sil_imgs.shape[2])
+        self.use_unity_prior = bool(use_unity_prior)
+        self.batch_size = int(batch_size)
+        self.n_betas = K.N_BETAS
+        self.shape_family_list = np.array(shape_family)
+        self.resident_targets = resident_targets
+
+        if constants is None:
+            constants = (model_io.load_from_smalify_data(data_root, int(shape_family)) if data_root
+                         else model_io.load_asset(shape_family=int(shape_family)))
+        self.constants = constants
+        dev = self.device
+        if self.use_unity_prior:
+            mean = torch.from_numpy(constants.unity_mean).float().to(dev)
+            self.mean_betas = mean.clone()
+            self.betas_prec = torch.from_numpy(constants.unity_prec).float().to(dev)
+            self.betas = nn.Parameter(mean[:20].clone())
+            self.log_beta_scales = nn.Parameter(mean[20:].clone())
+        else:
+            self.mean_betas = torch.from_numpy(constants.cluster_mean).float().to(dev)
+            self.betas_prec = torch.from_numpy(constants.cluster_prec).float().to(dev)
+            self.betas = nn.Parameter(self.mean_betas.clone())
+            self.log_beta_scales = nn.Parameter(torch.zeros(self.num_images, 6, device=dev), requires_grad=False)
+        self._zero_logscale = torch.zeros(6, device=dev)
+
+        n = self.num_images
+        init = torch.tensor(K.GLOBAL_ROT_INIT, dtype=torch.float32, device=dev)
+        self.global_rotation = nn.Parameter(init[None].repeat(n, 1))
+        self.trans = nn.Parameter(torch.zeros(n, 3, device=dev))
+        self.joint_rotations = nn.Parameter(torch.zeros(n, K.N_POSE, 3, device=dev))
+        self.global_mask = torch.ones(1, 3, device=dev)
+        self.rotation_mask = torch.ones(K.N_POSE, 3, device=dev)
+
+        self.faces = torch.from_numpy(np.asarray(constants.faces).astype(np.int64)).to(dev)
+        self._handle = _cabi.Handle(constants, self.device.index, n, self.image_size, self.use_unity_prior)
+        self._grad_ws = {
+            "betas": torch.zeros(20, device=dev), "log_beta_scales": torch.zeros(6, device=dev),
+            "global_rotation": torch.zeros(n, 3, device=dev), "joint_rotations": torch.zeros(n, K.N_POSE, 3, device=dev),
+            "trans": torch.zeros(n, 3, device=dev)}
+        self._windows_for = None
+        self._masks_sent = None
+        self._vis_sent = None
+        # host copies in the layout the library takes (uint8 masks, float32 joints)
+        self._sil_u8 = (self.sil_imgs.reshape(n, self.image_size, self.image_size) > 0.5).to(torch.uint8).contiguous()
+        self._joints_f32 = self.target_joints.reshape(n, K.N_KEYPOINTS, 2).float().contiguous()
+        if self.device.type == "cuda":
+            self._sil_u8 = self._sil_u8.pin_memory() if not self._sil_u8.is_cuda else self._sil_u8
+            self._joints_f32 = self._joints_f32.pin_memory() if not self._joints_f32.is_cuda else self._joints_f32
+        self._upload_targets(0, n)
+
+    # ------------------------------------------------------------------
+    def _lbs_dev(self):
+        return self.log_beta_scales if self.use_unity_prior else self._zero_logscale
+
+    def _vis_u8(self, a, n):
+        return self.target_visibility[a:a + n].reshape(n, K.N_KEYPOINTS).to(torch.uint8).contiguous()
+
+    def _upload_targets(self, a, n):
+        h = self._handle
+        vis = self._vis_u8(a, n)
+        from_host = 0 if self._sil_u8.is_cuda else 1
+        if from_host:
+            vis = vis.cpu()
+            joints, sil = self._joints_f32[a:a + n], self._sil_u8[a:a + n]
+        else:
+            vis = vis.to(self.device)
+            joints, sil = self._joints_f32[a:a + n], self._sil_u8[a:a + n]
+        h.check(h.lib.smalfit_set_targets(h.h, a, n, _ptr(sil), _ptr(joints), _ptr(vis), from_host,
+                                          _stream(self.device)), "smalfit_set_targets")
+        if from_host:
+            torch.cuda.current_stream(self.device).synchronize()     # vis is a temporary host tensor
+
+    def _sync_visibility(self, a, n):
+        vis = self._vis_u8(a, n).to(self.device, non_blocking=False)
+        h = self._handle
+        h.check(h.lib.smalfit_set_visibility(h.h, a, n, _ptr(vis), 0, _stream(self.device)), "smalfit_set_visibility")
+        self._vis_keepalive = vis
+
+    def _sync_masks(self):
+        key = (self.global_mask._version, self.global_mask.data_ptr(), self.rotation_mask._version, self.rotation_mask.data_ptr())
+        if key == self._masks_sent:
+            return
+        gm = np.ascontiguousarray(self.global_mask.detach().cpu().numpy().reshape(3), dtype=np.float32)
+        rm = np.ascontiguousarray(self.rotation_mask.detach().cpu().numpy().reshape(K.N_POSE * 3), dtype=np.float32)
+        h = self._handle
+        fp = ctypes.POINTER(ctypes.c_float)
+        h.check(h.lib.smalfit_set_masks(h.h, gm.ctypes.data_as(fp), rm.ctypes.data_as(fp)), "smalfit_set_masks")
+        self._masks_sent = key
+
+    def set_windows(self, frames_per_window):
+        """frames_per_window[i] = size of the window frame i is optimised in (the B of the
+        reference's mean() reductions)."""
+        arr = np.ascontiguousarray(frames_per_window, dtype=np.int32)
+        h = self._handle
+        h.check(h.lib.smalfit_set_windows(h.h, arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(arr)),
+                "smalfit_set_windows")
+
+    def _set_window_for(self, a, n):
+        if self._windows_for is None:
+            self._windows_for = np.full(self.num_images, self.num_images, dtype=np.int32)
+            self._windows_for[:] = -1
+        if not np.all(self._windows_for[a:a + n] == n):
+            self._windows_for[a:a + n] = n
+            arr = np.where(self._windows_for > 0, self._windows_for, self.num_images).astype(np.int32)
+            self.set_windows(arr)
+
+    # ------------------------------------------------------------------
+    def forward(self, batch_range, weights, stage_id):
+        """SMALFitter.forward (smal_fitter.py:107-175): returns (loss, objs)."""
+        a, n = _contiguous_range(batch_range)
+        self._sync_masks()
+        self._set_window_for(a, n)
+        if self.resident_targets:
+            self._sync_visibility(a, n)
+        else:
+            self._upload_targets(a, n)         # the per-call H2D copy of smal_fitter.py:118-120
+        loss, terms = _LossGradFn.apply(self, a, n, [float(w) for w in weights], self.betas, self.log_beta_scales,
+                                        self.global_rotation, self.joint_rotations, self.trans)
+        w_j2d, w_reproj, w_betas, w_pose, _w_limit, w_splay = [float(w) for w in weights]
+        objs = {}
+        if w_j2d > 0:
+            objs["joint"] = terms[_cabi.L_JOINT]
+        if w_pose > 0:
+            objs["pose"] = terms[_cabi.L_POSE]
+        if w_splay > 0:
+            objs["splay"] = terms[_cabi.L_SPLAY]
+        if w_betas > 0:
+            objs["betas"] = terms[_cabi.L_BETAS]
+        if w_reproj > 0:
+            objs["sil_reproj"] = terms[_cabi.L_SIL]
+        return loss, objs
+
+    def get_temporal(self, w_temp):
+        """smal_fitter.py:177-190: returns (joint_loss, global_loss, trans_loss)."""
+        self._sync_masks()
+        return _TemporalFn.apply(self, float(w_temp), self.global_rotation, self.joint_rotations, self.trans)
+
+    # ------------------------------------------------------------------
+    @torch.no_grad()
+    def render(self, batch_range=None):
+        """Soft silhouettes (B,1,S,S) and projected keypoints (B,25,2) of the current
+        parameters (Renderer.forward's first two outputs, p3d_renderer.py:61-74)."""
+        a, n = _contiguous_range(batch_range if batch_range is not None else range(self.num_images))
+        self._sync_masks()
+        S = self.image_size
+        sil = torch.empty(n, 1, S, S, device=self.device)
+        kp = torch.empty(n, K.N_KEYPOINTS, 2, device=self.device)
+        params = _tensors(self.betas, self._lbs_dev(), self.global_rotation, self.joint_rotations, self.trans)
+        h = self._handle
+        h.check(h.lib.smalfit_render(h.h, ctypes.byref(params), a, n, _ptr(sil), _ptr(kp), _stream(self.device)),
+                "smalfit_render")
+        return sil, kp
+
+    @torch.no_grad()
+    def vertices(self, batch_range=None):
+        a, n = _contiguous_range(batch_range if batch_range is not None else range(self.num_images))
+        self._sync_masks()
+        v = torch.empty(n, self.constants.v_template.shape[0], 3, device=self.device)
+        params = _tensors(self.betas, self._lbs_dev(), self.global_rotation, self.joint_rotations, self.trans)
+        h = self._handle
+        h.check(h.lib.smalfit_vertices(h.h, ctypes.byref(params), a, n, _ptr(v), _stream(self.device)), "smalfit_vertices")
+        return v
+
+    def counters(self):
+        arr = (ctypes.c_int64 * 4)()
+        h = self._handle
+        h.check(h.lib.smalfit_counters(h.h, arr, _stream(self.device)), "smalfit_counters")
+        return dict(capped_pixels=arr[0], spilled_pixels=arr[1], raster_launches=arr[2], launches=arr[3])
+
+    # ------------------------------------------------------------------
+    def export_parameters(self, frame_id):
+        """The per-frame dict ImageExporter pickles (smal_fitter.py:213-219,268)."""
+        with torch.no_grad():
+            return {
+                "global_rotation": (self.global_rotation[frame_id] * self.global_mask[0]).cpu().numpy(),
+                "joint_rotations": (self.joint_rotations[frame_id] * self.rotation_mask).cpu().numpy(),
+                "betas": self.betas.detach().cpu().numpy(),
+                "log_betascale": (self.log_beta_scales if self.use_unity_prior else self.log_beta_scales[frame_id]).detach().cpu().numpy(),
+                "trans": self.trans[frame_id].detach().cpu().numpy(),
+            }
+
+    def load_checkpoint(self, checkpoint_path, epoch):
+        """smal_fitter.py:192-207: per-frame pickles; betas / scales are averaged over frames."""
+        beta_list, scale_list = [], []
+        with torch.no_grad():
+            for frame_id in range(self.num_images):
+                param_file = os.path.join(checkpoint_path, "{0:04}".format(frame_id), "{0}.pkl".format(epoch))
+                with open(param_file, "rb") as f:
+                    p = pkl.load(f)
+                self.global_rotation[frame_id] = torch.from_numpy(p["global_rotation"]).float().to(self.device)
+                self.joint_rotations[frame_id] = torch.from_numpy(p["joint_rotations"]).float().to(self.device).view(K.N_POSE, 3)
+                self.trans[frame_id] = torch.from_numpy(p["trans"]).float().to(self.device)
+                beta_list.append(p["betas"][:self.n_betas])
+                scale_list.append(p["log_betascale"])
+        self.betas = nn.Parameter(torch.from_numpy(np.mean(beta_list, axis=0)).float().to(self.device))
+        self.log_beta_scales = nn.Parameter(torch.from_numpy(np.mean(scale_list, axis=0)).float().to(self.device))
+
+
+class FusedFit:
+    """One call = one epoch of optimize_to_joints.py:117-137 on flat device buffers:
+    loss + gradients of every window, temporal term, [all-reduce of the flat gradient when the
+    frames are sharded over ranks], Adam.  Parameters stay the fitter's nn.Parameters
+    (re-pointed at slices of one flat buffer)."""
+
+    SIZES = lambda n: (20, 6, n * 3, n * K.N_POSE * 3, n * 3)  # noqa: E731
+
+    def __init__(self, fitter: SMALFitter, window_size: int | None = None, frame_shard=None, process_group=None):
+        self.f = fitter
+        n = fitter.num_images
+        dev = fitter.device
+        if not fitter.use_unity_prior:
+            raise NotImplementedError("FusedFit supports the unity-prior (shared log_beta_scales) configuration")
+        self.sizes = FusedFit.SIZES(n)
+        total = sum(self.sizes)
+        self.flat_p = torch.empty(total, device=dev)
+        self.flat_g = torch.zeros(total, device=dev)
+        self.flat_m = torch.zeros(total, device=dev)
+        self.flat_v = torch.zeros(total, device=dev)
+        names = ("betas", "log_beta_scales", "global_rotation", "joint_rotations", "trans")
+        shapes = ((20,), (6,), (n, 3), (n, K.N_POSE, 3), (n, 3))
+        off = 0
+        self.views = {}
+        with torch.no_grad():
+            for name, size, shape in zip(names, self.sizes, shapes):
+                par = getattr(fitter, name)
+                self.flat_p[off:off + size] = par.detach().reshape(-1)
+                par.data = self.flat_p[off:off + size].view(shape)
+                self.views[name] = tuple(buf[off:off + size] for buf in (self.flat_p, self.flat_g, self.flat_m, self.flat_v))
+                off += size
+        self.window = window_size or n
+        wins = np.empty(n, dtype=np.int32)
+        for j in range(0, n, self.window):
+            wins[j:j + self.window] = min(self.window, n - j)
+        fitter.set_windows(wins)
+        fitter._windows_for = wins.copy()
+        self.n_windows = (n + self.window - 1) // self.window
+        self.shard = frame_shard or (0, n)
+        self.group = process_group
+        self.terms = torch.zeros(8, device=dev)
+        self.temporal_terms = torch.zeros(3, device=dev)
+        self.step_count = 0
+        self._graph = None
+        self._graph_key = None
+        self._warmed = False
+
+    def _t(self, idx):
+        names = ("betas", "log_beta_scales", "global_rotation", "joint_rotations", "trans")
+        return _tensors(*(self.views[k][idx] for k in names))
+
+    def reset_optimizer(self):
+        """Fresh Adam state, as a new torch.optim.Adam per stage (optimize_to_joints.py:96)."""
+        self.flat_m.zero_()
+        self.flat_v.zero_()
+        self.step_count = 0
+        h = self.f._handle
+        h.check(h.lib.smalfit_adam_reset(h.h, _stream(self.f.device)), "smalfit_adam_reset")
+        self._graph = None
+
+    def _enqueue(self, weights, w_temp, lr, train, device_step: bool):
+        f = self.f
+        h = f._handle
+        st = _stream(f.device)
+        a, b = self.shard
+        sharded = self.group is not None
+        if sharded:
+            self.flat_g.zero_()
+        params, grads = self._t(0), self._t(1)
+        rank0 = (not sharded) or torch.distributed.get_rank(self.group) == 0
+        h.check(h.lib.smalfit_loss_grad(h.h, ctypes.byref(params), a, b - a, _weights6(weights),
+                                        self.n_windows if rank0 else 0, ctypes.byref(grads), _ptr(self.terms), st),
+                "smalfit_loss_grad")
+        if sharded:
+            torch.distributed.all_reduce(self.flat_g, group=self.group)
+            torch.distributed.all_reduce(self.terms, group=self.group)
+        h.check(h.lib.smalfit_temporal(h.h, ctypes.byref(params), f.num_images, float(w_temp), ctypes.byref(grads),
+                                       _ptr(self.temporal_terms), st), "smalfit_temporal")
+        tr = (ctypes.c_int32 * 5)(*[int(x) for x in train])
+        m, v = self._t(2), self._t(3)
+        h.check(h.lib.smalfit_adam_step(h.h, ctypes.byref(params), ctypes.byref(grads), ctypes.byref(m), ctypes.byref(v),
+                                        f.num_images, tr, float(lr), K.ADAM_BETAS[0], K.ADAM_BETAS[1], K.ADAM_EPS,
+                                        0 if device_step else self.step_count, st), "smalfit_adam_step")
+
+    def step(self, weights, w_temp, lr, train=(1, 1, 1, 1, 1), use_graph: bool = False):
+        """Returns nothing; self.terms / self.temporal_terms hold the loss terms on the device."""
+        self.step_count += 1
+        f = self.f
+        f._sync_masks()
+        if not use_graph or not self._warmed:
+            # eager launch (also the first call: loads every kernel before a capture)
+            self._enqueue(weights, w_temp, lr, train, device_step=True)
+            self._warmed = True
+            return
+        key = (tuple(float(w) for w in weights), float(w_temp), float(lr), tuple(int(t) for t in train))
+        if self._graph is None or self._graph_key != key:
+            # warm-up on a side stream, then capture
+            s = torch.cuda.Stream(device=f.device)
+            s.wait_stream(torch.cuda.current_stream(f.device))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(s):
+                with torch.cuda.graph(g, stream=s):
+                    self._enqueue(weights, w_temp, lr, train, device_step=True)
+            torch.cuda.current_stream(f.device).wait_stream(s)
+            self._graph, self._graph_key = g, key
+        self._graph.replay()
+
+    def total_loss(self) -> torch.Tensor:
+        return self.terms[_cabi.L_TOTAL] + self.temporal_terms.sum()

@@ -1,0 +1,124 @@
+"""GPU parity: libsmalfit (through the SMALFitter / C-ABI surface) against the CPU oracle
+on identical seeded inputs.  Tolerances: loss terms rel 1e-5-class (fp32 kernels
+vs fp64 oracle: 2e-5), gradients 1e-4 of the tensor's max magnitude, silhouettes 2e-5 abs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import smal_oracle as O
+from smalify_b200 import constants as K
+from smalify_b200 import synthetic
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+S_SMALL = 64
+N_SMALL = 3
+STAGE1 = K.STAGE_SCHEDULE[1][:6]
+STAGE0 = K.STAGE_SCHEDULE[0][:6]
+
+
+@pytest.fixture(scope="module")
+def seq(constants, oracle64):
+    data, gt = synthetic.make_sequence(constants, N_SMALL, S_SMALL, H.oracle_renderer(oracle64, S_SMALL), seed=0)
+    return data, gt
+
+
+@pytest.fixture(scope="module")
+def fitter(constants, seq):
+    from smalify_b200.smal_fitter import SMALFitter
+    data, _ = seq
+    return SMALFitter("cuda", data, N_SMALL, 1, True, constants=constants)
+
+
+def _states(oracle64, gt):
+    init = O.FitParams.initial(oracle64, N_SMALL, K.GLOBAL_ROT_INIT)
+    mid = H.perturbed_params(oracle64, gt, seed=5)
+    near = H.perturbed_params(oracle64, gt, seed=6, scale=0.2)
+    return {"init": init, "mid": mid, "near": near}
+
+
+def test_vertices_and_keypoints(fitter, oracle64, seq):
+    _, gt = seq
+    for name, p in _states(oracle64, gt).items():
+        H.load_params_into(fitter, p)
+        v = fitter.vertices().cpu().double()
+        _, kp = fitter.render()
+        theta = torch.cat([p.global_rotation[:, None], p.joint_rotations], 1)
+        vo, jo, _ = O.smal_forward(oracle64, p.betas.expand(N_SMALL, 20), theta, p.log_beta_scales.expand(N_SMALL, 6))
+        vo = vo + p.trans[:, None]
+        jo = jo + p.trans[:, None]
+        assert (v - vo).abs().max() < 2e-6, name
+        kpo = O.project_points_screen(jo[:, list(O.CANONICAL)], S_SMALL)
+        assert (kp.cpu().double() - kpo).abs().max() < 2e-4, name      # pixels
+
+
+def test_silhouette(fitter, oracle64, seq):
+    _, gt = seq
+    for name, p in _states(oracle64, gt).items():
+        H.load_params_into(fitter, p)
+        alpha, _ = fitter.render()
+        theta = torch.cat([p.global_rotation[:, None], p.joint_rotations], 1)
+        vo, _, _ = O.smal_forward(oracle64, p.betas.expand(N_SMALL, 20), theta, p.log_beta_scales.expand(N_SMALL, 6))
+        ao = O.render_silhouettes(oracle64, vo + p.trans[:, None], S_SMALL)
+        err = (alpha.cpu().double() - ao).abs()
+        # fp32 pz can reorder two fragments at the K=100 cut in a handful of pixels
+        assert float((err > 2e-5).double().mean()) < 2e-3, (name, float(err.max()))
+        assert float(err.mean()) < 1e-5, name
+    c = fitter.counters()
+    assert c["spilled_pixels"] >= 0
+
+
+@pytest.mark.parametrize("weights,label", [(STAGE0, "stage0"), (STAGE1, "stage1"), (K.STAGE_SCHEDULE[2][:6], "stage2")])
+def test_loss_and_gradients(fitter, oracle64, seq, weights, label):
+    data, gt = seq
+    for name, p in _states(oracle64, gt).items():
+        lo, objs_o, go = H.oracle_loss_and_grads(oracle64, p, data, range(N_SMALL), weights, S_SMALL)
+        H.load_params_into(fitter, p)
+        for t in fitter.parameters():
+            t.grad = None
+            t.requires_grad_(True)
+        loss, objs = fitter(list(range(N_SMALL)), weights, 1)
+        loss.backward()
+        assert abs(float(loss) - lo) <= 2e-5 * abs(lo) + 1e-6, (label, name, float(loss), lo)
+        for k, v in objs_o.items():
+            assert abs(float(objs[k]) - v) <= 3e-5 * abs(v) + 1e-6, (label, name, k, float(objs[k]), v)
+        for k in ("global_rotation", "trans", "joint_rotations", "betas", "log_beta_scales"):
+            g = getattr(fitter, k).grad
+            if float(go[k].abs().max()) == 0.0:
+                assert g is None or float(g.abs().max()) < 1e-6
+                continue
+            assert H.rel_err(g, go[k]) < 1e-4, (label, name, k, H.rel_err(g, go[k]))
+
+
+def test_windows_and_temporal(fitter, oracle64, seq):
+    data, gt = seq
+    p = H.perturbed_params(oracle64, gt, seed=9)
+    w = STAGE1
+    for t in p.tensors():
+        t.requires_grad_(True)
+        t.grad = None
+    rgb, sil, joints, vis = data
+    total = O.epoch_loss(oracle64, p, sil, joints, vis, 2, w, 100.0, S_SMALL)      # windows of 2 + 1 frames
+    total.backward()
+    H.load_params_into(fitter, p)
+    for t in fitter.parameters():
+        t.grad = None
+        t.requires_grad_(True)
+    acc = 0
+    for j in range(0, N_SMALL, 2):
+        loss, _ = fitter(list(range(j, min(N_SMALL, j + 2))), w, 1)
+        acc = acc + loss.mean()
+    jl, gl, tl = fitter.get_temporal(100.0)
+    acc = acc + jl + gl + tl
+    acc.backward()
+    assert abs(float(acc) - float(total)) <= 2e-5 * abs(float(total))
+    for k in ("global_rotation", "trans", "joint_rotations", "betas", "log_beta_scales"):
+        assert H.rel_err(getattr(fitter, k).grad, getattr(p, k).grad) < 1e-4, k
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from smalify_b200 import _cabi
+    with pytest.raises(_cabi.SmalfitError):
+        _cabi.load_library(str(tmp_path / "libsmalfit_missing.so"))
