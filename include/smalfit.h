@@ -188,6 +188,13 @@ SMALFIT_API int smalfit_vertices(smalfit_t h, const smalfit_tensors_t* params, i
                      float* verts, void* stream);
 
 /* ---- diagnostics ------------------------------------------------------- */
+/* Per-phase device times of the most recent smalfit_loss_grad (CUDA events on the caller's
+ * stream; do not enable while capturing a CUDA graph).  ms[0] shape+frame forward,
+ * [1] face rectangles + vertex staging copy, [2] raster forward, [3] raster backward,
+ * [4] frame backward, [5] shape backward + finalize, [6] whole call. */
+SMALFIT_API int smalfit_set_profiling(smalfit_t h, int enable);
+SMALFIT_API int smalfit_get_profile(smalfit_t h, float ms[8]);
+
 /* counters[0] = pixels whose fragment count exceeded the K=100 cap (last call)
  * counters[1] = pixels whose fragment count exceeded the selection buffer (inexact!)
  * counters[2] = raster kernel launches since create, counters[3] = all kernel launches */

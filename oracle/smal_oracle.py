@@ -340,7 +340,7 @@ class FitParams:
 
 
 def fitter_forward(m: OracleModel, p: FitParams, sil, target_joints, visibility, batch_range, weights,
-                   image_size: int, return_aux: bool = False):
+                   image_size: int, return_aux: bool = False, silhouette_fn=None):
     """SMALFitter.forward.  sil (N,1,S,S), target_joints (N,25,2) (row,col),
     visibility (N,25) {0,1}.  weights = (w_j2d, w_reproj, w_betas, w_pose, w_limit, w_splay)."""
     w_j2d, w_reproj, w_betas, w_pose, _w_limit, w_splay = [float(w) for w in weights]
@@ -373,7 +373,7 @@ def fitter_forward(m: OracleModel, p: FitParams, sil, target_joints, visibility,
         res = (allb - m.shape_mean[None]) @ m.shape_prec
         objs["betas"] = w_betas * torch.mean(res ** 2)                           # :162-171
     if w_reproj > 0 or return_aux:
-        sil_r = render_silhouettes(m, verts, image_size)
+        sil_r = (silhouette_fn or render_silhouettes)(m, verts, image_size)
         aux["silhouettes"] = sil_r
         if w_reproj > 0:
             objs["sil_reproj"] = w_reproj * torch.mean(torch.abs(sil_r - sil[br].to(m.dtype)))   # :172-173
@@ -397,12 +397,13 @@ def temporal_terms(p: FitParams, w_temp: float):
     return jl, gl, tl
 
 
-def epoch_loss(m, p, sil, tj, vis, window, weights, w_temp, image_size):
+def epoch_loss(m, p, sil, tj, vis, window, weights, w_temp, image_size, silhouette_fn=None):
     """One epoch of optimize_to_joints.py:117-135: sum of window losses + temporal."""
     n = p.global_rotation.shape[0]
     acc = torch.zeros((), dtype=m.dtype)
     for j in range(0, n, window):
-        loss, _ = fitter_forward(m, p, sil, tj, vis, range(j, min(n, j + window)), weights, image_size)
+        loss, _ = fitter_forward(m, p, sil, tj, vis, range(j, min(n, j + window)), weights, image_size,
+                                 silhouette_fn=silhouette_fn)
         acc = acc + loss
     jl, gl, tl = temporal_terms(p, w_temp)
     return acc + jl + gl + tl
@@ -418,7 +419,7 @@ def stage_visibility(visibility: torch.Tensor, stage_id: int) -> torch.Tensor:
 
 
 def fit(m, p: FitParams, sil, tj, vis, window, schedule, image_size, allow_limb_scaling=True,
-        iters_override=None, callback=None):
+        iters_override=None, callback=None, silhouette_fn=None):
     """The stage loop of optimize_to_joints.py:90-137 with torch.optim.Adam."""
     for stage_id, row in enumerate(schedule):
         weights, w_temp, iters, lr = row[:6], row[6], int(row[7]), row[8]
@@ -437,7 +438,7 @@ def fit(m, p: FitParams, sil, tj, vis, window, schedule, image_size, allow_limb_
         v = stage_visibility(vis, stage_id)
         for it in range(iters):
             opt.zero_grad()
-            loss = epoch_loss(m, p, sil, tj, v, window, weights, w_temp, image_size)
+            loss = epoch_loss(m, p, sil, tj, v, window, weights, w_temp, image_size, silhouette_fn=silhouette_fn)
             loss.backward()
             opt.step()
             if callback is not None:

@@ -83,6 +83,8 @@ def load_library(path: str | None = None) -> C.CDLL:
         "smalfit_adam_reset": ([vp, vp], C.c_int),
         "smalfit_render": ([vp, TP, C.c_int, C.c_int, vp, vp, vp], C.c_int),
         "smalfit_vertices": ([vp, TP, C.c_int, C.c_int, vp, vp], C.c_int),
+        "smalfit_set_profiling": ([vp, C.c_int], C.c_int),
+        "smalfit_get_profile": ([vp, _f32p], C.c_int),
         "smalfit_counters": ([vp, C.POINTER(C.c_int64), vp], C.c_int),
     }
     for name, (args, res) in protos.items():
@@ -98,7 +100,7 @@ EXPORTED_SYMBOLS = (
     "smalfit_abi_version", "smalfit_create", "smalfit_destroy", "smalfit_last_error", "smalfit_set_targets",
     "smalfit_set_visibility", "smalfit_set_masks", "smalfit_set_windows", "smalfit_set_per_frame_shapes",
     "smalfit_loss_grad", "smalfit_temporal", "smalfit_adam_step", "smalfit_adam_reset", "smalfit_render", "smalfit_vertices",
-    "smalfit_counters",
+    "smalfit_counters", "smalfit_set_profiling", "smalfit_get_profile",
 )
 
 

@@ -61,6 +61,10 @@ struct smalfit_ctx {
     DevPool pool;
     std::string error;
     long long n_raster_launches = 0, n_launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[8] = {};
+    bool ev_valid = false;
+    void mark(int i, cudaStream_t st) { if (profiling) cudaEventRecord(ev[i], st); }
 };
 
 namespace {
@@ -255,6 +259,7 @@ void smalfit_destroy(smalfit_t h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     h->pool.release();
+    for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
 }
 
@@ -312,15 +317,22 @@ int smalfit_set_windows(smalfit_t h, const int32_t* fpw, int n) {
 
 static int run_forward(smalfit_t h, const Params& p, int frame0, int n, Weights wt, bool raster, float* alpha_out,
                        float* verts_out, cudaStream_t st) {
+    h->mark(0, st);
     launch_shape_forward(h->m, h->w, p, st);
     launch_frame_forward(h->m, h->w, p, frame0, n, wt, verts_out, st);
     h->n_launches += 2;
+    h->mark(1, st);
     if (raster) {
         launch_face_rects(h->m, h->w, frame0, n, st);
+        launch_ndc_soa(h->m, h->w, h->ndc_soa, frame0, n, st);
+        h->mark(2, st);
         launch_raster_forward(h->m, h->w, h->sc, h->ndc_soa, frame0, n, wt, alpha_out, h->raster_ctas, st);
         h->n_launches += 3;
         h->n_raster_launches += 1;
+    } else {
+        h->mark(2, st);
     }
+    h->mark(3, st);
     return check_launch(h, "forward kernels");
 }
 
@@ -340,9 +352,13 @@ int smalfit_loss_grad(smalfit_t h, const smalfit_tensors_t* params, int frame0, 
     int rc = run_forward(h, p, frame0, n, wt, raster, nullptr, nullptr, st);
     if (rc) return rc;
     if (raster) { launch_raster_backward(h->m, h->w, frame0, n, st); h->n_launches += 1; h->n_raster_launches += 1; }
+    h->mark(4, st);
     launch_frame_backward(h->m, h->w, p, g, frame0, n, wt, st);
+    h->mark(5, st);
     launch_shape_backward(h->m, h->w, p, g, frame0, n, wt, prior_windows < 0 ? 0 : prior_windows, loss_terms, st);
     h->n_launches += 3;
+    h->mark(6, st);
+    if (h->profiling) h->ev_valid = true;
     return check_launch(h, "backward kernels");
 }
 
@@ -408,6 +424,35 @@ int smalfit_vertices(smalfit_t h, const smalfit_tensors_t* params, int frame0, i
     cudaSetDevice(h->device);
     const Weights wt{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     return run_forward(h, to_params(params), frame0, n, wt, false, nullptr, verts, (cudaStream_t)stream);
+}
+
+int smalfit_set_profiling(smalfit_t h, int enable) {
+    if (!h) return SMALFIT_EINVAL;
+    cudaSetDevice(h->device);
+    if (enable && !h->ev[0]) {
+        for (int i = 0; i < 8; ++i) {
+            cudaError_t e = cudaEventCreate(&h->ev[i]);
+            if (e != cudaSuccess) return check_cuda(h, e, "cudaEventCreate");
+        }
+    }
+    h->profiling = enable != 0;
+    h->ev_valid = false;
+    return SMALFIT_OK;
+}
+
+int smalfit_get_profile(smalfit_t h, float ms[8]) {
+    if (!h || !ms) return SMALFIT_EINVAL;
+    if (!h->ev_valid) return fail(h, SMALFIT_ESTATE, "smalfit_get_profile: no profiled smalfit_loss_grad call yet");
+    cudaSetDevice(h->device);
+    cudaError_t e = cudaEventSynchronize(h->ev[6]);
+    if (e != cudaSuccess) return check_cuda(h, e, "cudaEventSynchronize");
+    for (int i = 0; i < 6; ++i) {
+        e = cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]);
+        if (e != cudaSuccess) return check_cuda(h, e, "cudaEventElapsedTime");
+    }
+    e = cudaEventElapsedTime(&ms[6], h->ev[0], h->ev[6]);
+    ms[7] = 0.f;
+    return check_cuda(h, e, "cudaEventElapsedTime");
 }
 
 int smalfit_counters(smalfit_t h, int64_t counters[4], void* stream) {

@@ -586,10 +586,13 @@ __global__ void __launch_bounds__(256) ndc_soa_kernel(ModelDev m, Workspace w, i
     o[v] = a.x; o[m.Vp + v] = a.y; o[2 * m.Vp + v] = a.z;
 }
 
-void launch_raster_forward(const ModelDev& m, const Workspace& w, const RasterScratch& sc, float* ndc_soa,
-                              int frame0, int n, Weights wt, float* alpha_out, int n_ctas, cudaStream_t st) {
+void launch_ndc_soa(const ModelDev& m, const Workspace& w, float* ndc_soa, int frame0, int n, cudaStream_t st) {
     dim3 g((m.Vp + 255) / 256, n);
     ndc_soa_kernel<<<g, 256, 0, st>>>(m, w, frame0, ndc_soa);
+}
+
+void launch_raster_forward(const ModelDev& m, const Workspace& w, const RasterScratch& sc, float* ndc_soa,
+                           int frame0, int n, Weights wt, float* alpha_out, int n_ctas, cudaStream_t st) {
     cudaMemsetAsync(w.work_counter, 0, sizeof(unsigned), st);
     raster_forward_kernel<<<n_ctas, RAST_THREADS, raster_smem_bytes(m), st>>>(m, w, sc, frame0, n, wt, ndc_soa, alpha_out);
 }

@@ -101,6 +101,7 @@ void launch_shape_forward(const ModelDev& m, const Workspace& w, const Params& p
 void launch_frame_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n,
                           Weights wt, float* verts_out, cudaStream_t st);
 void launch_face_rects(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st);
+void launch_ndc_soa(const ModelDev& m, const Workspace& w, float* ndc_soa, int frame0, int n, cudaStream_t st);
 void launch_raster_forward(const ModelDev& m, const Workspace& w, const RasterScratch& sc, float* ndc_soa,
                            int frame0, int n, Weights wt, float* alpha_out, int n_ctas, cudaStream_t st);
 void launch_raster_backward(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st);

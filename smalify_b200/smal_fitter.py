@@ -304,6 +304,18 @@ class SMALFitter(nn.Module):
         h.check(h.lib.smalfit_vertices(h.h, ctypes.byref(params), a, n, _ptr(v), _stream(self.device)), "smalfit_vertices")
         return v
 
+    def set_profiling(self, enable: bool):
+        h = self._handle
+        h.check(h.lib.smalfit_set_profiling(h.h, int(bool(enable))), "smalfit_set_profiling")
+
+    def profile(self):
+        """Per-phase device milliseconds of the last loss_grad call (see smalfit_get_profile)."""
+        arr = (ctypes.c_float * 8)()
+        h = self._handle
+        h.check(h.lib.smalfit_get_profile(h.h, arr), "smalfit_get_profile")
+        keys = ("pose_forward", "face_rects", "raster_forward", "raster_backward", "frame_backward", "shape_backward", "total")
+        return {k: float(arr[i]) for i, k in enumerate(keys)}
+
     def counters(self):
         arr = (ctypes.c_int64 * 4)()
         h = self._handle
