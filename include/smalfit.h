@@ -196,8 +196,9 @@ SMALFIT_API int smalfit_set_profiling(smalfit_t h, int enable);
 SMALFIT_API int smalfit_get_profile(smalfit_t h, float ms[8]);
 
 /* counters[0] = pixels whose fragment count exceeded the K=100 cap (last call)
- * counters[1] = pixels whose fragment count exceeded the selection buffer (inexact!)
- * counters[2] = raster kernel launches since create, counters[3] = all kernel launches */
+ * counters[1] = of those, pixels whose fragments spilled from shared memory to the global buffer (exact, slower)
+ * counters[2] = (face, tile) entries dropped because a frame's tile pool overflowed (results INEXACT if > 0)
+ * counters[3] = kernel launches since create.  counters[0..2] are reset by the call. */
 SMALFIT_API int smalfit_counters(smalfit_t h, int64_t counters[4], void* stream);
 
 #ifdef __cplusplus

@@ -56,7 +56,7 @@ struct smalfit_ctx {
     AdamState* adam_state = nullptr;
     // mutable target buffers (Workspace holds const views)
     uint8_t* sil = nullptr; float* kp_target = nullptr; uint8_t* vis = nullptr;
-    float* tile_tsum = nullptr; float* inv_window = nullptr; float* gmask = nullptr; float* rmask = nullptr;
+    float* region_tsum = nullptr; float* inv_window = nullptr; float* gmask = nullptr; float* rmask = nullptr;
     bool targets_set = false;
     DevPool pool;
     std::string error;
@@ -109,7 +109,7 @@ int smalfit_abi_version(void) { return SMALFIT_ABI_VERSION; }
 const char* smalfit_last_error(smalfit_t h) { return h ? h->error.c_str() : g_create_error.c_str(); }
 
 int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int image_size, smalfit_t* out) {
-    if (!md || !out || max_frames <= 0 || image_size <= 0 || image_size > 4096)
+    if (!md || !out || max_frames <= 0 || image_size <= 0 || image_size > 1024)
         return fail(nullptr, SMALFIT_EINVAL, "smalfit_create: bad arguments");
     if (md->n_verts <= 0 || md->n_verts > 65535 || md->n_faces <= 0 || md->n_faces > 65504)
         return fail(nullptr, SMALFIT_EINVAL, "smalfit_create: mesh size out of range (V=%d F=%d)", md->n_verts, md->n_faces);
@@ -125,7 +125,7 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
 
     smalfit_ctx* h = new smalfit_ctx();
     h->device = device; h->N = max_frames; h->S = image_size; h->n_sm = prop.multiProcessorCount;
-    h->raster_ctas = 2 * h->n_sm;
+    h->raster_ctas = h->n_sm;
     const int V = md->n_verts, F = md->n_faces;
     ModelDev& m = h->m;
     m.V = V; m.F = F; m.Fp = (F + 31) / 32 * 32; m.Vp = (V + 3) / 4 * 4;
@@ -209,10 +209,14 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     w.gjoint = P.alloc<float>(N * NMJ * 3, true);
     w.kp_proj = P.alloc<float>(N * NKP * 2, true);
     w.face_rect = P.alloc<uint2>(N * m.Fp);
-    w.frame_bounds = P.alloc<int4>(N);
+    w.pool_cap = 8 * m.Fp;
+    w.tile_pool = P.alloc<uint4>(N * (size_t)w.pool_cap);
+    w.tile_off = P.alloc<unsigned>(N * (tiles + 1), true);
+    w.frame_next = P.alloc<unsigned>(N + 1, true);
+    w.frames_done = w.frame_next + N;
     w.pix = P.alloc<uint2>(N * SS, true);
     w.pix_tfid = P.alloc<uint16_t>(N * SS, true);
-    w.tile_l1 = P.alloc<float>(N * tiles, true);
+    w.region_l1 = P.alloc<float>(N * tiles * REGIONS_PER_TILE, true);
     w.face_grad = P.alloc<float>(N * m.Fp * 8, true);
     w.dvs = P.alloc<float>(N * V * 3, true);
     w.gJ = P.alloc<float>(N * NJ * 3, true);
@@ -222,17 +226,18 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     h->sil = P.alloc<uint8_t>(N * SS, true);
     h->kp_target = P.alloc<float>(N * NKP * 2, true);
     h->vis = P.alloc<uint8_t>(N * NKP, true);
-    h->tile_tsum = P.alloc<float>(N * tiles, true);
+    h->region_tsum = P.alloc<float>(N * tiles * REGIONS_PER_TILE, true);
     std::vector<float> ones(N > 102 ? N : 102, 1.0f);
     std::vector<float> invw(N, 1.0f / (float)N);
     h->inv_window = P.upload(invw.data(), N);
     h->gmask = P.upload(ones.data(), 3);
     h->rmask = P.upload(ones.data(), (NJ - 1) * 3);
-    w.sil = h->sil; w.kp_target = h->kp_target; w.vis = h->vis; w.tile_tsum = h->tile_tsum;
+    w.sil = h->sil; w.kp_target = h->kp_target; w.vis = h->vis; w.region_tsum = h->region_tsum;
     w.inv_window = h->inv_window; w.gmask = h->gmask; w.rmask = h->rmask;
     const size_t n_warps = (size_t)h->raster_ctas * RAST_WARPS;
-    w.sl_fid = P.alloc<uint16_t>(n_warps * m.Fp);
-    w.sl_mask = P.alloc<uint32_t>(n_warps * m.Fp);
+    h->sc.ent = P.alloc<uint2>(n_warps * m.Fp);
+    h->sc.mask = P.alloc<unsigned>(n_warps * m.Fp);
+    h->sc.plist = P.alloc<unsigned short>(n_warps * m.Fp);
     h->sc.key = P.alloc<unsigned>(n_warps * m.Fp);
     h->sc.m = P.alloc<float>(n_warps * m.Fp);
     h->sc.fid = P.alloc<unsigned short>(n_warps * m.Fp);
@@ -281,10 +286,10 @@ int smalfit_set_targets(smalfit_t h, int frame0, int n, const uint8_t* sil, cons
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->kp_target + (size_t)frame0 * NKP * 2, joints, (size_t)n * NKP * 2 * sizeof(float), kind, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->vis + (size_t)frame0 * NKP, visibility, (size_t)n * NKP, kind, st);
     if (e != cudaSuccess) return check_cuda(h, e, "smalfit_set_targets copy");
-    launch_tile_tsum(h->w, frame0, n, h->tile_tsum, st);
+    launch_region_tsum(h->w, frame0, n, h->region_tsum, st);
     h->n_launches += 1;
     h->targets_set = true;
-    return check_launch(h, "tile_tsum");
+    return check_launch(h, "region_tsum");
 }
 
 int smalfit_set_visibility(smalfit_t h, int frame0, int n, const uint8_t* visibility, int from_host, void* stream) {
@@ -323,7 +328,7 @@ static int run_forward(smalfit_t h, const Params& p, int frame0, int n, Weights 
     h->n_launches += 2;
     h->mark(1, st);
     if (raster) {
-        launch_face_rects(h->m, h->w, frame0, n, st);
+        launch_bin_faces(h->m, h->w, frame0, n, st);
         launch_ndc_soa(h->m, h->w, h->ndc_soa, frame0, n, st);
         h->mark(2, st);
         launch_raster_forward(h->m, h->w, h->sc, h->ndc_soa, frame0, n, wt, alpha_out, h->raster_ctas, st);
@@ -462,10 +467,10 @@ int smalfit_counters(smalfit_t h, int64_t counters[4], void* stream) {
     unsigned long long host[4] = {0, 0, 0, 0};
     cudaError_t e = cudaMemcpyAsync(host, h->w.counters, sizeof(host), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(h->w.counters, 0, 2 * sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->w.counters, 0, 4 * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return check_cuda(h, e, "smalfit_counters");
     counters[0] = (int64_t)host[0]; counters[1] = (int64_t)host[1];
-    counters[2] = h->n_raster_launches; counters[3] = h->n_launches;
+    counters[2] = (int64_t)host[2]; counters[3] = h->n_launches;
     return SMALFIT_OK;
 }
 

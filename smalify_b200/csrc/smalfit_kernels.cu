@@ -149,7 +149,6 @@ frame_forward_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, 
     const int slot = (w.n_shapes == 1) ? 0 : fr;
     const float* vs = w.v_shaped + (size_t)slot * m.V * 3;
 
-    if (tid == 0) w.frame_bounds[fr] = make_int4(1 << 30, -1, 1 << 30, -1);
     frame_pose_forward(S, m, w, p, fr, slot);
 
     // sparse linear-blend skinning + camera
@@ -234,7 +233,12 @@ void launch_frame_forward(const ModelDev& m, const Workspace& w, const Params& p
 }
 
 // ---------------------------------------------------------------------------
-// face_rects: per (frame, face) pixel rectangle of the blur-expanded bbox
+// bin_faces: one CTA per frame.  Every face gets its conservative pixel rectangle; faces are
+// binned into the 32x32-pixel tiles they touch.  Deterministic (no global atomics): each warp
+// owns a contiguous range of faces, pass 1 counts per (warp, tile), a prefix turns the counts
+// into cursors, pass 2 fills in face order (lanes that hit the same tile in the same step are
+// ranked with match_any).  Pool entry (16 B): face id + its three vertex ids + the rectangle in
+// tile-local pixel coordinates, so the rasteriser needs no further gathers to build its lists.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ FaceSetup load_face(const float4* ndc, ushort4 f4) {
     const float4 a = ndc[f4.x], b = ndc[f4.y], c = ndc[f4.z];
@@ -243,36 +247,110 @@ __device__ __forceinline__ FaceSetup load_face(const float4* ndc, ushort4 f4) {
     return fs;
 }
 
-__global__ void __launch_bounds__(256) face_rect_kernel(ModelDev m, Workspace w, int frame0) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    const int fr = frame0 + blockIdx.y;
-    int c0 = 0xFFFF, c1 = 0, r0 = 0xFFFF, r1 = 0;
-    bool ok = false;
-    if (f < m.Fp) {
-        const FaceSetup fs = load_face(w.ndc + (size_t)fr * m.Vp, m.faces4[f]);
-        int a, b, c, d;
-        ok = face_pixel_rect(fs, w.S, a, b, c, d);
-        if (ok) { c0 = a; c1 = b; r0 = c; r1 = d; }
-        w.face_rect[(size_t)fr * m.Fp + f] = make_uint2((unsigned)c0 | ((unsigned)c1 << 16), (unsigned)r0 | ((unsigned)r1 << 16));
+__global__ void __launch_bounds__(256) bin_faces_kernel(ModelDev m, Workspace w, int frame0) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = w.tiles_x * w.tiles_y;
+    unsigned* cnt = reinterpret_cast<unsigned*>(smem_raw);          // [8][T] counts, then cursors
+    unsigned* tot = cnt + 8 * T;                                    // [T]
+    __shared__ unsigned part[256];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int fr = frame0 + blockIdx.x;
+    const float4* ndc = w.ndc + (size_t)fr * m.Vp;
+    uint2* rects = w.face_rect + (size_t)fr * m.Fp;
+    for (int i = tid; i < 8 * T; i += 256) cnt[i] = 0u;
+    __syncthreads();
+    const int seg = ((m.Fp / 8) + 31) / 32 * 32;
+    const int f_lo = min(wid * seg, m.Fp), f_hi = min(f_lo + seg, m.Fp);
+    // pass 1: rectangles + counts
+    for (int f = f_lo + lane; f < f_hi; f += 32) {
+        const FaceSetup fs = load_face(ndc, m.faces4[f]);
+        int c0, c1, r0, r1;
+        if (face_pixel_rect(fs, w.S, c0, c1, r0, r1)) {
+            rects[f] = make_uint2((unsigned)c0 | ((unsigned)c1 << 16), (unsigned)r0 | ((unsigned)r1 << 16));
+            for (int ty = r0 / TILE_H; ty <= r1 / TILE_H; ++ty)
+                for (int tx = c0 / TILE_W; tx <= c1 / TILE_W; ++tx) atomicAdd(&cnt[wid * T + ty * w.tiles_x + tx], 1u);
+        } else {
+            rects[f] = make_uint2(0xffffu, 0xffffu);
+        }
     }
-    // frame bounds: warp-reduce then one atomic per warp
-    int mc0 = ok ? c0 : (1 << 30), mc1 = ok ? c1 : -1, mr0 = ok ? r0 : (1 << 30), mr1 = ok ? r1 : -1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mc0 = min(mc0, __shfl_xor_sync(0xffffffffu, mc0, o));
-        mc1 = max(mc1, __shfl_xor_sync(0xffffffffu, mc1, o));
-        mr0 = min(mr0, __shfl_xor_sync(0xffffffffu, mr0, o));
-        mr1 = max(mr1, __shfl_xor_sync(0xffffffffu, mr1, o));
+    __syncthreads();
+    // prefix over tiles (blocked: each thread owns a run of consecutive tiles)
+    const int per = (T + 255) / 256;
+    unsigned local = 0;
+    for (int k = 0; k < per; ++k) {
+        const int t = tid * per + k;
+        if (t < T) {
+            unsigned a = 0;
+            for (int q = 0; q < 8; ++q) a += cnt[q * T + t];
+            tot[t] = a;
+            local += a;
+        }
     }
-    if ((threadIdx.x & 31) == 0 && mc1 >= 0) {
-        int* fb = reinterpret_cast<int*>(w.frame_bounds + fr);
-        atomicMin(fb + 0, mc0); atomicMax(fb + 1, mc1); atomicMin(fb + 2, mr0); atomicMax(fb + 3, mr1);
+    part[tid] = local;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned run = 0;
+        for (int i = 0; i < 256; ++i) { const unsigned v = part[i]; part[i] = run; run += v; }
     }
+    __syncthreads();
+    unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
+    unsigned run = part[tid];
+    for (int k = 0; k < per; ++k) {
+        const int t = tid * per + k;
+        if (t < T) {
+            toff[t] = run;
+            unsigned r2 = run;
+            for (int q = 0; q < 8; ++q) { const unsigned c = cnt[q * T + t]; cnt[q * T + t] = r2; r2 += c; }
+            run += tot[t];
+            if (t == T - 1) toff[T] = run;
+        }
+    }
+    __syncthreads();
+    // pass 2: fill, in face order within a warp
+    const unsigned ltmask = lanemask_lt();
+    uint4* pool = w.tile_pool + (size_t)fr * w.pool_cap;
+    unsigned dropped = 0;
+    for (int base = f_lo; base < f_hi; base += 32) {
+        const int f = base + lane;
+        const uint2 r = rects[f];
+        const int c0 = (int)(r.x & 0xffffu), c1 = (int)(r.x >> 16), r0 = (int)(r.y & 0xffffu), r1 = (int)(r.y >> 16);
+        const bool ok = c0 <= c1;
+        const int tc0 = c0 / TILE_W, tr0 = r0 / TILE_H;
+        const int ntw = ok ? (c1 / TILE_W - tc0 + 1) : 0;
+        const int nt = ok ? ntw * (r1 / TILE_H - tr0 + 1) : 0;
+        const int maxnt = __reduce_max_sync(0xffffffffu, nt);
+        const ushort4 f4 = m.faces4[f];
+        for (int k = 0; k < maxnt; ++k) {
+            int t = -1, tx = 0, ty = 0;
+            if (k < nt) { ty = tr0 + k / ntw; tx = tc0 + k % ntw; t = ty * w.tiles_x + tx; }
+            const unsigned mm = __match_any_sync(0xffffffffu, t);
+            unsigned basepos = 0;
+            const int rank = __popc(mm & ltmask);
+            if (t >= 0) basepos = cnt[wid * T + t];
+            __syncwarp();
+            if (t >= 0 && rank == 0) cnt[wid * T + t] = basepos + (unsigned)__popc(mm);
+            __syncwarp();
+            if (t >= 0) {
+                const unsigned pos = basepos + (unsigned)rank;
+                if (pos < (unsigned)w.pool_cap) {
+                    const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+                    const unsigned lc0 = (unsigned)max(c0 - x0, 0), lc1 = (unsigned)min(c1 - x0, TILE_W - 1);
+                    const unsigned lr0 = (unsigned)max(r0 - y0, 0), lr1 = (unsigned)min(r1 - y0, TILE_H - 1);
+                    pool[pos] = make_uint4((unsigned)f | ((unsigned)f4.x << 16), (unsigned)f4.y | ((unsigned)f4.z << 16),
+                                           lc0 | (lc1 << 8) | (lr0 << 16) | (lr1 << 24), 0u);
+                } else {
+                    ++dropped;
+                }
+            }
+        }
+    }
+    if (dropped) atomicAdd(w.counters + 2, (unsigned long long)dropped);
 }
 
-void launch_face_rects(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st) {
-    dim3 grid((m.Fp + 255) / 256, n);
-    face_rect_kernel<<<grid, 256, 0, st>>>(m, w, frame0);
+size_t bin_smem_bytes(const Workspace& w) { return (size_t)9 * w.tiles_x * w.tiles_y * sizeof(unsigned); }
+
+void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st) {
+    bin_faces_kernel<<<n, 256, bin_smem_bytes(w), st>>>(m, w, frame0);
 }
 
 // ---------------------------------------------------------------------------
@@ -305,24 +383,27 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // ---------------------------------------------------------------------------
 // raster_forward
 //
-// Persistent CTAs (8 warps) pull (frame, 16x16 tile) items.  The frame's NDC vertices
-// (x[], y[], z[] as three 15.6 KB arrays) are staged into shared memory with one TMA
-// bulk copy per array and reused for consecutive tiles of the same frame.  Each warp
-// owns an 8x4 pixel region of the tile:
-//   A. scan all face rectangles (coalesced), keep the faces touching the region together
-//      with the 32-bit mask of region pixels inside their rectangle  -> sub-list
-//   B. for each of the 32 pixels: compact the sub-list faces whose bit is set into a
-//      queue; every 32 queued faces are evaluated one per lane (vertices gathered from
-//      shared memory); fragments are appended to the warp's (key, m, face) buffer
-//   C. n <= K: product of all m.  n > K: exact K-th order statistic of (pz, face id) by
-//      warp-cooperative bisection on the key bits, product over the selected set
-//   D. lane q finishes pixel q: alpha, L1 term, coef = dL/dalpha * P / sigma, threshold
+// Persistent CTAs of 16 warps, one per SM.  A CTA keeps one frame's NDC vertices (x[], y[], z[],
+// 15.6 KB each) in shared memory, staged by three TMA bulk copies; its warps are otherwise fully
+// independent: each pulls 8x4-pixel regions of that frame from the frame's counter, and when the
+// frame runs dry the CTA hops to the next frame (the only CTA-wide barrier).  Per region a warp
+//   A. filters the region's tile list (bin_faces) into a sub-list (face id, vertex ids, 32-bit mask
+//      of region pixels inside the face rectangle) held in shared memory,
+//   B. per pixel: compacts the entries whose bit is set and evaluates them one per lane (vertices
+//      gathered from shared memory).  With at most K candidates every fragment is selected: the
+//      running product is kept and the pixel stops once it falls below 2^-25 (alpha == 1.0f exactly,
+//      no gradient).  Otherwise fragments go to the warp's (key, m, face) buffer and
+//   C. n > K: exact K-th order statistic of (pz, face id) by warp-cooperative bisection on the key
+//      bits (keys cached in registers), product over the selected set,
+//   D. lane q finishes pixel q: alpha, L1 term, coef = dL/dalpha * P / sigma, z-threshold.
 // ---------------------------------------------------------------------------
 struct RasterWarpSmem {
     unsigned key[KCAP];
     float mval[KCAP];
     unsigned short fid[KCAP];
-    unsigned short queue[64];
+    uint2 ent[SLCAP];              // (fid | v0 << 16, v1 | v2 << 16)
+    unsigned mask[SLCAP];
+    unsigned short plist[SLCAP];   // per-pixel candidate entries
 };
 
 struct KeyStore {           // fragment buffer: shared memory first, global spill beyond KCAP
@@ -337,17 +418,17 @@ struct KeyStore {           // fragment buffer: shared memory first, global spil
     __device__ __forceinline__ unsigned short f(int i) const { return i < KCAP ? s->fid[i] : gfid[i - KCAP]; }
 };
 
-__device__ __forceinline__ int warp_count_le(const KeyStore& ks, int n, unsigned t, int lane) {
-    int c = 0;
-    for (int i = lane; i < n; i += 32) c += (ks.key(i) <= t) ? 1 : 0;
-    return __reduce_add_sync(0xffffffffu, c);
-}
-
 // Exact K nearest by (key, face id).  Returns the product of m over the selected set and the
 // threshold (tkey, tfid): selected <=> key < tkey || (key == tkey && fid <= tfid).
 __device__ float select_k_nearest(const KeyStore& ks, int n, int lane, unsigned& tkey, unsigned& tfid) {
+    constexpr int NR = KCAP / 32;
+    unsigned kr[NR];                       // keys of the shared-memory part, cached in registers
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { const int i = r * 32 + lane; kr[r] = (i < n) ? ks.s->key[i] : 0xffffffffu; }
     unsigned lo = 0xffffffffu, hi = 0u;
-    for (int i = lane; i < n; i += 32) { const unsigned k = ks.key(i); lo = min(lo, k); hi = max(hi, k); }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { lo = min(lo, kr[r]); if (r * 32 + lane < n) hi = max(hi, kr[r]); }
+    for (int i = KCAP + lane; i < n; i += 32) { const unsigned k = ks.gkey[i - KCAP]; lo = min(lo, k); hi = max(hi, k); }
     lo = __reduce_min_sync(0xffffffffu, lo);
     hi = __reduce_max_sync(0xffffffffu, hi);
     // smallest t with count(key <= t) >= K; stop early when a split of exactly K is found
@@ -355,7 +436,11 @@ __device__ float select_k_nearest(const KeyStore& ks, int n, int lane, unsigned&
     unsigned t = hi;
     while (lo < hi) {
         const unsigned mid = lo + ((hi - lo) >> 1);
-        const int c = warp_count_le(ks, n, mid, lane);
+        int c = 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) c += (kr[r] <= mid) ? 1 : 0;       // padding keys are 0xffffffff > mid
+        for (int i = KCAP + lane; i < n; i += 32) c += (ks.gkey[i - KCAP] <= mid) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
         if (c == RAST_K) { t = mid; exact = true; break; }
         if (c > RAST_K) hi = mid; else lo = mid + 1;
     }
@@ -389,7 +474,7 @@ __device__ float select_k_nearest(const KeyStore& ks, int n, int lane, unsigned&
     return warp_prod(prod);
 }
 
-__global__ void __launch_bounds__(RAST_THREADS, 2)
+__global__ void __launch_bounds__(RAST_THREADS, 1)
 raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int n_frames, Weights wt,
                       const float* ndc_soa /* [N][3][Vp] */, float* alpha_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -398,14 +483,14 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
     float* vz = vy + m.Vp;
     RasterWarpSmem* wsm_all = reinterpret_cast<RasterWarpSmem*>(vz + m.Vp);
     __shared__ unsigned long long bar;
-    __shared__ unsigned s_item;
-    __shared__ float s_l1[RAST_WARPS];
+    __shared__ int s_state;        // 0: frame has work, 1: frame exhausted (skip), 2: everything done
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     RasterWarpSmem& wsm = wsm_all[wid];
     const int gwarp = blockIdx.x * RAST_WARPS + wid;
-    unsigned short* sl_fid = w.sl_fid + (size_t)gwarp * m.Fp;
-    unsigned* sl_mask = w.sl_mask + (size_t)gwarp * m.Fp;
+    uint2* g_ent = sc.ent + (size_t)gwarp * m.Fp;           // sub-lists longer than SLCAP
+    unsigned* g_mask = sc.mask + (size_t)gwarp * m.Fp;
+    unsigned short* g_plist = sc.plist + (size_t)gwarp * m.Fp;
     KeyStore ks;
     ks.s = &wsm;
     ks.gkey = sc.key + (size_t)gwarp * m.Fp; ks.gm = sc.m + (size_t)gwarp * m.Fp; ks.gfid = sc.fid + (size_t)gwarp * m.Fp;
@@ -413,39 +498,24 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     __syncthreads();
     unsigned parity = 0;
-    int cached_frame = -1;
 
     const int S = w.S;
     const float inv_s = 1.f / (float)S;
-    const int tiles = w.tiles_x * w.tiles_y;
-    const int n_items = n_frames * tiles;
+    const int T = w.tiles_x * w.tiles_y;
+    const int R = T * REGIONS_PER_TILE;
     const unsigned ltmask = lanemask_lt();
     unsigned long long n_capped = 0, n_spilled = 0;
+    int cur = (int)(((long long)blockIdx.x * n_frames) / gridDim.x);
 
-    for (;;) {
-        if (tid == 0) s_item = atomicAdd(w.work_counter, 1u);
-        __syncthreads();
-        const unsigned item = s_item;
-        if (item >= (unsigned)n_items) break;
-        const int fr = frame0 + (int)(item / tiles);
-        const int tile = (int)(item % tiles);
-        const int tx = tile % w.tiles_x, ty = tile / w.tiles_x;
-        const int4 fb = w.frame_bounds[fr];
-        const int tx0 = tx * TILE_W, ty0 = ty * TILE_H;
-        const bool tile_empty = (fb.y < tx0) || (fb.x > tx0 + TILE_W - 1) || (fb.w < ty0) || (fb.z > ty0 + TILE_H - 1);
-        if (tile_empty) {
-            // no face touches the tile: alpha = 0 everywhere, |alpha - T| = T
-            if (tid == 0) w.tile_l1[(size_t)fr * tiles + tile] = w.tile_tsum[(size_t)fr * tiles + tile];
-            if (alpha_out) {
-                const int x = tx0 + (tid & 15), y = ty0 + (tid >> 4);
-                if (x < S && y < S) alpha_out[((size_t)(fr - frame0) * S + y) * S + x] = 0.f;
-            }
-            __syncthreads();      // s_item is rewritten next iteration
-            continue;
-        }
-        if (fr != cached_frame) {
-            // all warps are past the previous frame's vertices (barrier above)
-            if (tid == 0) {
+    for (int visited = 0; visited < n_frames; ++visited, cur = (cur + 1 == n_frames) ? 0 : cur + 1) {
+        const int fr = frame0 + cur;
+        __syncthreads();           // every warp is past the previous frame's vertices
+        if (tid == 0) {
+            int st = 0;
+            if (*(volatile unsigned*)(w.frames_done) >= (unsigned)n_frames) st = 2;
+            else if (*(volatile unsigned*)(w.frame_next + fr) >= (unsigned)R) st = 1;
+            s_state = st;
+            if (st == 0) {
                 const unsigned bytes = (unsigned)(m.Vp * sizeof(float));
                 const float* src = ndc_soa + (size_t)fr * 3 * m.Vp;
                 mbar_expect_tx(&bar, 3 * bytes);
@@ -453,99 +523,145 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
                 tma_load_1d(vy, src + m.Vp, bytes, &bar);
                 tma_load_1d(vz, src + 2 * m.Vp, bytes, &bar);
             }
-            mbar_wait(&bar, parity);
-            parity ^= 1u;
-            cached_frame = fr;
         }
+        __syncthreads();
+        const int st = s_state;
+        if (st == 2) break;
+        if (st == 1) continue;
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
 
-        // ---- this warp's 8x4 region ------------------------------------------------
-        const int x0 = tx0 + (wid & 1) * REGION_W, y0 = ty0 + (wid >> 1) * REGION_H;
-        const uint2* rects = w.face_rect + (size_t)fr * m.Fp;
-        int L = 0;
-        for (int base = 0; base < m.Fp; base += 32) {
-            const uint2 r = rects[base + lane];
-            const int c0 = (int)(r.x & 0xffffu), c1 = (int)(r.x >> 16), r0 = (int)(r.y & 0xffffu), r1 = (int)(r.y >> 16);
-            const bool ov = (c0 <= x0 + REGION_W - 1) && (c1 >= x0) && (r0 <= y0 + REGION_H - 1) && (r1 >= y0);
-            const unsigned bal = __ballot_sync(0xffffffffu, ov);
-            if (ov) {
-                const int a = max(c0 - x0, 0), b = min(c1 - x0, REGION_W - 1);
-                const unsigned cm = ((1u << (b + 1)) - 1u) & ~((1u << a) - 1u);       // 8-bit column mask
-                const int ra = max(r0 - y0, 0), rb = min(r1 - y0, REGION_H - 1);
-                unsigned mk = 0u;
-                for (int rr = ra; rr <= rb; ++rr) mk |= cm << (8 * rr);
-                const int pos = L + __popc(bal & ltmask);
-                sl_fid[pos] = (unsigned short)(base + lane);
-                sl_mask[pos] = mk;
+        const unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
+        const uint4* pool = w.tile_pool + (size_t)fr * w.pool_cap;
+        for (;;) {
+            unsigned reg = 0;
+            if (lane == 0) {
+                reg = atomicAdd(w.frame_next + fr, 1u);
+                if (reg == (unsigned)R) atomicAdd(w.frames_done, 1u);      // first draw past the end
             }
-            L += __popc(bal);
-        }
-        __syncwarp();
+            reg = __shfl_sync(0xffffffffu, reg, 0);
+            if (reg >= (unsigned)R) break;
+            const int tile = (int)reg / REGIONS_PER_TILE, sub = (int)reg % REGIONS_PER_TILE;
+            const int lx0 = (sub % (TILE_W / REGION_W)) * REGION_W, ly0 = (sub / (TILE_W / REGION_W)) * REGION_H;
+            const int x0 = (tile % w.tiles_x) * TILE_W + lx0, y0 = (tile / w.tiles_x) * TILE_H + ly0;
+            const unsigned off = toff[tile];
+            const int len = (int)(min(toff[tile + 1], (unsigned)w.pool_cap) - min(off, (unsigned)w.pool_cap));
+            const int px_x = x0 + (lane & 7), px_y = y0 + (lane >> 3);
+            const bool px_in = (px_x < S) && (px_y < S);
+            if (len == 0 || x0 >= S || y0 >= S) {
+                // no face reaches the tile: alpha = 0, |alpha - T| = T; pix is never read here
+                if (lane == 0) w.region_l1[(size_t)fr * R + reg] = w.region_tsum[(size_t)fr * R + reg];
+                if (alpha_out && px_in) alpha_out[((size_t)(fr - frame0) * S + px_y) * S + px_x] = 0.f;
+                continue;
+            }
 
-        float myP = 1.f;
-        unsigned myTkey = 0xffffffffu, myTfid = 0xffffu;
-        int myN = 0;
-        if (L > 0) {
-            for (int q = 0; q < 32; ++q) {
-                const float px = pix_to_ndc(x0 + (q & 7), inv_s), py = pix_to_ndc(y0 + (q >> 3), inv_s);
-                int n = 0, qhead = 0, qn = 0;
-                for (int base = 0; base < L || qn > 0; base += 32) {
-                    if (base < L) {
-                        const int idx = base + lane;
-                        const bool pass = (idx < L) && ((sl_mask[idx] >> q) & 1u);
-                        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                        if (pass) wsm.queue[(qhead + qn + __popc(bal & ltmask)) & 63] = sl_fid[idx];
-                        qn += __popc(bal);
-                        __syncwarp();
+            // A. sub-list (shared memory; if it does not fit, a second pass puts it in global scratch)
+            int L = 0;
+            bool in_smem = true;
+            for (int pass = 0; pass < 2; ++pass) {
+                L = 0;
+                for (int base = 0; base < len; base += 32) {
+                    const int j = base + lane;
+                    uint4 e = make_uint4(0u, 0u, 0xffffffffu, 0u);
+                    if (j < len) e = pool[off + j];
+                    const int c0 = (int)(e.z & 0xffu), c1 = (int)((e.z >> 8) & 0xffu), r0 = (int)((e.z >> 16) & 0xffu), r1 = (int)(e.z >> 24);
+                    const bool ov = (j < len) && (c0 <= lx0 + REGION_W - 1) && (c1 >= lx0) && (r0 <= ly0 + REGION_H - 1) && (r1 >= ly0);
+                    const unsigned bal = __ballot_sync(0xffffffffu, ov);
+                    if (ov) {
+                        const int a = max(c0 - lx0, 0), b = min(c1 - lx0, REGION_W - 1);
+                        const unsigned cm = ((1u << (b + 1)) - 1u) & ~((1u << a) - 1u);       // 8-bit column mask
+                        const int ra = max(r0 - ly0, 0), rb = min(r1 - ly0, REGION_H - 1);
+                        unsigned mk = 0u;
+                        for (int rr = ra; rr <= rb; ++rr) mk |= cm << (8 * rr);
+                        const int pos = L + __popc(bal & ltmask);
+                        if (in_smem) { if (pos < SLCAP) { wsm.ent[pos] = make_uint2(e.x, e.y); wsm.mask[pos] = mk; } }
+                        else { g_ent[pos] = make_uint2(e.x, e.y); g_mask[pos] = mk; }
                     }
-                    if (qn >= 32 || (base + 32 >= L && qn > 0)) {
-                        const int cnt = min(qn, 32);
-                        bool valid = false;
-                        unsigned key = 0u; float mv = 1.f; unsigned short fidx = 0;
-                        if (lane < cnt) {
-                            fidx = wsm.queue[(qhead + lane) & 63];
-                            const ushort4 f4 = m.faces4[fidx];
-                            const FaceSetup fs = face_setup(vx[f4.x], vy[f4.x], vz[f4.x], vx[f4.y], vy[f4.y], vz[f4.y],
-                                                            vx[f4.z], vy[f4.z], vz[f4.z]);
-                            Fragment frag;
-                            valid = (f4.w != 0) && face_eval(fs, px, py, frag);
-                            if (valid) {
-                                float pp;
-                                frag_prob(frag.sd, pp, mv);
-                                key = __float_as_uint(frag.pz + 0.f);
+                    L += __popc(bal);
+                }
+                if (L <= SLCAP || !in_smem) break;
+                in_smem = false;
+            }
+            __syncwarp();
+            const uint2* ent = in_smem ? wsm.ent : g_ent;
+            const unsigned* emask = in_smem ? wsm.mask : g_mask;
+            unsigned short* plist = in_smem ? wsm.plist : g_plist;
+
+            float myP = 1.f;
+            unsigned myTkey = 0xffffffffu, myTfid = 0xffffu;
+            int myN = 0;
+            if (L > 0) {
+                for (int q = 0; q < 32; ++q) {
+                    // B1. candidates of pixel q
+                    int np = 0;
+                    for (int base = 0; base < L; base += 32) {
+                        const int idx = base + lane;
+                        const bool pass = (idx < L) && ((emask[idx] >> q) & 1u);
+                        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                        if (pass) plist[np + __popc(bal & ltmask)] = (unsigned short)idx;
+                        np += __popc(bal);
+                    }
+                    __syncwarp();
+                    float P = 1.f;
+                    unsigned tk = 0xffffffffu, tf = 0xffffu;
+                    int n = 0;
+                    if (np > 0) {
+                        const float px = pix_to_ndc(x0 + (q & 7), inv_s), py = pix_to_ndc(y0 + (q >> 3), inv_s);
+                        const bool all_selected = (np <= RAST_K);
+                        float running = 1.f;
+                        for (int b0 = 0; b0 < np; b0 += 32) {
+                            const int i = b0 + lane;
+                            bool valid = false;
+                            unsigned key = 0u; float mv = 1.f; unsigned fidx = 0;
+                            if (i < np) {
+                                const uint2 e = ent[plist[i]];
+                                fidx = e.x & 0xffffu;
+                                const unsigned v0 = e.x >> 16, v1 = e.y & 0xffffu, v2 = e.y >> 16;
+                                float sd, pz;
+                                valid = frag_forward(vx[v0], vy[v0], vz[v0], vx[v1], vy[v1], vz[v1], vx[v2], vy[v2], vz[v2],
+                                                     px, py, !all_selected, sd, pz);
+                                if (valid) {
+                                    float pp;
+                                    frag_prob(sd, pp, mv);
+                                    key = __float_as_uint(pz + 0.f);
+                                }
+                            }
+                            const unsigned bal = __ballot_sync(0xffffffffu, valid);
+                            if (all_selected) {
+                                running *= warp_prod(mv);           // mv == 1 for lanes without a fragment
+                                n += __popc(bal);
+                                if (running < P_SKIP) { running = 0.f; break; }     // alpha == 1.0f exactly
+                            } else {
+                                if (valid) ks.put(n + __popc(bal & ltmask), key, mv, (unsigned short)fidx);
+                                n += __popc(bal);
                             }
                         }
-                        const unsigned bal = __ballot_sync(0xffffffffu, valid);
-                        if (valid) ks.put(n + __popc(bal & ltmask), key, mv, fidx);
-                        n += __popc(bal);
-                        qhead = (qhead + cnt) & 63;
-                        qn -= cnt;
-                        __syncwarp();
+                        if (all_selected) {
+                            P = running;
+                        } else {
+                            __syncwarp();
+                            if (n > RAST_K) {
+                                P = select_k_nearest(ks, n, lane, tk, tf);
+                                if (lane == 0) { ++n_capped; if (n > KCAP) ++n_spilled; }
+                            } else if (n > 0) {
+                                float pr = 1.f;
+                                for (int i = lane; i < n; i += 32) pr *= ks.m(i);
+                                P = warp_prod(pr);
+                            }
+                        }
                     }
+                    if (lane == q) { myP = P; myTkey = tk; myTfid = tf; myN = n; }
+                    __syncwarp();
                 }
-                float P = 1.f;
-                unsigned tk = 0xffffffffu, tf = 0xffffu;
-                if (n > RAST_K) {
-                    P = select_k_nearest(ks, n, lane, tk, tf);
-                    if (lane == 0) { ++n_capped; if (n > KCAP) ++n_spilled; }
-                } else if (n > 0) {
-                    float pr = 1.f;
-                    for (int i = lane; i < n; i += 32) pr *= wsm.mval[i];
-                    P = warp_prod(pr);
-                }
-                if (lane == q) { myP = P; myTkey = tk; myTfid = tf; myN = n; }
-                __syncwarp();
             }
-        }
 
-        // ---- epilogue: lane = pixel -------------------------------------------------
-        {
-            const int x = x0 + (lane & 7), y = y0 + (lane >> 3);
+            // D. epilogue: lane = pixel
             float l1 = 0.f;
-            if (x < S && y < S) {
-                const size_t pi = ((size_t)fr * S + y) * S + x;
+            if (px_in) {
+                const size_t pi = ((size_t)fr * S + px_y) * S + px_x;
                 const float alpha = 1.f - myP;
-                const float T = (float)w.sil[pi];
-                const float d = alpha - T;
+                const float Tm = (float)w.sil[pi];
+                const float d = alpha - Tm;
                 l1 = fabsf(d);
                 float coef = 0.f;
                 if (myN > 0 && myP >= P_SKIP && d != 0.f) {
@@ -554,16 +670,10 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
                 }
                 w.pix[pi] = make_uint2(__float_as_uint(coef), myTkey);
                 if (myTkey != 0xffffffffu) w.pix_tfid[pi] = (unsigned short)myTfid;
-                if (alpha_out) alpha_out[((size_t)(fr - frame0) * S + y) * S + x] = alpha;
+                if (alpha_out) alpha_out[((size_t)(fr - frame0) * S + px_y) * S + px_x] = alpha;
             }
             l1 = warp_sum(l1);
-            if (lane == 0) s_l1[wid] = l1;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            float t = 0.f;
-            for (int i = 0; i < RAST_WARPS; ++i) t += s_l1[i];
-            w.tile_l1[(size_t)fr * tiles + tile] = t;
+            if (lane == 0) w.region_l1[(size_t)fr * R + reg] = l1;
         }
     }
     if (lane == 0 && (n_capped | n_spilled)) {
@@ -593,7 +703,7 @@ void launch_ndc_soa(const ModelDev& m, const Workspace& w, float* ndc_soa, int f
 
 void launch_raster_forward(const ModelDev& m, const Workspace& w, const RasterScratch& sc, float* ndc_soa,
                            int frame0, int n, Weights wt, float* alpha_out, int n_ctas, cudaStream_t st) {
-    cudaMemsetAsync(w.work_counter, 0, sizeof(unsigned), st);
+    cudaMemsetAsync(w.frame_next, 0, sizeof(unsigned) * (size_t)(w.N + 1), st);      // + frames_done
     raster_forward_kernel<<<n_ctas, RAST_THREADS, raster_smem_bytes(m), st>>>(m, w, sc, frame0, n, wt, ndc_soa, alpha_out);
 }
 
@@ -797,7 +907,13 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
     }
     lpose = block_sum(lpose, S.red);
     lsplay = block_sum(lsplay, S.red);
-    if (tid == 0) { w.frame_loss[fr * 4 + 1] = lpose; w.frame_loss[fr * 4 + 2] = lsplay; }
+    float lsil = 0.f;
+    if (use_sil) {
+        const int R = w.tiles_x * w.tiles_y * REGIONS_PER_TILE;
+        for (int r = tid; r < R; r += FRAME_THREADS) lsil += w.region_l1[(size_t)fr * R + r];
+        lsil = block_sum(lsil, S.red) * wt.sil * invw / ((float)w.S * (float)w.S);
+    }
+    if (tid == 0) { w.frame_loss[fr * 4 + 1] = lpose; w.frame_loss[fr * 4 + 2] = lsplay; w.frame_loss[fr * 4 + 3] = lsil; }
     if (tid < 3) { if (g.glob) g.glob[fr * 3 + tid] = S.thg[tid] * w.gmask[tid]; }
     else if (tid < NJ * 3) { if (g.joint) g.joint[(size_t)fr * (NJ - 1) * 3 + (tid - 3)] = S.thg[tid] * w.rmask[tid - 3]; }
 }
@@ -851,7 +967,6 @@ finalize_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, int n_fr
     __shared__ float red[40];
     __shared__ float diff[32], res[32];
     const int tid = threadIdx.x;
-    const int tiles = w.tiles_x * w.tiles_y;
     // loss terms: fixed-order sums over the frames of the range
     float lk = 0.f, lp = 0.f, lsp = 0.f, lsil = 0.f;
     for (int f = tid; f < n_frames; f += blockDim.x) {
@@ -859,11 +974,7 @@ finalize_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, int n_fr
         lk += w.frame_loss[fr * 4 + 0];
         lp += w.frame_loss[fr * 4 + 1];
         lsp += w.frame_loss[fr * 4 + 2];
-        if (wt.sil > 0.f) {
-            float t = 0.f;
-            for (int q = 0; q < tiles; ++q) t += w.tile_l1[(size_t)fr * tiles + q];
-            lsil += t * wt.sil * w.inv_window[fr] / ((float)w.S * (float)w.S);
-        }
+        if (wt.sil > 0.f) lsil += w.frame_loss[fr * 4 + 3];
     }
     lk = block_sum(lk, red); lp = block_sum(lp, red); lsp = block_sum(lsp, red); lsil = block_sum(lsil, red);
 
@@ -1001,22 +1112,26 @@ void launch_adam(float* p, const float* g, float* m, float* v, int n, float lr, 
 }
 
 // ---------------------------------------------------------------------------
-// per-tile sums of the target mask (loss of tiles no face touches)
+// per-region sums of the target mask (the L1 term of regions no face reaches)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tile_tsum_kernel(Workspace w, int frame0, float* out) {
-    __shared__ float red[40];
-    const int tile = blockIdx.x, fr = frame0 + blockIdx.y;
-    const int tx = tile % w.tiles_x, ty = tile / w.tiles_x;
-    const int x = tx * TILE_W + (threadIdx.x & 15), y = ty * TILE_H + (threadIdx.x >> 4);
+__global__ void __launch_bounds__(256) region_tsum_kernel(Workspace w, int frame0, float* out) {
+    const int R = w.tiles_x * w.tiles_y * REGIONS_PER_TILE;
+    const int reg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int fr = frame0 + blockIdx.y;
+    if (reg >= R) return;
+    const int tile = reg / REGIONS_PER_TILE, sub = reg % REGIONS_PER_TILE;
+    const int x = (tile % w.tiles_x) * TILE_W + (sub % (TILE_W / REGION_W)) * REGION_W + (lane & 7);
+    const int y = (tile / w.tiles_x) * TILE_H + (sub / (TILE_W / REGION_W)) * REGION_H + (lane >> 3);
     float v = 0.f;
     if (x < w.S && y < w.S) v = (float)w.sil[((size_t)fr * w.S + y) * w.S + x];
-    v = block_sum(v, red);
-    if (threadIdx.x == 0) out[(size_t)fr * w.tiles_x * w.tiles_y + tile] = v;
+    v = warp_sum(v);
+    if (lane == 0) out[(size_t)fr * R + reg] = v;
 }
 
-void launch_tile_tsum(const Workspace& w, int frame0, int n, float* tile_tsum, cudaStream_t st) {
-    dim3 grid(w.tiles_x * w.tiles_y, n);
-    tile_tsum_kernel<<<grid, 256, 0, st>>>(w, frame0, tile_tsum);
+void launch_region_tsum(const Workspace& w, int frame0, int n, float* region_tsum, cudaStream_t st) {
+    const int R = w.tiles_x * w.tiles_y * REGIONS_PER_TILE;
+    dim3 grid((R + 7) / 8, n);
+    region_tsum_kernel<<<grid, 256, 0, st>>>(w, frame0, region_tsum);
 }
 
 cudaError_t configure_kernels(const ModelDev& m) {
@@ -1024,6 +1139,8 @@ cudaError_t configure_kernels(const ModelDev& m) {
     cudaError_t e = cudaFuncSetAttribute(frame_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(frame_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(bin_faces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 1024 * (int)sizeof(unsigned));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(raster_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes(m));
 }

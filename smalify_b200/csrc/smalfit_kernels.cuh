@@ -8,11 +8,14 @@
 namespace smf {
 
 constexpr int FRAME_THREADS = 256;
-constexpr int RAST_WARPS = 8;               // warps per raster-forward CTA
+constexpr int RAST_WARPS = 16;              // warps per raster-forward CTA (one CTA per SM)
 constexpr int RAST_THREADS = RAST_WARPS * 32;
 constexpr int REGION_W = 8, REGION_H = 4;   // pixels handled by one warp at a time
-constexpr int TILE_W = 16, TILE_H = 16;     // 8 regions per CTA work item
-constexpr int KCAP = 512;                   // fragment selection buffer per warp (shared memory part)
+constexpr int TILE_W = 32, TILE_H = 32;     // CTA work item: 32 regions, pulled dynamically by the warps
+constexpr int REGIONS_PER_TILE = (TILE_W / REGION_W) * (TILE_H / REGION_H);
+constexpr int KCAP = 256;                   // fragment selection buffer per warp (shared memory part)
+constexpr int SLCAP = 448;                  // region sub-list entries kept in shared memory
+constexpr int MAX_TILES = 1024;             // 32x32 tiles per frame (image side <= 1024)
 constexpr int MAX_LEVELS = 16;
 constexpr float P_SKIP = 2.98023224e-8f;    // 2^-25: below this 1-P rounds to 1.0f in fp32
 
@@ -61,27 +64,28 @@ struct Workspace {
     float* gjoint;              // [N][41*3] dL/d(model joints) from the keypoint term
     float* kp_proj;             // [N][25*2]
     uint2* face_rect;           // [N][Fp]  (c0 | c1<<16, r0 | r1<<16), empty: c0 > c1
-    int4* frame_bounds;         // [N] pixel bounds (c0, c1, r0, r1) of all faces
+    uint4* tile_pool;           // [N][pool_cap] binned faces (fid|v0<<16, v1|v2<<16, tile-local rect, -)
+    unsigned* tile_off;         // [N][tiles+1] offsets into the frame's pool
+    int pool_cap;
+    unsigned* frame_next;       // [N] next region to hand out   (followed by frames_done)
+    unsigned* frames_done;      // [1] frames whose counter ran past the end
     uint2* pix;                 // [N][S*S] (float coef, u32 tkey)
     uint16_t* pix_tfid;         // [N][S*S] tie face id (capped pixels only)
-    float* tile_l1;             // [N][tiles]
+    float* region_l1;           // [N][tiles*32] per-region sum |alpha - T|
     float* face_grad;           // [N][Fp][8] (gx0,gy0,gx1,gy1,gx2,gy2,-,-)
     float* dvs;                 // [N][V*3]  per-frame dL/dv_shaped
     float* gJ;                  // [N][105]  per-frame dL/dJ(rest joints)
     float* gls;                 // [N][6]    per-frame dL/dlogscale
-    float* frame_loss;          // [N][4]    kp, pose, splay, (unused)
+    float* frame_loss;          // [N][4]    kp, pose, splay, silhouette
     float* beta_partial;        // [n_shapes][n_blocks][20]
     // targets
     const uint8_t* sil;         // [N][S*S]
     const float* kp_target;     // [N][25*2]
     const uint8_t* vis;         // [N][25]
-    const float* tile_tsum;     // [N][tiles]
+    const float* region_tsum;   // [N][tiles*32] per-region sum of the target mask
     const float* inv_window;    // [N] 1 / frames_per_window
     const float* gmask;         // [3]
     const float* rmask;         // [102]
-    // raster scratch
-    uint16_t* sl_fid;           // [n_raster_warps][Fp]
-    uint32_t* sl_mask;          // [n_raster_warps][Fp]
     unsigned int* work_counter; // [1]
     unsigned long long* counters;   // [4]
 };
@@ -89,8 +93,9 @@ struct Workspace {
 struct Weights { float j2d, sil, betas, pose, limit, splay; };
 struct AdamState { int step; float bc1; float bc2_sqrt; int pad; };
 
-struct RasterScratch {      // global spill buffers for pixels with more than KCAP fragments, per resident warp
-    unsigned* key; float* m; unsigned short* fid;
+struct RasterScratch {      // per resident warp, [n_raster_warps][Fp] each
+    unsigned* key; float* m; unsigned short* fid;          // fragments beyond KCAP of a pixel
+    uint2* ent; unsigned* mask; unsigned short* plist;     // sub-lists longer than SLCAP
 };
 
 // ---- launch wrappers (defined in smalfit_kernels.cu) ----------------------
@@ -100,7 +105,7 @@ size_t raster_smem_bytes(const ModelDev& m);
 void launch_shape_forward(const ModelDev& m, const Workspace& w, const Params& p, cudaStream_t st);
 void launch_frame_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n,
                           Weights wt, float* verts_out, cudaStream_t st);
-void launch_face_rects(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st);
+void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st);
 void launch_ndc_soa(const ModelDev& m, const Workspace& w, float* ndc_soa, int frame0, int n, cudaStream_t st);
 void launch_raster_forward(const ModelDev& m, const Workspace& w, const RasterScratch& sc, float* ndc_soa,
                            int frame0, int n, Weights wt, float* alpha_out, int n_ctas, cudaStream_t st);
@@ -115,6 +120,6 @@ void launch_temporal(const Workspace& w, const Params& p, const Grads& g, int N,
 void launch_adam_tick(AdamState* s, float b1, float b2, int host_step, cudaStream_t st);
 void launch_adam(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2,
                  float eps, const AdamState* s, cudaStream_t st);
-void launch_tile_tsum(const Workspace& w, int frame0, int n, float* tile_tsum, cudaStream_t st);
+void launch_region_tsum(const Workspace& w, int frame0, int n, float* region_tsum, cudaStream_t st);
 
 }  // namespace smf

@@ -57,6 +57,11 @@ SMF_HD float ffma(float a, float b, float c) { return fmaf(a, b, c); }
 SMF_HD float fsat(float a) { return a < 0.f ? 0.f : (a > 1.f ? 1.f : a); }
 #endif
 
+// a x b (2-D) with one rounding-pinned FMA; shared by every place that forms edge functions so
+// that forward and backward see bit-identical barycentric numerators and depths
+SMF_HD float cross2(float ax, float ay, float bx, float by) { return ffma(ax, by, -fmul(ay, bx)); }
+SMF_HD float dot2(float ax, float ay, float bx, float by) { return ffma(ax, bx, fmul(ay, by)); }
+
 // ---------------------------------------------------------------------------
 // 3x3 helpers (row-major float[9])
 // ---------------------------------------------------------------------------
@@ -268,14 +273,14 @@ SMF_HD FaceSetup face_setup(float x0, float y0, float z0, float x1, float y1, fl
     f.e02x = fsub(x2, x0); f.e02y = fsub(y2, y0);
     f.e12x = fsub(x2, x1); f.e12y = fsub(y2, y1);
     // area = EdgeFunction(v2; v0, v1) = (x2-x0)(y1-y0) - (y2-y0)(x1-x0)
-    const float area = fsub(fmul(f.e02x, f.e01y), fmul(f.e02y, f.e01x));
+    const float area = cross2(f.e02x, f.e02y, f.e01x, f.e01y);
     const float zmax = fmaxf(z0, fmaxf(z1, z2));
     const bool degenerate = (area <= RAST_EPS) && (area >= -RAST_EPS);
     f.valid = (zmax >= 0.f && !degenerate) ? 1.f : 0.f;
     f.rden = 1.f / fadd(area, RAST_EPS);
-    const float l01 = fadd(fmul(f.e01x, f.e01x), fmul(f.e01y, f.e01y));
-    const float l02 = fadd(fmul(f.e02x, f.e02x), fmul(f.e02y, f.e02y));
-    const float l12 = fadd(fmul(f.e12x, f.e12x), fmul(f.e12y, f.e12y));
+    const float l01 = dot2(f.e01x, f.e01y, f.e01x, f.e01y);
+    const float l02 = dot2(f.e02x, f.e02y, f.e02x, f.e02y);
+    const float l12 = dot2(f.e12x, f.e12y, f.e12x, f.e12y);
     f.rl01 = (l01 <= RAST_EPS) ? 0.f : 1.f / l01;
     f.rl02 = (l02 <= RAST_EPS) ? 0.f : 1.f / l02;
     f.rl12 = (l12 <= RAST_EPS) ? 0.f : 1.f / l12;
@@ -319,22 +324,22 @@ SMF_HD bool face_eval(const FaceSetup& f, float px, float py, Fragment& fr) {
     const float bx = fsub(px, f.x1), by = fsub(py, f.y1);     // p - v1
     const float cx = fsub(px, f.x2), cy = fsub(py, f.y2);     // p - v2
     // barycentric numerators (edge functions)
-    const float n0 = fsub(fmul(bx, f.e12y), fmul(by, f.e12x));        // E(p; v1, v2)
-    const float n1 = fsub(fmul(cy, f.e02x), fmul(cx, f.e02y));        // E(p; v2, v0) = (p-v2) x (v0-v2)
-    const float n2 = fsub(fmul(ax, f.e01y), fmul(ay, f.e01x));        // E(p; v0, v1)
+    const float n0 = cross2(bx, by, f.e12x, f.e12y);                  // E(p; v1, v2)
+    const float n1 = cross2(f.e02x, f.e02y, cx, cy);                  // E(p; v2, v0) = (p-v2) x (v0-v2)
+    const float n2 = cross2(ax, ay, f.e01x, f.e01y);                  // E(p; v0, v1)
     const float w0 = fmul(n0, f.rden), w1 = fmul(n1, f.rden), w2 = fmul(n2, f.rden);
     const float pz = ffma(w2, f.z2, ffma(w1, f.z1, fmul(w0, f.z0)));
     if (pz < 0.f) return false;
     // squared distances to the three segments
-    const float t01 = (f.rl01 == 0.f) ? 1.f : fsat(fmul(fadd(fmul(f.e01x, ax), fmul(f.e01y, ay)), f.rl01));
-    const float q01x = fsub(fmul(t01, f.e01x), ax), q01y = fsub(fmul(t01, f.e01y), ay);
-    const float d01 = fadd(fmul(q01x, q01x), fmul(q01y, q01y));
-    const float t02 = (f.rl02 == 0.f) ? 1.f : fsat(fmul(fadd(fmul(f.e02x, ax), fmul(f.e02y, ay)), f.rl02));
-    const float q02x = fsub(fmul(t02, f.e02x), ax), q02y = fsub(fmul(t02, f.e02y), ay);
-    const float d02 = fadd(fmul(q02x, q02x), fmul(q02y, q02y));
-    const float t12 = (f.rl12 == 0.f) ? 1.f : fsat(fmul(fadd(fmul(f.e12x, bx), fmul(f.e12y, by)), f.rl12));
-    const float q12x = fsub(fmul(t12, f.e12x), bx), q12y = fsub(fmul(t12, f.e12y), by);
-    const float d12 = fadd(fmul(q12x, q12x), fmul(q12y, q12y));
+    const float t01 = (f.rl01 == 0.f) ? 1.f : fsat(fmul(dot2(f.e01x, f.e01y, ax, ay), f.rl01));
+    const float q01x = ffma(t01, f.e01x, -ax), q01y = ffma(t01, f.e01y, -ay);
+    const float d01 = dot2(q01x, q01y, q01x, q01y);
+    const float t02 = (f.rl02 == 0.f) ? 1.f : fsat(fmul(dot2(f.e02x, f.e02y, ax, ay), f.rl02));
+    const float q02x = ffma(t02, f.e02x, -ax), q02y = ffma(t02, f.e02y, -ay);
+    const float d02 = dot2(q02x, q02y, q02x, q02y);
+    const float t12 = (f.rl12 == 0.f) ? 1.f : fsat(fmul(dot2(f.e12x, f.e12y, bx, by), f.rl12));
+    const float q12x = ffma(t12, f.e12x, -bx), q12y = ffma(t12, f.e12y, -by);
+    const float d12 = dot2(q12x, q12y, q12x, q12y);
     // closest edge, ties 01 -> 02 -> 12 (PointTriangleDistanceBackward order)
     int e; float d, t, qx, qy;
     if (d01 <= d02 && d01 <= d12) { e = 0; d = d01; t = t01; qx = q01x; qy = q01y; }
@@ -343,6 +348,52 @@ SMF_HD bool face_eval(const FaceSetup& f, float px, float py, Fragment& fr) {
     const bool inside = (w0 > 0.f) && (w1 > 0.f) && (w2 > 0.f);
     if (!inside && d >= RAST_BLUR) return false;
     fr.pz = pz; fr.sd = inside ? -d : d; fr.edge = e; fr.t = t; fr.qx = qx; fr.qy = qy;
+    return true;
+}
+
+// Forward-only fragment test straight from the nine vertex floats: the signed squared distance
+// (and, when want_pz, the depth -- bit-identical to face_eval's) without building a FaceSetup.
+// Segment distances use |a|^2, |b|^2 and cross^2/|e|^2 (equal to the clamped-t form in exact
+// arithmetic); the blur-expanded bbox test is implied by the distance test and omitted.
+SMF_HD bool frag_forward(float x0, float y0, float z0, float x1, float y1, float z1, float x2, float y2, float z2,
+                         float px, float py, bool want_pz, float& sd, float& pz) {
+    const float e01x = fsub(x1, x0), e01y = fsub(y1, y0);
+    const float e02x = fsub(x2, x0), e02y = fsub(y2, y0);
+    const float e12x = fsub(x2, x1), e12y = fsub(y2, y1);
+    const float area = cross2(e02x, e02y, e01x, e01y);
+    if ((area <= RAST_EPS && area >= -RAST_EPS) || fmaxf(z0, fmaxf(z1, z2)) < 0.f) return false;
+    const float den = fadd(area, RAST_EPS);
+    const float ax = fsub(px, x0), ay = fsub(py, y0);
+    const float bx = fsub(px, x1), by = fsub(py, y1);
+    const float cx = fsub(px, x2), cy = fsub(py, y2);
+    const float n0 = cross2(bx, by, e12x, e12y);
+    const float n1 = cross2(e02x, e02y, cx, cy);
+    const float n2 = cross2(ax, ay, e01x, e01y);
+    pz = 0.f;
+    if (want_pz) {
+        const float rden = 1.f / den;
+        const float w0 = fmul(n0, rden), w1 = fmul(n1, rden), w2 = fmul(n2, rden);
+        pz = ffma(w2, z2, ffma(w1, z1, fmul(w0, z0)));
+        if (pz < 0.f) return false;
+    } else {
+        const float sn = ffma(n2, z2, ffma(n1, z1, fmul(n0, z0)));
+        if ((sn < 0.f && den > 0.f) || (sn > 0.f && den < 0.f)) return false;
+    }
+    const bool inside = (den > 0.f) ? (n0 > 0.f && n1 > 0.f && n2 > 0.f) : (n0 < 0.f && n1 < 0.f && n2 < 0.f);
+    const float da = dot2(ax, ay, ax, ay), db = dot2(bx, by, bx, by), dc = dot2(cx, cy, cx, cy);
+    const float l01 = dot2(e01x, e01y, e01x, e01y), l02 = dot2(e02x, e02y, e02x, e02y), l12 = dot2(e12x, e12y, e12x, e12y);
+    const float p01 = dot2(e01x, e01y, ax, ay), p02 = dot2(e02x, e02y, ax, ay), p12 = dot2(e12x, e12y, bx, by);
+#if defined(__CUDA_ARCH__)
+    const float i01 = __fdividef(fmul(n2, n2), l01), i02 = __fdividef(fmul(n1, n1), l02), i12 = __fdividef(fmul(n0, n0), l12);
+#else
+    const float i01 = n2 * n2 / l01, i02 = n1 * n1 / l02, i12 = n0 * n0 / l12;
+#endif
+    const float d01 = (l01 <= RAST_EPS || p01 >= l01) ? db : (p01 <= 0.f ? da : i01);
+    const float d02 = (l02 <= RAST_EPS || p02 >= l02) ? dc : (p02 <= 0.f ? da : i02);
+    const float d12 = (l12 <= RAST_EPS || p12 >= l12) ? dc : (p12 <= 0.f ? db : i12);
+    const float d = fminf(d01, fminf(d02, d12));
+    if (!inside && d >= RAST_BLUR) return false;
+    sd = inside ? -d : d;
     return true;
 }
 

@@ -320,7 +320,7 @@ class SMALFitter(nn.Module):
         arr = (ctypes.c_int64 * 4)()
         h = self._handle
         h.check(h.lib.smalfit_counters(h.h, arr, _stream(self.device)), "smalfit_counters")
-        return dict(capped_pixels=arr[0], spilled_pixels=arr[1], raster_launches=arr[2], launches=arr[3])
+        return dict(capped_pixels=arr[0], spilled_pixels=arr[1], dropped_bin_entries=arr[2], launches=arr[3])
 
     # ------------------------------------------------------------------
     def export_parameters(self, frame_id):

@@ -51,6 +51,14 @@ int chk_face_eval(const float* tri /* x0,y0,z0,x1,y1,z1,x2,y2,z2 */, float px, f
     return 1;
 }
 
+// lean forward variant: out = (pz, sd)
+int chk_frag_forward(const float* tri, float px, float py, int want_pz, float* out) {
+    float sd = 0.f, pz = 0.f;
+    const bool ok = frag_forward(tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8], px, py, want_pz != 0, sd, pz);
+    out[0] = pz; out[1] = sd;
+    return ok ? 1 : 0;
+}
+
 int chk_face_rect(const float* tri, int S, int* rect) {
     const FaceSetup fs = face_setup(tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8]);
     return face_pixel_rect(fs, S, rect[0], rect[1], rect[2], rect[3]) ? 1 : 0;
