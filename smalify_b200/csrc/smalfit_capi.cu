@@ -212,6 +212,7 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     w.pool_cap = 8 * m.Fp;
     w.tile_pool = P.alloc<uint4>(N * (size_t)w.pool_cap);
     w.tile_off = P.alloc<unsigned>(N * (tiles + 1), true);
+    w.tile_order = P.alloc<unsigned short>(N * tiles, true);
     w.frame_next = P.alloc<unsigned>(N + 1, true);
     w.frames_done = w.frame_next + N;
     w.pix = P.alloc<uint2>(N * SS, true);

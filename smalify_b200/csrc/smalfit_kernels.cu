@@ -305,6 +305,14 @@ __global__ void __launch_bounds__(256) bin_faces_kernel(ModelDev m, Workspace w,
             if (t == T - 1) toff[T] = run;
         }
     }
+    // hand-out order of the tiles: longest list first, so a frame's last regions are the cheap ones
+    unsigned short* order = w.tile_order + (size_t)fr * T;
+    for (int t = tid; t < T; t += 256) {
+        const unsigned c = tot[t];
+        int rank = 0;
+        for (int u = 0; u < T; ++u) { const unsigned cu = tot[u]; rank += (cu > c || (cu == c && u < t)) ? 1 : 0; }
+        order[rank] = (unsigned short)t;
+    }
     __syncthreads();
     // pass 2: fill, in face order within a warp
     const unsigned ltmask = lanemask_lt();
@@ -532,6 +540,7 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
         parity ^= 1u;
 
         const unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
+        const unsigned short* torder = w.tile_order + (size_t)fr * T;
         const uint4* pool = w.tile_pool + (size_t)fr * w.pool_cap;
         for (;;) {
             unsigned reg = 0;
@@ -541,7 +550,8 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
             }
             reg = __shfl_sync(0xffffffffu, reg, 0);
             if (reg >= (unsigned)R) break;
-            const int tile = (int)reg / REGIONS_PER_TILE, sub = (int)reg % REGIONS_PER_TILE;
+            const int tile = (int)torder[(int)reg / REGIONS_PER_TILE], sub = (int)reg % REGIONS_PER_TILE;
+            const unsigned oreg = (unsigned)(tile * REGIONS_PER_TILE + sub);      // storage index of the region
             const int lx0 = (sub % (TILE_W / REGION_W)) * REGION_W, ly0 = (sub / (TILE_W / REGION_W)) * REGION_H;
             const int x0 = (tile % w.tiles_x) * TILE_W + lx0, y0 = (tile / w.tiles_x) * TILE_H + ly0;
             const unsigned off = toff[tile];
@@ -550,7 +560,7 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
             const bool px_in = (px_x < S) && (px_y < S);
             if (len == 0 || x0 >= S || y0 >= S) {
                 // no face reaches the tile: alpha = 0, |alpha - T| = T; pix is never read here
-                if (lane == 0) w.region_l1[(size_t)fr * R + reg] = w.region_tsum[(size_t)fr * R + reg];
+                if (lane == 0) w.region_l1[(size_t)fr * R + oreg] = w.region_tsum[(size_t)fr * R + oreg];
                 if (alpha_out && px_in) alpha_out[((size_t)(fr - frame0) * S + px_y) * S + px_x] = 0.f;
                 continue;
             }
@@ -673,7 +683,7 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
                 if (alpha_out) alpha_out[((size_t)(fr - frame0) * S + px_y) * S + px_x] = alpha;
             }
             l1 = warp_sum(l1);
-            if (lane == 0) w.region_l1[(size_t)fr * R + reg] = l1;
+            if (lane == 0) w.region_l1[(size_t)fr * R + oreg] = l1;
         }
     }
     if (lane == 0 && (n_capped | n_spilled)) {
@@ -715,7 +725,11 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(ModelDev m, Worksp
     const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int fr = frame0 + blockIdx.y;
     if (f >= m.Fp) return;
-    const FaceSetup fs = load_face(w.ndc + (size_t)fr * m.Vp, m.faces4[f]);
+    const ushort4 f4 = m.faces4[f];
+    const float4* ndc = w.ndc + (size_t)fr * m.Vp;
+    const float4 A = ndc[f4.x], B = ndc[f4.y], C = ndc[f4.z];
+    FaceSetup fs = face_setup(A.x, A.y, A.z, B.x, B.y, B.z, C.x, C.y, C.z);
+    if (f4.w == 0) fs.valid = 0.f;
     float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int c0, c1, r0, r1;
     if (face_pixel_rect(fs, w.S, c0, c1, r0, r1)) {
@@ -731,13 +745,22 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(ModelDev m, Worksp
             const uint2 pr = pix[(size_t)y * S + x];
             const float coef = __uint_as_float(pr.x);
             if (coef == 0.f) continue;
-            Fragment frag;
-            if (!face_eval(fs, pix_to_ndc(x, inv_s), pix_to_ndc(y, inv_s), frag)) continue;
-            const unsigned key = __float_as_uint(frag.pz + 0.f);
-            if (key > pr.y) continue;
-            if (key == pr.y && (unsigned)f > (unsigned)w.pix_tfid[((size_t)fr * S + y) * S + x]) continue;
+            const float px = pix_to_ndc(x, inv_s), py = pix_to_ndc(y, inv_s);
+            // same acceptance test and depth as the forward pass (frag_forward); the depth only matters
+            // for pixels that carry a K-nearest threshold
+            const bool capped = pr.y != 0xffffffffu;
+            float sd, pz;
+            if (!frag_forward(A.x, A.y, A.z, B.x, B.y, B.z, C.x, C.y, C.z, px, py, capped, sd, pz)) continue;
+            if (capped) {
+                const unsigned key = __float_as_uint(pz + 0.f);
+                if (key > pr.y) continue;
+                if (key == pr.y && (unsigned)f > (unsigned)w.pix_tfid[((size_t)fr * S + y) * S + x]) continue;
+            }
             float p, mv;
-            frag_prob(frag.sd, p, mv);
+            frag_prob(sd, p, mv);
+            Fragment frag;
+            closest_edge(fs, px, py, frag);
+            frag.sd = sd;
             frag_grad(frag, -coef * p, g);
         }
 #pragma unroll

@@ -66,6 +66,7 @@ struct Workspace {
     uint2* face_rect;           // [N][Fp]  (c0 | c1<<16, r0 | r1<<16), empty: c0 > c1
     uint4* tile_pool;           // [N][pool_cap] binned faces (fid|v0<<16, v1|v2<<16, tile-local rect, -)
     unsigned* tile_off;         // [N][tiles+1] offsets into the frame's pool
+    unsigned short* tile_order; // [N][tiles] tiles sorted by decreasing list length (hand-out order)
     int pool_cap;
     unsigned* frame_next;       // [N] next region to hand out   (followed by frames_done)
     unsigned* frames_done;      // [1] frames whose counter ran past the end

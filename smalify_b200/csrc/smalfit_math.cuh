@@ -397,6 +397,25 @@ SMF_HD bool frag_forward(float x0, float y0, float z0, float x1, float y1, float
     return true;
 }
 
+// Closest edge of an accepted fragment with its clamped parameter and (p_proj - p), the
+// quantities PointTriangleDistanceBackward differentiates (ties 01 -> 02 -> 12).
+SMF_HD void closest_edge(const FaceSetup& f, float px, float py, Fragment& fr) {
+    const float ax = fsub(px, f.x0), ay = fsub(py, f.y0);
+    const float bx = fsub(px, f.x1), by = fsub(py, f.y1);
+    const float t01 = (f.rl01 == 0.f) ? 1.f : fsat(fmul(dot2(f.e01x, f.e01y, ax, ay), f.rl01));
+    const float q01x = ffma(t01, f.e01x, -ax), q01y = ffma(t01, f.e01y, -ay);
+    const float d01 = dot2(q01x, q01y, q01x, q01y);
+    const float t02 = (f.rl02 == 0.f) ? 1.f : fsat(fmul(dot2(f.e02x, f.e02y, ax, ay), f.rl02));
+    const float q02x = ffma(t02, f.e02x, -ax), q02y = ffma(t02, f.e02y, -ay);
+    const float d02 = dot2(q02x, q02y, q02x, q02y);
+    const float t12 = (f.rl12 == 0.f) ? 1.f : fsat(fmul(dot2(f.e12x, f.e12y, bx, by), f.rl12));
+    const float q12x = ffma(t12, f.e12x, -bx), q12y = ffma(t12, f.e12y, -by);
+    const float d12 = dot2(q12x, q12y, q12x, q12y);
+    if (d01 <= d02 && d01 <= d12) { fr.edge = 0; fr.t = t01; fr.qx = q01x; fr.qy = q01y; }
+    else if (d02 <= d01 && d02 <= d12) { fr.edge = 1; fr.t = t02; fr.qx = q02x; fr.qy = q02y; }
+    else { fr.edge = 2; fr.t = t12; fr.qx = q12x; fr.qy = q12y; }
+}
+
 // 1 - sigmoid(-sd/sigma) the way the reference forms it in fp32: p = sigmoid(x), m = 1 - p.
 SMF_HD void frag_prob(float sd, float& p, float& m) {
 #if defined(__CUDA_ARCH__)
