@@ -274,9 +274,19 @@ def run_ours(args):
     phase_ms = {k: statistics.mean(p[k] for p in prof) for k in prof[0]}
     cnt = fitter.counters()
 
-    if rank != 0:
+    def finish():
+        # leave without tearing NCCL down: destroying the process group while CUDA graphs that captured
+        # its collectives are alive can dead-lock; every measurement is complete at this point
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            torch.distributed.destroy_process_group()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if world > 1:
+        torch.distributed.barrier()
+    if rank != 0:
+        finish()
         return
     peaks, peak_kind = measured_peaks()
     V, F = c.v_template.shape[0], c.faces.shape[0]
@@ -322,8 +332,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": None, "unit": "iters/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {ex!r}"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
