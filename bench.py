@@ -147,7 +147,7 @@ def run_reference(args):
     cores = raster_c.num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": 1000.0 * t_full, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": 1000.0 * t_full, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"synthetic rs_dog-like sequence, WINDOW_SIZE={N}, {S}x{S} sil, stage-1 weights",
                    "frames": N, "image_size": S},

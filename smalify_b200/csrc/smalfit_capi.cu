@@ -209,7 +209,13 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     w.gjoint = P.alloc<float>(N * NMJ * 3, true);
     w.kp_proj = P.alloc<float>(N * NKP * 2, true);
     w.face_rect = P.alloc<uint2>(N * m.Fp);
-    w.pool_cap = 8 * m.Fp;
+    {   // (face, tile) entries per frame grow with the face size in pixels: ~Fp * ((bbox_px + 32) / 32)^2
+        const float bbox_px = 18.f * (float)image_size / 256.f;
+        const float per_face = ((bbox_px + 32.f) / 32.f) * ((bbox_px + 32.f) / 32.f);
+        int mult = (int)(2.5f * per_face + 1.f);
+        mult = mult < 8 ? 8 : (mult > 64 ? 64 : mult);
+        w.pool_cap = mult * m.Fp;
+    }
     w.tile_pool = P.alloc<uint4>(N * (size_t)w.pool_cap);
     w.tile_off = P.alloc<unsigned>(N * (tiles + 1), true);
     w.tile_order = P.alloc<unsigned short>(N * tiles, true);
@@ -244,6 +250,8 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     h->sc.fid = P.alloc<unsigned short>(n_warps * m.Fp);
     h->adam_state = P.alloc<AdamState>(1, true);
     w.work_counter = P.alloc<unsigned int>(1, true);
+    w.temporal_partial = P.alloc<float>(((size_t)N * 108 + 255) / 256 * 3 + 3, true);
+    w.temporal_ticket = P.alloc<unsigned>(1, true);
     w.counters = P.alloc<unsigned long long>(4, true);
     if (P.err != cudaSuccess) {
         const cudaError_t pe = P.err;
@@ -394,12 +402,13 @@ int smalfit_adam_step(smalfit_t h, const smalfit_tensors_t* params, const smalfi
     const int len[5] = {ns * NBETA, ns * NLS, n_frames * 3, n_frames * (NJ - 1) * 3, n_frames * 3};
     launch_adam_tick(h->adam_state, beta1, beta2, step, st);
     h->n_launches += 1;
+    AdamSegments seg;
     for (int i = 0; i < 5; ++i) {
-        if (!train[i]) continue;
-        if (!P5[i] || !G5[i] || !M5[i] || !V5[i]) return fail(h, SMALFIT_EINVAL, "smalfit_adam_step: NULL tensor %d", i);
-        launch_adam(P5[i], G5[i], M5[i], V5[i], len[i], lr, beta1, beta2, eps, h->adam_state, st);
-        h->n_launches += 1;
+        seg.p[i] = P5[i]; seg.g[i] = G5[i]; seg.m[i] = M5[i]; seg.v[i] = V5[i]; seg.len[i] = len[i]; seg.train[i] = train[i] ? 1 : 0;
+        if (train[i] && (!P5[i] || !G5[i] || !M5[i] || !V5[i])) return fail(h, SMALFIT_EINVAL, "smalfit_adam_step: NULL tensor %d", i);
     }
+    launch_adam5(seg, lr, beta1, beta2, eps, h->adam_state, st);
+    h->n_launches += 1;
     return check_launch(h, "adam kernel");
 }
 

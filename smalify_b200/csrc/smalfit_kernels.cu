@@ -139,7 +139,7 @@ __device__ void frame_pose_forward(FrameSmem& S, const ModelDev& m, const Worksp
 // ---------------------------------------------------------------------------
 // frame_forward
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(FRAME_THREADS)
+__global__ void __launch_bounds__(FRAME_FWD_THREADS)
 frame_forward_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, float* verts_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FrameSmem& S = *reinterpret_cast<FrameSmem*>(smem_raw);
@@ -153,7 +153,7 @@ frame_forward_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, 
 
     // sparse linear-blend skinning + camera
     float4* ndc = w.ndc + (size_t)fr * m.Vp;
-    for (int v = tid; v < m.V; v += FRAME_THREADS) {
+    for (int v = tid; v < m.V; v += blockDim.x) {
         const float x = vs[v * 3 + 0], y = vs[v * 3 + 1], z = vs[v * 3 + 2];
         float ax = 0.f, ay = 0.f, az = 0.f;
 #pragma unroll
@@ -178,11 +178,11 @@ frame_forward_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, 
             o[0] = X; o[1] = Y; o[2] = Z;
         }
     }
-    for (int v = m.V + tid; v < m.Vp; v += FRAME_THREADS) ndc[v] = make_float4(0.f, 0.f, -1.f, 0.f);
+    for (int v = m.V + tid; v < m.Vp; v += blockDim.x) ndc[v] = make_float4(0.f, 0.f, -1.f, 0.f);
     __syncthreads();
 
     // 41 model joints: regressed from the posed vertices (+ trans), smal_torch.py:171-184
-    for (int j = wid; j < NMJ; j += FRAME_THREADS / 32) {
+    for (int j = wid; j < NMJ; j += (int)(blockDim.x >> 5)) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
         for (int e = m.mj_ptr[j] + lane; e < m.mj_ptr[j + 1]; e += 32) {
             const float wk = m.mj_weight[e];
@@ -229,7 +229,7 @@ frame_forward_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, 
 void launch_frame_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n,
                           Weights wt, float* verts_out, cudaStream_t st) {
     const size_t smem = sizeof(FrameSmem) + (size_t)m.V * 3 * sizeof(float);
-    frame_forward_kernel<<<n, FRAME_THREADS, smem, st>>>(m, w, p, frame0, wt, verts_out);
+    frame_forward_kernel<<<n, FRAME_FWD_THREADS, smem, st>>>(m, w, p, frame0, wt, verts_out);
 }
 
 // ---------------------------------------------------------------------------
@@ -745,22 +745,17 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(ModelDev m, Worksp
             const uint2 pr = pix[(size_t)y * S + x];
             const float coef = __uint_as_float(pr.x);
             if (coef == 0.f) continue;
-            const float px = pix_to_ndc(x, inv_s), py = pix_to_ndc(y, inv_s);
-            // same acceptance test and depth as the forward pass (frag_forward); the depth only matters
-            // for pixels that carry a K-nearest threshold
-            const bool capped = pr.y != 0xffffffffu;
-            float sd, pz;
-            if (!frag_forward(A.x, A.y, A.z, B.x, B.y, B.z, C.x, C.y, C.z, px, py, capped, sd, pz)) continue;
-            if (capped) {
-                const unsigned key = __float_as_uint(pz + 0.f);
+            // same edge functions / depth as the forward pass (bit-identical keys); the clamped-t
+            // distances differ from the forward's only in the last bits
+            Fragment frag;
+            if (!face_eval(fs, pix_to_ndc(x, inv_s), pix_to_ndc(y, inv_s), frag)) continue;
+            if (pr.y != 0xffffffffu) {
+                const unsigned key = __float_as_uint(frag.pz + 0.f);
                 if (key > pr.y) continue;
                 if (key == pr.y && (unsigned)f > (unsigned)w.pix_tfid[((size_t)fr * S + y) * S + x]) continue;
             }
             float p, mv;
-            frag_prob(sd, p, mv);
-            Fragment frag;
-            closest_edge(fs, px, py, frag);
-            frag.sd = sd;
+            frag_prob(frag.sd, p, mv);
             frag_grad(frag, -coef * p, g);
         }
 #pragma unroll
@@ -781,7 +776,7 @@ void launch_raster_backward(const ModelDev& m, const Workspace& w, int frame0, i
 // ---------------------------------------------------------------------------
 // frame_backward
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(FRAME_THREADS)
+__global__ void __launch_bounds__(FRAME_BWD_THREADS)
 frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, Weights wt) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FrameSmem& S = *reinterpret_cast<FrameSmem*>(smem_raw);
@@ -801,7 +796,7 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
     const float* fg = w.face_grad + (size_t)fr * m.Fp * 8;
     float* dvs = w.dvs + (size_t)fr * m.V * 3;
     float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-    for (int v = tid; v < m.V; v += FRAME_THREADS) {
+    for (int v = tid; v < m.V; v += blockDim.x) {
         float g0 = 0.f, g1 = 0.f, g2 = 0.f;
         if (use_sil) {
             float gx = 0.f, gy = 0.f;
@@ -843,7 +838,7 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
     __syncthreads();
 
     // 2. per joint: dL/dG_j = sum_v w gw_v vs_v^T, dL/doff_j = sum_v w gw_v
-    for (int j = wid; j < NJ; j += FRAME_THREADS / 32) {
+    for (int j = wid; j < NJ; j += (int)(blockDim.x >> 5)) {
         float a[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) a[k] = 0.f;
@@ -933,7 +928,7 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
     float lsil = 0.f;
     if (use_sil) {
         const int R = w.tiles_x * w.tiles_y * REGIONS_PER_TILE;
-        for (int r = tid; r < R; r += FRAME_THREADS) lsil += w.region_l1[(size_t)fr * R + r];
+        for (int r = tid; r < R; r += blockDim.x) lsil += w.region_l1[(size_t)fr * R + r];
         lsil = block_sum(lsil, S.red) * wt.sil * invw / ((float)w.S * (float)w.S);
     }
     if (tid == 0) { w.frame_loss[fr * 4 + 1] = lpose; w.frame_loss[fr * 4 + 2] = lsplay; w.frame_loss[fr * 4 + 3] = lsil; }
@@ -944,7 +939,7 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
 void launch_frame_backward(const ModelDev& m, const Workspace& w, const Params& p, const Grads& g,
                            int frame0, int n, Weights wt, cudaStream_t st) {
     const size_t smem = sizeof(FrameSmem) + (size_t)m.V * 3 * sizeof(float);
-    frame_backward_kernel<<<n, FRAME_THREADS, smem, st>>>(m, w, p, g, frame0, wt);
+    frame_backward_kernel<<<n, FRAME_BWD_THREADS, smem, st>>>(m, w, p, g, frame0, wt);
 }
 
 // ---------------------------------------------------------------------------
@@ -1069,10 +1064,12 @@ void launch_shape_backward(const ModelDev& m, const Workspace& w, const Params& 
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) temporal_kernel(Workspace w, Params p, Grads g, int N, float w_temp, float* terms) {
     __shared__ float red[40];
+    __shared__ bool s_last;
     const int tid = threadIdx.x;
     float lj = 0.f, lg = 0.f, lt = 0.f;
     const int per = 3 + (NJ - 1) * 3 + 3;    // 108 values per frame: glob(3) joint(102) trans(3)
-    for (int idx = tid; idx < N * per; idx += blockDim.x) {
+    const int idx = blockIdx.x * blockDim.x + tid;
+    if (idx < N * per) {
         const int fr = idx / per, k = idx - fr * per;
         const float* src; float* dst; float mask; float norm; int stride, off;
         if (k < 3) { src = p.glob; dst = g.glob; stride = 3; off = k; mask = w.gmask[k]; norm = 1.f / 3.f; }
@@ -1093,11 +1090,29 @@ __global__ void __launch_bounds__(256) temporal_kernel(Workspace w, Params p, Gr
         if (dst) dst[(size_t)fr * stride + off] += grad * mask;
     }
     lj = block_sum(lj, red); lg = block_sum(lg, red); lt = block_sum(lt, red);
-    if (tid == 0 && terms) { terms[0] = lj; terms[1] = lg; terms[2] = lt; }
+    // fixed-order sum of the per-block partials by the last block to arrive
+    if (tid == 0) {
+        float* part = w.temporal_partial + blockIdx.x * 3;
+        part[0] = lj; part[1] = lg; part[2] = lt;
+        __threadfence();
+        s_last = (atomicAdd(w.temporal_ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && tid == 0) {
+        __threadfence();
+        float a = 0.f, b = 0.f, c = 0.f;
+        for (unsigned i = 0; i < gridDim.x; ++i) {
+            const volatile float* part = w.temporal_partial + i * 3;
+            a += part[0]; b += part[1]; c += part[2];
+        }
+        if (terms) { terms[0] = a; terms[1] = b; terms[2] = c; }
+        *w.temporal_ticket = 0u;
+    }
 }
 
 void launch_temporal(const Workspace& w, const Params& p, const Grads& g, int N, float w_temp, float* terms, cudaStream_t st) {
-    temporal_kernel<<<1, 256, 0, st>>>(w, p, g, N, w_temp, terms);
+    const int total = N * (3 + (NJ - 1) * 3 + 3);
+    temporal_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, p, g, N, w_temp, terms);
 }
 
 // ---------------------------------------------------------------------------
@@ -1122,6 +1137,30 @@ __global__ void __launch_bounds__(256) adam_kernel(float* p, const float* g, flo
     m[i] = mi; v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     p[i] -= (lr / bc1) * (mi / denom);
+}
+
+__global__ void __launch_bounds__(256) adam5_kernel(AdamSegments seg, float lr, float b1, float b2, float eps, const AdamState* s) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = 0;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        if (k == q && i >= seg.len[q]) { i -= seg.len[q]; k = q + 1; }
+    }
+    if (k >= 5 || !seg.train[k]) return;
+    const float bc1 = s->bc1, bc2_sqrt = s->bc2_sqrt;
+    const float gi = seg.g[k][i];
+    const float mi = b1 * seg.m[k][i] + (1.f - b1) * gi;
+    const float vi = b2 * seg.v[k][i] + (1.f - b2) * gi * gi;
+    seg.m[k][i] = mi; seg.v[k][i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    seg.p[k][i] -= (lr / bc1) * (mi / denom);
+}
+
+void launch_adam5(const AdamSegments& seg, float lr, float b1, float b2, float eps, const AdamState* s, cudaStream_t st) {
+    int total = 0;
+    for (int q = 0; q < 5; ++q) total += seg.len[q];
+    if (total <= 0) return;
+    adam5_kernel<<<(total + 255) / 256, 256, 0, st>>>(seg, lr, b1, b2, eps, s);
 }
 
 void launch_adam_tick(AdamState* s, float b1, float b2, int host_step, cudaStream_t st) {

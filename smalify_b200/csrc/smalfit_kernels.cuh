@@ -7,7 +7,8 @@
 
 namespace smf {
 
-constexpr int FRAME_THREADS = 256;
+constexpr int FRAME_FWD_THREADS = 512;
+constexpr int FRAME_BWD_THREADS = 1024;
 constexpr int RAST_WARPS = 16;              // warps per raster-forward CTA (one CTA per SM)
 constexpr int RAST_THREADS = RAST_WARPS * 32;
 constexpr int REGION_W = 8, REGION_H = 4;   // pixels handled by one warp at a time
@@ -88,11 +89,14 @@ struct Workspace {
     const float* gmask;         // [3]
     const float* rmask;         // [102]
     unsigned int* work_counter; // [1]
+    float* temporal_partial;    // [blocks][3] per-block temporal loss partials
+    unsigned* temporal_ticket;  // [1]
     unsigned long long* counters;   // [4]
 };
 
 struct Weights { float j2d, sil, betas, pose, limit, splay; };
 struct AdamState { int step; float bc1; float bc2_sqrt; int pad; };
+struct AdamSegments { float* p[5]; const float* g[5]; float* m[5]; float* v[5]; int len[5]; int train[5]; };
 
 struct RasterScratch {      // per resident warp, [n_raster_warps][Fp] each
     unsigned* key; float* m; unsigned short* fid;          // fragments beyond KCAP of a pixel
@@ -118,6 +122,7 @@ void launch_shape_backward(const ModelDev& m, const Workspace& w, const Params& 
                            cudaStream_t st);
 void launch_temporal(const Workspace& w, const Params& p, const Grads& g, int N, float w_temp,
                      float* terms, cudaStream_t st);
+void launch_adam5(const AdamSegments& seg, float lr, float b1, float b2, float eps, const AdamState* s, cudaStream_t st);
 void launch_adam_tick(AdamState* s, float b1, float b2, int host_step, cudaStream_t st);
 void launch_adam(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2,
                  float eps, const AdamState* s, cudaStream_t st);
