@@ -294,8 +294,15 @@ def run_ours(args):
     alg_bytes = frames_rank * b_alg_bytes(S, V, F)
     rf_ms = phase_ms["raster_forward"]
     achieved = alg_bytes / (rf_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "raster_forward_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            t = json.load(fh)
+        if t.get("frames_per_gpu") == frames_rank and t.get("image_size") == S:
+            traffic = t["dram_bytes_per_launch"]      # dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
                 "kernel": "raster_forward_kernel", "kernel_ms": rf_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "phase_ms": phase_ms,
                 "note": "path is FP32-ALU bound (SURVEY 8d): HBM fraction is reported as the contract asks"}

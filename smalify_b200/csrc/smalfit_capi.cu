@@ -60,7 +60,7 @@ struct smalfit_ctx {
     bool targets_set = false;
     DevPool pool;
     std::string error;
-    long long n_raster_launches = 0, n_launches = 0;
+    long long n_launches = 0;
     bool profiling = false;
     cudaEvent_t ev[8] = {};
     bool ev_valid = false;
@@ -249,7 +249,6 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     h->sc.m = P.alloc<float>(n_warps * m.Fp);
     h->sc.fid = P.alloc<unsigned short>(n_warps * m.Fp);
     h->adam_state = P.alloc<AdamState>(1, true);
-    w.work_counter = P.alloc<unsigned int>(1, true);
     w.temporal_partial = P.alloc<float>(((size_t)N * 108 + 255) / 256 * 3 + 3, true);
     w.temporal_ticket = P.alloc<unsigned>(1, true);
     w.counters = P.alloc<unsigned long long>(4, true);
@@ -342,7 +341,6 @@ static int run_forward(smalfit_t h, const Params& p, int frame0, int n, Weights 
         h->mark(2, st);
         launch_raster_forward(h->m, h->w, h->sc, h->ndc_soa, frame0, n, wt, alpha_out, h->raster_ctas, st);
         h->n_launches += 3;
-        h->n_raster_launches += 1;
     } else {
         h->mark(2, st);
     }
@@ -365,7 +363,7 @@ int smalfit_loss_grad(smalfit_t h, const smalfit_tensors_t* params, int frame0, 
     const bool raster = wt.sil > 0.f;
     int rc = run_forward(h, p, frame0, n, wt, raster, nullptr, nullptr, st);
     if (rc) return rc;
-    if (raster) { launch_raster_backward(h->m, h->w, frame0, n, st); h->n_launches += 1; h->n_raster_launches += 1; }
+    if (raster) { launch_raster_backward(h->m, h->w, frame0, n, st); h->n_launches += 1; }
     h->mark(4, st);
     launch_frame_backward(h->m, h->w, p, g, frame0, n, wt, st);
     h->mark(5, st);

@@ -247,19 +247,19 @@ __device__ __forceinline__ FaceSetup load_face(const float4* ndc, ushort4 f4) {
     return fs;
 }
 
-__global__ void __launch_bounds__(256) bin_faces_kernel(ModelDev m, Workspace w, int frame0) {
+__global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Workspace w, int frame0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = w.tiles_x * w.tiles_y;
-    unsigned* cnt = reinterpret_cast<unsigned*>(smem_raw);          // [8][T] counts, then cursors
-    unsigned* tot = cnt + 8 * T;                                    // [T]
-    __shared__ unsigned part[256];
+    unsigned* cnt = reinterpret_cast<unsigned*>(smem_raw);          // [BIN_WARPS][T] counts, then cursors
+    unsigned* tot = cnt + BIN_WARPS * T;                                    // [T]
+    __shared__ unsigned part[BIN_THREADS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int fr = frame0 + blockIdx.x;
     const float4* ndc = w.ndc + (size_t)fr * m.Vp;
     uint2* rects = w.face_rect + (size_t)fr * m.Fp;
-    for (int i = tid; i < 8 * T; i += 256) cnt[i] = 0u;
+    for (int i = tid; i < BIN_WARPS * T; i += BIN_THREADS) cnt[i] = 0u;
     __syncthreads();
-    const int seg = ((m.Fp / 8) + 31) / 32 * 32;
+    const int seg = ((m.Fp + BIN_WARPS - 1) / BIN_WARPS + 31) / 32 * 32;
     const int f_lo = min(wid * seg, m.Fp), f_hi = min(f_lo + seg, m.Fp);
     // pass 1: rectangles + counts
     for (int f = f_lo + lane; f < f_hi; f += 32) {
@@ -275,13 +275,13 @@ __global__ void __launch_bounds__(256) bin_faces_kernel(ModelDev m, Workspace w,
     }
     __syncthreads();
     // prefix over tiles (blocked: each thread owns a run of consecutive tiles)
-    const int per = (T + 255) / 256;
+    const int per = (T + BIN_THREADS - 1) / BIN_THREADS;
     unsigned local = 0;
     for (int k = 0; k < per; ++k) {
         const int t = tid * per + k;
         if (t < T) {
             unsigned a = 0;
-            for (int q = 0; q < 8; ++q) a += cnt[q * T + t];
+            for (int q = 0; q < BIN_WARPS; ++q) a += cnt[q * T + t];
             tot[t] = a;
             local += a;
         }
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(256) bin_faces_kernel(ModelDev m, Workspace w,
     __syncthreads();
     if (tid == 0) {
         unsigned run = 0;
-        for (int i = 0; i < 256; ++i) { const unsigned v = part[i]; part[i] = run; run += v; }
+        for (int i = 0; i < BIN_THREADS; ++i) { const unsigned v = part[i]; part[i] = run; run += v; }
     }
     __syncthreads();
     unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
@@ -300,14 +300,14 @@ __global__ void __launch_bounds__(256) bin_faces_kernel(ModelDev m, Workspace w,
         if (t < T) {
             toff[t] = run;
             unsigned r2 = run;
-            for (int q = 0; q < 8; ++q) { const unsigned c = cnt[q * T + t]; cnt[q * T + t] = r2; r2 += c; }
+            for (int q = 0; q < BIN_WARPS; ++q) { const unsigned c = cnt[q * T + t]; cnt[q * T + t] = r2; r2 += c; }
             run += tot[t];
             if (t == T - 1) toff[T] = run;
         }
     }
     // hand-out order of the tiles: longest list first, so a frame's last regions are the cheap ones
     unsigned short* order = w.tile_order + (size_t)fr * T;
-    for (int t = tid; t < T; t += 256) {
+    for (int t = tid; t < T; t += BIN_THREADS) {
         const unsigned c = tot[t];
         int rank = 0;
         for (int u = 0; u < T; ++u) { const unsigned cu = tot[u]; rank += (cu > c || (cu == c && u < t)) ? 1 : 0; }
@@ -355,10 +355,10 @@ __global__ void __launch_bounds__(256) bin_faces_kernel(ModelDev m, Workspace w,
     if (dropped) atomicAdd(w.counters + 2, (unsigned long long)dropped);
 }
 
-size_t bin_smem_bytes(const Workspace& w) { return (size_t)9 * w.tiles_x * w.tiles_y * sizeof(unsigned); }
+size_t bin_smem_bytes(const Workspace& w) { return (size_t)(BIN_WARPS + 1) * w.tiles_x * w.tiles_y * sizeof(unsigned); }
 
 void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st) {
-    bin_faces_kernel<<<n, 256, bin_smem_bytes(w), st>>>(m, w, frame0);
+    bin_faces_kernel<<<n, BIN_THREADS, bin_smem_bytes(w), st>>>(m, w, frame0);
 }
 
 // ---------------------------------------------------------------------------
@@ -1202,7 +1202,7 @@ cudaError_t configure_kernels(const ModelDev& m) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(frame_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(bin_faces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 1024 * (int)sizeof(unsigned));
+    e = cudaFuncSetAttribute(bin_faces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (BIN_WARPS + 1) * MAX_TILES * (int)sizeof(unsigned));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(raster_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes(m));
 }

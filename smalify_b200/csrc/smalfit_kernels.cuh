@@ -8,6 +8,7 @@
 namespace smf {
 
 constexpr int FRAME_FWD_THREADS = 512;
+constexpr int BIN_WARPS = 32, BIN_THREADS = BIN_WARPS * 32;
 constexpr int FRAME_BWD_THREADS = 1024;
 constexpr int RAST_WARPS = 16;              // warps per raster-forward CTA (one CTA per SM)
 constexpr int RAST_THREADS = RAST_WARPS * 32;
@@ -88,7 +89,6 @@ struct Workspace {
     const float* inv_window;    // [N] 1 / frames_per_window
     const float* gmask;         // [3]
     const float* rmask;         // [102]
-    unsigned int* work_counter; // [1]
     float* temporal_partial;    // [blocks][3] per-block temporal loss partials
     unsigned* temporal_ticket;  // [1]
     unsigned long long* counters;   // [4]

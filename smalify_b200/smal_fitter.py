@@ -368,7 +368,7 @@ class FusedFit:
         self.sizes = FusedFit.SIZES(n)
         total = sum(self.sizes)
         self.flat_p = torch.empty(total, device=dev)
-        self.flat_g = torch.zeros(total, device=dev)
+        self.flat_g = torch.zeros(total + 8, device=dev)       # + the 8 loss terms: one all-reduce covers both
         self.flat_m = torch.zeros(total, device=dev)
         self.flat_v = torch.zeros(total, device=dev)
         names = ("betas", "log_beta_scales", "global_rotation", "joint_rotations", "trans")
@@ -391,7 +391,7 @@ class FusedFit:
         self.n_windows = (n + self.window - 1) // self.window
         self.shard = frame_shard or (0, n)
         self.group = process_group
-        self.terms = torch.zeros(8, device=dev)
+        self.terms = self.flat_g[total:total + 8]
         self.temporal_terms = torch.zeros(3, device=dev)
         self.step_count = 0
         self._graph = None
@@ -425,8 +425,7 @@ class FusedFit:
                                         self.n_windows if rank0 else 0, ctypes.byref(grads), _ptr(self.terms), st),
                 "smalfit_loss_grad")
         if sharded:
-            torch.distributed.all_reduce(self.flat_g, group=self.group)
-            torch.distributed.all_reduce(self.terms, group=self.group)
+            torch.distributed.all_reduce(self.flat_g, group=self.group)      # gradients + loss terms
         h.check(h.lib.smalfit_temporal(h.h, ctypes.byref(params), f.num_images, float(w_temp), ctypes.byref(grads),
                                        _ptr(self.temporal_terms), st), "smalfit_temporal")
         tr = (ctypes.c_int32 * 5)(*[int(x) for x in train])
