@@ -251,6 +251,8 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     h->adam_state = P.alloc<AdamState>(1, true);
     w.temporal_partial = P.alloc<float>(((size_t)N * 108 + 255) / 256 * 3 + 3, true);
     w.temporal_ticket = P.alloc<unsigned>(1, true);
+    w.slot_loss = P.alloc<float>(N, true);
+    w.finalize_ticket = P.alloc<unsigned>(1, true);
     w.counters = P.alloc<unsigned long long>(4, true);
     if (P.err != cudaSuccess) {
         const cudaError_t pe = P.err;

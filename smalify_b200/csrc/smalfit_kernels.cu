@@ -978,15 +978,69 @@ shape_backward_kernel(ModelDev m, Workspace w, int frame0, int n_frames, int n_b
     }
 }
 
-// one CTA: reduce partials, add the shape prior (smal_fitter.py:162-171), sum the loss terms
+// finalize: one CTA per shape slot reduces its dL/dbetas partials and adds the shape prior
+// (smal_fitter.py:162-171); the last CTA to finish sums the loss terms in a fixed order.
 __global__ void __launch_bounds__(256)
 finalize_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, int n_frames, Weights wt,
                 int prior_windows, int n_blocks, float* loss_terms) {
     __shared__ float red[40];
     __shared__ float diff[32], res[32];
+    __shared__ bool s_last;
     const int tid = threadIdx.x;
-    // loss terms: fixed-order sums over the frames of the range
-    float lk = 0.f, lp = 0.f, lsp = 0.f, lsil = 0.f;
+    const int slot = blockIdx.x;
+    const int D = m.shape_dim;
+    // shared shapes: every window contributes w_betas * mean(res^2); per-frame shapes: one window each
+    const float pw = (w.n_shapes == 1) ? (float)prior_windows : 1.f;
+    const bool in_range = (w.n_shapes == 1) || (slot >= frame0 && slot < frame0 + n_frames);
+    const bool prior = wt.betas > 0.f && in_range;
+    const float cb = wt.betas * pw / (float)D;
+    float lbetas = 0.f;
+    if (prior) {
+        if (tid < D) diff[tid] = ((tid < NBETA) ? p.betas[slot * NBETA + tid] : p.logscale[slot * NLS + tid - NBETA]) - m.shape_mean[tid];
+        __syncthreads();
+        if (tid < D) {
+            float a = 0.f;
+            for (int i = 0; i < D; ++i) a = fmaf(diff[i], m.shape_prec[i * D + tid], a);
+            res[tid] = a;
+            lbetas = cb * a * a;
+        }
+        __syncthreads();
+    }
+    if (in_range) {
+        if (tid < NBETA && g.betas) {
+            float t = 0.f;
+            for (int q = 0; q < n_blocks; ++q) t += w.beta_partial[((size_t)slot * n_blocks + q) * NBETA + tid];
+            if (prior) {
+                float a = 0.f;
+                for (int k = 0; k < D; ++k) a = fmaf(m.shape_prec[tid * D + k], res[k], a);
+                t += 2.f * cb * a;
+            }
+            g.betas[slot * NBETA + tid] = t;
+        }
+        if (tid >= 32 && tid < 32 + NLS && g.logscale) {
+            const int k = tid - 32;
+            const int fa = (w.n_shapes == 1) ? frame0 : slot, fb = (w.n_shapes == 1) ? frame0 + n_frames : slot + 1;
+            float t = 0.f;
+            for (int fr = fa; fr < fb; ++fr) t += w.gls[fr * NLS + k];
+            if (prior && D > NBETA) {       // the log-scale entries live at index 20+k of the 26-d residual
+                float a = 0.f;
+                for (int kk = 0; kk < D; ++kk) a = fmaf(m.shape_prec[(NBETA + k) * D + kk], res[kk], a);
+                t += 2.f * cb * a;
+            }
+            g.logscale[slot * NLS + k] = t;
+        }
+    }
+    lbetas = block_sum(lbetas, red);
+    if (tid == 0) {
+        w.slot_loss[slot] = lbetas;
+        __threadfence();
+        s_last = (atomicAdd(w.finalize_ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // loss terms: fixed-order sums over the frames of the range and over the slots
+    float lk = 0.f, lp = 0.f, lsp = 0.f, lsil = 0.f, lb = 0.f;
     for (int f = tid; f < n_frames; f += blockDim.x) {
         const int fr = frame0 + f;
         lk += w.frame_loss[fr * 4 + 0];
@@ -994,60 +1048,16 @@ finalize_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, int n_fr
         lsp += w.frame_loss[fr * 4 + 2];
         if (wt.sil > 0.f) lsil += w.frame_loss[fr * 4 + 3];
     }
+    for (int q = tid; q < w.n_shapes; q += blockDim.x) lb += ((volatile float*)w.slot_loss)[q];
     lk = block_sum(lk, red); lp = block_sum(lp, red); lsp = block_sum(lsp, red); lsil = block_sum(lsil, red);
-
-    float lbetas = 0.f;
-    for (int slot = 0; slot < w.n_shapes; ++slot) {
-        const int D = m.shape_dim;
-        // shared shapes: every window contributes w_betas * mean(res^2); per-frame shapes: one window each
-        const float pw = (w.n_shapes == 1) ? (float)prior_windows : 1.f;
-        const bool in_range = (w.n_shapes == 1) || (slot >= frame0 && slot < frame0 + n_frames);
-        if (wt.betas > 0.f && in_range) {
-            if (tid < D) diff[tid] = ((tid < NBETA) ? p.betas[slot * NBETA + tid] : p.logscale[slot * NLS + tid - NBETA]) - m.shape_mean[tid];
-            __syncthreads();
-            if (tid < D) {
-                float a = 0.f;
-                for (int i = 0; i < D; ++i) a = fmaf(diff[i], m.shape_prec[i * D + tid], a);
-                res[tid] = a;
-            }
-            __syncthreads();
+    lb = block_sum(lb, red);
+    if (tid == 0) {
+        if (loss_terms) {
+            loss_terms[0] = lk; loss_terms[1] = lsil; loss_terms[2] = lb; loss_terms[3] = lp;
+            loss_terms[4] = 0.f; loss_terms[5] = lsp; loss_terms[6] = 0.f;
+            loss_terms[7] = lk + lsil + lb + lp + lsp;
         }
-        const float cb = wt.betas * pw / (float)D;
-        float pg = 0.f;
-        if (wt.betas > 0.f && in_range && tid < D) {
-            float a = 0.f;
-            for (int k = 0; k < D; ++k) a = fmaf(m.shape_prec[tid * D + k], res[k], a);
-            pg = 2.f * cb * a;
-            lbetas += cb * res[tid] * res[tid];
-        }
-        if (in_range) {
-            if (tid < NBETA && g.betas) {
-                float t = 0.f;
-                for (int q = 0; q < n_blocks; ++q) t += w.beta_partial[((size_t)slot * n_blocks + q) * NBETA + tid];
-                g.betas[slot * NBETA + tid] = t + pg;
-            }
-            if (tid >= 32 && tid < 32 + NLS && g.logscale) {
-                const int k = tid - 32;
-                const int fa = (w.n_shapes == 1) ? frame0 : slot, fb = (w.n_shapes == 1) ? frame0 + n_frames : slot + 1;
-                float t = 0.f;
-                for (int fr = fa; fr < fb; ++fr) t += w.gls[fr * NLS + k];
-                // prior gradient of the log-scale entries lives at index 20+k of the 26-d residual
-                float pgl = 0.f;
-                if (wt.betas > 0.f && D > NBETA) {
-                    float a = 0.f;
-                    for (int kk = 0; kk < D; ++kk) a = fmaf(m.shape_prec[(NBETA + k) * D + kk], res[kk], a);
-                    pgl = 2.f * cb * a;
-                }
-                g.logscale[slot * NLS + k] = t + pgl;
-            }
-        }
-        __syncthreads();
-    }
-    lbetas = block_sum(lbetas, red);
-    if (tid == 0 && loss_terms) {
-        loss_terms[0] = lk; loss_terms[1] = lsil; loss_terms[2] = lbetas; loss_terms[3] = lp;
-        loss_terms[4] = 0.f; loss_terms[5] = lsp; loss_terms[6] = 0.f;
-        loss_terms[7] = lk + lsil + lbetas + lp + lsp;
+        *w.finalize_ticket = 0u;
     }
 }
 
@@ -1056,7 +1066,7 @@ void launch_shape_backward(const ModelDev& m, const Workspace& w, const Params& 
     const int n_blocks = (m.V * 3 + 255) / 256;
     dim3 grid(n_blocks, w.n_shapes);
     shape_backward_kernel<<<grid, 256, 0, st>>>(m, w, frame0, n, n_blocks);
-    finalize_kernel<<<1, 256, 0, st>>>(m, w, p, g, frame0, n, wt, prior_windows, n_blocks, loss_terms);
+    finalize_kernel<<<w.n_shapes, 256, 0, st>>>(m, w, p, g, frame0, n, wt, prior_windows, n_blocks, loss_terms);
 }
 
 // ---------------------------------------------------------------------------

@@ -89,6 +89,8 @@ struct Workspace {
     const float* inv_window;    // [N] 1 / frames_per_window
     const float* gmask;         // [3]
     const float* rmask;         // [102]
+    float* slot_loss;           // [N] shape-prior loss per shape slot
+    unsigned* finalize_ticket;  // [1]
     float* temporal_partial;    // [blocks][3] per-block temporal loss partials
     unsigned* temporal_ticket;  // [1]
     unsigned long long* counters;   // [4]

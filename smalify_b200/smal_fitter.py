@@ -85,11 +85,20 @@ class _LossGradFn(torch.autograd.Function):
         ws = f._grad_ws
         need = ctx.needs_input_grad          # (fitter, frame0, n, weights, betas, lbs, glob, joint, trans)
         out = [None, None, None, None]
-        out.append(grad_loss * ctx.g_betas if need[4] else None)
-        if need[5]:
-            out.append(grad_loss * ctx.g_lbs if f.use_unity_prior else torch.zeros_like(f.log_beta_scales))
+        if f.per_frame_shapes:
+            for idx, gsrc in ((4, ctx.g_betas), (5, ctx.g_lbs)):
+                if need[idx]:
+                    gfull = torch.zeros_like(gsrc)
+                    gfull[a:a + n] = grad_loss * gsrc[a:a + n]
+                    out.append(gfull)
+                else:
+                    out.append(None)
         else:
-            out.append(None)
+            out.append(grad_loss * ctx.g_betas if need[4] else None)
+            if need[5]:
+                out.append(grad_loss * ctx.g_lbs if f.use_unity_prior else torch.zeros_like(f.log_beta_scales))
+            else:
+                out.append(None)
         for idx, key in ((6, "global_rotation"), (7, "joint_rotations"), (8, "trans")):
             if need[idx]:
                 g = torch.zeros_like(ws[key])
@@ -128,7 +137,7 @@ class SMALFitter(nn.Module):
 
     def __init__(self, device, data_batch, batch_size, shape_family, use_unity_prior,
                  constants: model_io.SmalConstants | None = None, data_root: str | None = None,
-                 resident_targets: bool = True):
+                 resident_targets: bool = True, per_frame_shapes: bool = False):
         super().__init__()
         self.rgb_imgs, self.sil_imgs, self.target_joints, self.target_visibility = data_batch
         self.target_visibility = self.target_visibility.long()
@@ -147,6 +156,11 @@ class SMALFitter(nn.Module):
         self.n_betas = K.N_BETAS
         self.shape_family_list = np.array(shape_family)
         self.resident_targets = resident_targets
+        # extension (BASELINE config 4, not in the reference): one shape and one window per frame,
+        # i.e. a batch of independent single-image fits
+        self.per_frame_shapes = bool(per_frame_shapes)
+        if self.per_frame_shapes and not self.use_unity_prior:
+            raise NotImplementedError("per_frame_shapes needs the unity prior (trainable log_beta_scales)")
 
         if constants is None:
             constants = (model_io.load_from_smalify_data(data_root, int(shape_family)) if data_root
@@ -157,8 +171,12 @@ class SMALFitter(nn.Module):
             mean = torch.from_numpy(constants.unity_mean).float().to(dev)
             self.mean_betas = mean.clone()
             self.betas_prec = torch.from_numpy(constants.unity_prec).float().to(dev)
-            self.betas = nn.Parameter(mean[:20].clone())
-            self.log_beta_scales = nn.Parameter(mean[20:].clone())
+            if self.per_frame_shapes:
+                self.betas = nn.Parameter(mean[:20][None].repeat(self.num_images, 1).contiguous())
+                self.log_beta_scales = nn.Parameter(mean[20:][None].repeat(self.num_images, 1).contiguous())
+            else:
+                self.betas = nn.Parameter(mean[:20].clone())
+                self.log_beta_scales = nn.Parameter(mean[20:].clone())
         else:
             self.mean_betas = torch.from_numpy(constants.cluster_mean).float().to(dev)
             self.betas_prec = torch.from_numpy(constants.cluster_prec).float().to(dev)
@@ -176,8 +194,12 @@ class SMALFitter(nn.Module):
 
         self.faces = torch.from_numpy(np.asarray(constants.faces).astype(np.int64)).to(dev)
         self._handle = _cabi.Handle(constants, self.device.index, n, self.image_size, self.use_unity_prior)
+        if self.per_frame_shapes:
+            self._handle.check(self._handle.lib.smalfit_set_per_frame_shapes(self._handle.h, 1), "smalfit_set_per_frame_shapes")
+        ns = n if self.per_frame_shapes else 1
         self._grad_ws = {
-            "betas": torch.zeros(20, device=dev), "log_beta_scales": torch.zeros(6, device=dev),
+            "betas": torch.zeros(ns * 20, device=dev).view(self.betas.shape),
+            "log_beta_scales": torch.zeros(ns * 6, device=dev).view(6) if ns == 1 else torch.zeros(n, 6, device=dev),
             "global_rotation": torch.zeros(n, 3, device=dev), "joint_rotations": torch.zeros(n, K.N_POSE, 3, device=dev),
             "trans": torch.zeros(n, 3, device=dev)}
         self._windows_for = None
@@ -239,6 +261,11 @@ class SMALFitter(nn.Module):
                 "smalfit_set_windows")
 
     def _set_window_for(self, a, n):
+        if self.per_frame_shapes:
+            if self._windows_for is None:
+                self._windows_for = np.ones(self.num_images, dtype=np.int32)
+                self.set_windows(self._windows_for)
+            return
         if self._windows_for is None:
             self._windows_for = np.full(self.num_images, self.num_images, dtype=np.int32)
             self._windows_for[:] = -1
@@ -365,14 +392,15 @@ class FusedFit:
         dev = fitter.device
         if not fitter.use_unity_prior:
             raise NotImplementedError("FusedFit supports the unity-prior (shared log_beta_scales) configuration")
-        self.sizes = FusedFit.SIZES(n)
+        ns = n if fitter.per_frame_shapes else 1
+        self.sizes = (ns * 20, ns * 6, n * 3, n * K.N_POSE * 3, n * 3)
         total = sum(self.sizes)
         self.flat_p = torch.empty(total, device=dev)
         self.flat_g = torch.zeros(total + 8, device=dev)       # + the 8 loss terms: one all-reduce covers both
         self.flat_m = torch.zeros(total, device=dev)
         self.flat_v = torch.zeros(total, device=dev)
         names = ("betas", "log_beta_scales", "global_rotation", "joint_rotations", "trans")
-        shapes = ((20,), (6,), (n, 3), (n, K.N_POSE, 3), (n, 3))
+        shapes = (tuple(fitter.betas.shape), tuple(fitter.log_beta_scales.shape), (n, 3), (n, K.N_POSE, 3), (n, 3))
         off = 0
         self.views = {}
         with torch.no_grad():
@@ -382,7 +410,7 @@ class FusedFit:
                 par.data = self.flat_p[off:off + size].view(shape)
                 self.views[name] = tuple(buf[off:off + size] for buf in (self.flat_p, self.flat_g, self.flat_m, self.flat_v))
                 off += size
-        self.window = window_size or n
+        self.window = 1 if fitter.per_frame_shapes else (window_size or n)
         wins = np.empty(n, dtype=np.int32)
         for j in range(0, n, self.window):
             wins[j:j + self.window] = min(self.window, n - j)

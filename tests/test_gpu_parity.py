@@ -118,6 +118,41 @@ def test_windows_and_temporal(fitter, oracle64, seq):
         assert H.rel_err(getattr(fitter, k).grad, getattr(p, k).grad) < 1e-4, k
 
 
+def test_per_frame_shapes_equal_independent_fits(constants, oracle64, seq):
+    """Extension (BASELINE config 4): one shape per frame = a batch of independent single-image problems.
+    Oracle side: the sum of single-frame losses, each frame with its own betas / log-scales."""
+    from smalify_b200.smal_fitter import SMALFitter
+    data, gt = seq
+    rgb, sil, joints, vis = data
+    f = SMALFitter("cuda", data, 1, 1, True, constants=constants, per_frame_shapes=True)
+    g = torch.Generator().manual_seed(21)
+    frames = []
+    total = torch.zeros((), dtype=torch.float64)
+    w = STAGE1
+    for i in range(N_SMALL):
+        p = H.perturbed_params(oracle64, {k: (v[i:i + 1] if v.dim() > 1 else v) for k, v in gt.items()}, seed=30 + i)
+        for t in p.tensors():
+            t.requires_grad_(True)
+        one = (None, sil[i:i + 1], joints[i:i + 1], vis[i:i + 1])
+        loss, _ = O.fitter_forward(oracle64, p, one[1], one[2], one[3], range(1), w, S_SMALL)
+        total = total + loss
+        frames.append(p)
+    total.backward()
+    with torch.no_grad():
+        for i, p in enumerate(frames):
+            f.betas[i] = p.betas.float().to(f.device)
+            f.log_beta_scales[i] = p.log_beta_scales.float().to(f.device)
+            f.global_rotation[i] = p.global_rotation[0].float().to(f.device)
+            f.joint_rotations[i] = p.joint_rotations[0].float().to(f.device)
+            f.trans[i] = p.trans[0].float().to(f.device)
+    loss, _ = f(list(range(N_SMALL)), w, 1)
+    loss.backward()
+    assert abs(float(loss) - float(total)) <= 2e-5 * abs(float(total))
+    for k in ("betas", "log_beta_scales", "global_rotation", "joint_rotations", "trans"):
+        ref = torch.stack([getattr(p, k).grad.reshape(getattr(f, k).shape[1:]) for p in frames])
+        assert H.rel_err(getattr(f, k).grad, ref) < 1e-4, k
+
+
 def test_missing_library_fails_loudly(tmp_path):
     from smalify_b200 import _cabi
     with pytest.raises(_cabi.SmalfitError):
