@@ -120,6 +120,7 @@ def run_reference(args):
     from oracle import cpu_path, raster_c
     from oracle import smal_oracle as O
     import helpers as H
+    raster_c.use_all_cores()
     c = model_io.load_asset()
     S, N = args.size, args.frames
     sample = max(2, min(args.cpu_sample_frames, N))
@@ -175,6 +176,7 @@ def run_ours(args):
     group = None
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     N, S = args.frames, args.size
@@ -328,6 +330,7 @@ def run_ours(args):
         try:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             from oracle import cpu_path, raster_c
+            raster_c.use_all_cores()
             sample = max(2, min(args.cpu_sample_frames, N))
             sub = tuple(None if t is None else t[:sample] for t in data)
             dt, _ = cpu_path.time_cpu_epochs(c, sub, sample, weights, w_temp, lr, S, 2, mode=1, warmup=1)

@@ -39,6 +39,8 @@ def lib():
                                                 ctypes.POINTER(ctypes.c_longlong)]
         _lib.raster_soft_silhouette.restype = None
         _lib.raster_num_threads.restype = ctypes.c_int
+        _lib.raster_set_threads.argtypes = [ctypes.c_int]
+        _lib.raster_set_threads.restype = None
     return _lib
 
 
@@ -88,3 +90,12 @@ class SoftSilhouetteC(torch.autograd.Function):
 
 def num_threads() -> int:
     return int(lib().raster_num_threads())
+
+
+def use_all_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core."""
+    import os
+    n = os.cpu_count() or 1
+    lib().raster_set_threads(n)
+    torch.set_num_threads(n)
+    return num_threads()

@@ -186,6 +186,14 @@ void raster_soft_silhouette(const float* verts, int V, const int* faces, int F, 
     if (stats) { stats[0] = s_pair; stats[1] = s_frag; stats[2] = s_touch; stats[3] = s_cap; }
 }
 
+void raster_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int raster_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
