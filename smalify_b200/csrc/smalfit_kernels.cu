@@ -542,14 +542,19 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
         const unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
         const unsigned short* torder = w.tile_order + (size_t)fr * T;
         const uint4* pool = w.tile_pool + (size_t)fr * w.pool_cap;
+        // the next region index is drawn one region ahead so that the atomic's round trip is hidden
+        unsigned next_reg = 0;
+        if (lane == 0) {
+            next_reg = atomicAdd(w.frame_next + fr, 1u);
+            if (next_reg == (unsigned)R) atomicAdd(w.frames_done, 1u);          // first draw past the end
+        }
         for (;;) {
-            unsigned reg = 0;
-            if (lane == 0) {
-                reg = atomicAdd(w.frame_next + fr, 1u);
-                if (reg == (unsigned)R) atomicAdd(w.frames_done, 1u);      // first draw past the end
-            }
-            reg = __shfl_sync(0xffffffffu, reg, 0);
+            const unsigned reg = __shfl_sync(0xffffffffu, next_reg, 0);
             if (reg >= (unsigned)R) break;
+            if (lane == 0) {
+                next_reg = atomicAdd(w.frame_next + fr, 1u);
+                if (next_reg == (unsigned)R) atomicAdd(w.frames_done, 1u);
+            }
             const int tile = (int)torder[(int)reg / REGIONS_PER_TILE], sub = (int)reg % REGIONS_PER_TILE;
             const unsigned oreg = (unsigned)(tile * REGIONS_PER_TILE + sub);      // storage index of the region
             const int lx0 = (sub % (TILE_W / REGION_W)) * REGION_W, ly0 = (sub / (TILE_W / REGION_W)) * REGION_H;
@@ -570,10 +575,13 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
             bool in_smem = true;
             for (int pass = 0; pass < 2; ++pass) {
                 L = 0;
+                uint4 e_next = make_uint4(0u, 0u, 0xffffffffu, 0u);
+                if (lane < len) e_next = pool[off + lane];
                 for (int base = 0; base < len; base += 32) {
                     const int j = base + lane;
-                    uint4 e = make_uint4(0u, 0u, 0xffffffffu, 0u);
-                    if (j < len) e = pool[off + j];
+                    const uint4 e = e_next;
+                    e_next = make_uint4(0u, 0u, 0xffffffffu, 0u);
+                    if (j + 32 < len) e_next = pool[off + j + 32];          // next block in flight while this one is filtered
                     const int c0 = (int)(e.z & 0xffu), c1 = (int)((e.z >> 8) & 0xffu), r0 = (int)((e.z >> 16) & 0xffu), r1 = (int)(e.z >> 24);
                     const bool ov = (j < len) && (c0 <= lx0 + REGION_W - 1) && (c1 >= lx0) && (r0 <= ly0 + REGION_H - 1) && (r1 >= ly0);
                     const unsigned bal = __ballot_sync(0xffffffffu, ov);
@@ -581,8 +589,8 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
                         const int a = max(c0 - lx0, 0), b = min(c1 - lx0, REGION_W - 1);
                         const unsigned cm = ((1u << (b + 1)) - 1u) & ~((1u << a) - 1u);       // 8-bit column mask
                         const int ra = max(r0 - ly0, 0), rb = min(r1 - ly0, REGION_H - 1);
-                        unsigned mk = 0u;
-                        for (int rr = ra; rr <= rb; ++rr) mk |= cm << (8 * rr);
+                        const unsigned rows = ((1u << (rb + 1)) - 1u) & ~((1u << ra) - 1u);   // 4-bit row mask
+                        const unsigned mk = cm * ((rows * 0x00204081u) & 0x01010101u);         // one byte of cm per selected row
                         const int pos = L + __popc(bal & ltmask);
                         if (in_smem) { if (pos < SLCAP) { wsm.ent[pos] = make_uint2(e.x, e.y); wsm.mask[pos] = mk; } }
                         else { g_ent[pos] = make_uint2(e.x, e.y); g_mask[pos] = mk; }
@@ -604,12 +612,15 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
                 for (int q = 0; q < 32; ++q) {
                     // B1. candidates of pixel q
                     int np = 0;
-                    for (int base = 0; base < L; base += 32) {
-                        const int idx = base + lane;
-                        const bool pass = (idx < L) && ((emask[idx] >> q) & 1u);
-                        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                        if (pass) plist[np + __popc(bal & ltmask)] = (unsigned short)idx;
-                        np += __popc(bal);
+                    for (int base = 0; base < L; base += 64) {
+                        const int i0 = base + lane, i1 = i0 + 32;
+                        const unsigned m0 = (i0 < L) ? emask[i0] : 0u, m1 = (i1 < L) ? emask[i1] : 0u;
+                        const bool p0 = (m0 >> q) & 1u, p1 = (m1 >> q) & 1u;
+                        const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+                        const int n0 = __popc(b0);
+                        if (p0) plist[np + __popc(b0 & ltmask)] = (unsigned short)i0;
+                        if (p1) plist[np + n0 + __popc(b1 & ltmask)] = (unsigned short)i1;
+                        np += n0 + __popc(b1);
                     }
                     __syncwarp();
                     float P = 1.f;

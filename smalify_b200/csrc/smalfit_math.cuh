@@ -384,7 +384,11 @@ SMF_HD bool frag_forward(float x0, float y0, float z0, float x1, float y1, float
     const float l01 = dot2(e01x, e01y, e01x, e01y), l02 = dot2(e02x, e02y, e02x, e02y), l12 = dot2(e12x, e12y, e12x, e12y);
     const float p01 = dot2(e01x, e01y, ax, ay), p02 = dot2(e02x, e02y, ax, ay), p12 = dot2(e12x, e12y, bx, by);
 #if defined(__CUDA_ARCH__)
-    const float i01 = __fdividef(fmul(n2, n2), l01), i02 = __fdividef(fmul(n1, n1), l02), i12 = __fdividef(fmul(n0, n0), l12);
+    float r01, r02, r12;      // MUFU.RCP (1 ulp): the squared distances feed a sigmoid, 1e-7 relative is ample
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r01) : "f"(l01));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r02) : "f"(l02));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r12) : "f"(l12));
+    const float i01 = fmul(fmul(n2, n2), r01), i02 = fmul(fmul(n1, n1), r02), i12 = fmul(fmul(n0, n0), r12);
 #else
     const float i01 = n2 * n2 / l01, i02 = n1 * n1 / l02, i12 = n0 * n0 / l12;
 #endif
@@ -419,7 +423,7 @@ SMF_HD void closest_edge(const FaceSetup& f, float px, float py, Fragment& fr) {
 // 1 - sigmoid(-sd/sigma) the way the reference forms it in fp32: p = sigmoid(x), m = 1 - p.
 SMF_HD void frag_prob(float sd, float& p, float& m) {
 #if defined(__CUDA_ARCH__)
-    p = __frcp_rn(1.f + __expf(sd * (1.f / RAST_SIGMA)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(1.f + __expf(sd * (1.f / RAST_SIGMA))));
 #else
     p = 1.f / (1.f + expf(sd * (1.f / RAST_SIGMA)));
 #endif
