@@ -411,7 +411,9 @@ struct RasterWarpSmem {
     unsigned short fid[KCAP];
     uint2 ent[SLCAP];              // (fid | v0 << 16, v1 | v2 << 16)
     unsigned mask[SLCAP];
-    unsigned short plist[SLCAP];   // per-pixel candidate entries
+    unsigned short pairs[PAIRCAP]; // packed (pixel << 5 | entry) pairs of one 32-entry block; also the
+                                   // candidate list of a capped pixel (PAIRCAP >= SLCAP)
+    float acc[32];                 // running product per pixel of the region
 };
 
 struct KeyStore {           // fragment buffer: shared memory first, global spill beyond KCAP
@@ -425,6 +427,17 @@ struct KeyStore {           // fragment buffer: shared memory first, global spil
     __device__ __forceinline__ float m(int i) const { return i < KCAP ? s->mval[i] : gm[i - KCAP]; }
     __device__ __forceinline__ unsigned short f(int i) const { return i < KCAP ? s->fid[i] : gfid[i - KCAP]; }
 };
+
+// 32x32 bit-matrix transpose across the warp: lane q ends up with bit j = (lane j's v >> q) & 1.
+__device__ __forceinline__ unsigned transpose32(unsigned v, int lane) {
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) {
+        const unsigned m = (k == 16) ? 0x0000ffffu : (k == 8) ? 0x00ff00ffu : (k == 4) ? 0x0f0f0f0fu : (k == 2) ? 0x33333333u : 0x55555555u;
+        const unsigned y = __shfl_xor_sync(0xffffffffu, v, k);
+        v = (lane & k) ? ((v & ~m) | ((y >> k) & m)) : ((v & m) | ((y << k) & ~m));
+    }
+    return v;
+}
 
 // Exact K nearest by (key, face id).  Returns the product of m over the selected set and the
 // threshold (tkey, tfid): selected <=> key < tkey || (key == tkey && fid <= tfid).
@@ -603,80 +616,125 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
             __syncwarp();
             const uint2* ent = in_smem ? wsm.ent : g_ent;
             const unsigned* emask = in_smem ? wsm.mask : g_mask;
-            unsigned short* plist = in_smem ? wsm.plist : g_plist;
+            unsigned short* plist = (L <= PAIRCAP) ? wsm.pairs : g_plist;
+
+            // B. candidates per pixel (lane = pixel): transpose the entry x pixel bit matrix block by block
+            int npq = 0;
+            for (int base = 0; base < L; base += 32) {
+                const unsigned mj = (base + lane < L) ? emask[base + lane] : 0u;
+                npq += __popc(transpose32(mj, lane));
+            }
+            const bool capped_q = npq > RAST_K;
+            const bool packed_q = px_in && npq > 0 && !capped_q;
 
             float myP = 1.f;
             unsigned myTkey = 0xffffffffu, myTfid = 0xffffu;
-            int myN = 0;
-            if (L > 0) {
-                for (int q = 0; q < 32; ++q) {
-                    // B1. candidates of pixel q
-                    int np = 0;
-                    for (int base = 0; base < L; base += 64) {
-                        const int i0 = base + lane, i1 = i0 + 32;
-                        const unsigned m0 = (i0 < L) ? emask[i0] : 0u, m1 = (i1 < L) ? emask[i1] : 0u;
-                        const bool p0 = (m0 >> q) & 1u, p1 = (m1 >> q) & 1u;
-                        const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
-                        const int n0 = __popc(b0);
-                        if (p0) plist[np + __popc(b0 & ltmask)] = (unsigned short)i0;
-                        if (p1) plist[np + n0 + __popc(b1 & ltmask)] = (unsigned short)i1;
-                        np += n0 + __popc(b1);
-                    }
+
+            // C. pixels with at most K candidates select every fragment: their (pixel, entry) pairs are
+            //    packed 32 per batch across pixel boundaries, one pair per lane; the per-pixel products
+            //    come out of a segmented scan (pairs are sorted by pixel)
+            if (__any_sync(0xffffffffu, packed_q)) {
+                wsm.acc[lane] = 1.f;
+                __syncwarp();
+                for (int base = 0; base < L; base += 32) {
+                    const unsigned mj = (base + lane < L) ? emask[base + lane] : 0u;
+                    unsigned tq = transpose32(mj, lane);
+                    if (!packed_q) tq = 0u;
+                    const int c = __popc(tq);
+                    int incl = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total == 0) continue;
+                    int o = incl - c;
+                    while (tq) { const int j = __ffs(tq) - 1; tq &= tq - 1u; wsm.pairs[o++] = (unsigned short)((lane << 5) | j); }
                     __syncwarp();
-                    float P = 1.f;
-                    unsigned tk = 0xffffffffu, tf = 0xffffu;
-                    int n = 0;
-                    if (np > 0) {
-                        const float px = pix_to_ndc(x0 + (q & 7), inv_s), py = pix_to_ndc(y0 + (q >> 3), inv_s);
-                        const bool all_selected = (np <= RAST_K);
-                        float running = 1.f;
-                        for (int b0 = 0; b0 < np; b0 += 32) {
-                            const int i = b0 + lane;
-                            bool valid = false;
-                            unsigned key = 0u; float mv = 1.f; unsigned fidx = 0;
-                            if (i < np) {
-                                const uint2 e = ent[plist[i]];
-                                fidx = e.x & 0xffffu;
-                                const unsigned v0 = e.x >> 16, v1 = e.y & 0xffffu, v2 = e.y >> 16;
-                                float sd, pz;
-                                valid = frag_forward(vx[v0], vy[v0], vz[v0], vx[v1], vy[v1], vz[v1], vx[v2], vy[v2], vz[v2],
-                                                     px, py, !all_selected, sd, pz);
-                                if (valid) {
-                                    float pp;
-                                    frag_prob(sd, pp, mv);
-                                    key = __float_as_uint(pz + 0.f);
-                                }
-                            }
-                            const unsigned bal = __ballot_sync(0xffffffffu, valid);
-                            if (all_selected) {
-                                running *= warp_prod(mv);           // mv == 1 for lanes without a fragment
-                                n += __popc(bal);
-                                if (running < P_SKIP) { running = 0.f; break; }     // alpha == 1.0f exactly
-                            } else {
-                                if (valid) ks.put(n + __popc(bal & ltmask), key, mv, (unsigned short)fidx);
-                                n += __popc(bal);
+                    for (int b0 = 0; b0 < total; b0 += 32) {
+                        const int i = b0 + lane;
+                        unsigned q = 255u;
+                        float mv = 1.f;
+                        if (i < total) {
+                            const unsigned pr = wsm.pairs[i];
+                            q = pr >> 5;
+                            const uint2 e = ent[base + (int)(pr & 31u)];
+                            const unsigned v0 = e.x >> 16, v1 = e.y & 0xffffu, v2 = e.y >> 16;
+                            float sd, pz;
+                            if (frag_forward(vx[v0], vy[v0], vz[v0], vx[v1], vy[v1], vz[v1], vx[v2], vy[v2], vz[v2],
+                                             pix_to_ndc(x0 + (int)(q & 7u), inv_s), pix_to_ndc(y0 + (int)(q >> 3), inv_s), false, sd, pz)) {
+                                float pp;
+                                frag_prob(sd, pp, mv);
                             }
                         }
-                        if (all_selected) {
-                            P = running;
-                        } else {
-                            __syncwarp();
-                            if (n > RAST_K) {
-                                P = select_k_nearest(ks, n, lane, tk, tf);
-                                if (lane == 0) { ++n_capped; if (n > KCAP) ++n_spilled; }
-                            } else if (n > 0) {
-                                float pr = 1.f;
-                                for (int i = lane; i < n; i += 32) pr *= ks.m(i);
-                                P = warp_prod(pr);
-                            }
+                        float val = mv;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const float y = __shfl_up_sync(0xffffffffu, val, d);
+                            const unsigned qy = __shfl_up_sync(0xffffffffu, q, d);
+                            if (lane >= d && qy == q) val *= y;
                         }
+                        const unsigned qn = __shfl_down_sync(0xffffffffu, q, 1);
+                        if (i < total && (lane == 31 || qn != q)) wsm.acc[q] *= val;      // one tail lane per pixel
+                        __syncwarp();
                     }
-                    if (lane == q) { myP = P; myTkey = tk; myTfid = tf; myN = n; }
-                    __syncwarp();
                 }
+                if (packed_q) myP = wsm.acc[lane];
             }
 
-            // D. epilogue: lane = pixel
+            // D. pixels with more than K candidates: one at a time, fragments buffered, exact K-nearest rule
+            unsigned cmask = __ballot_sync(0xffffffffu, px_in && capped_q);
+            while (cmask) {
+                const int q = __ffs(cmask) - 1;
+                cmask &= cmask - 1u;
+                int np = 0;
+                for (int base = 0; base < L; base += 64) {
+                    const int i0 = base + lane, i1 = i0 + 32;
+                    const unsigned m0 = (i0 < L) ? emask[i0] : 0u, m1 = (i1 < L) ? emask[i1] : 0u;
+                    const bool p0 = (m0 >> q) & 1u, p1 = (m1 >> q) & 1u;
+                    const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+                    const int n0 = __popc(b0);
+                    if (p0) plist[np + __popc(b0 & ltmask)] = (unsigned short)i0;
+                    if (p1) plist[np + n0 + __popc(b1 & ltmask)] = (unsigned short)i1;
+                    np += n0 + __popc(b1);
+                }
+                __syncwarp();
+                const float px = pix_to_ndc(x0 + (q & 7), inv_s), py = pix_to_ndc(y0 + (q >> 3), inv_s);
+                int n = 0;
+                for (int b0 = 0; b0 < np; b0 += 32) {
+                    const int i = b0 + lane;
+                    bool valid = false;
+                    unsigned key = 0u; float mv = 1.f; unsigned fidx = 0;
+                    if (i < np) {
+                        const uint2 e = ent[plist[i]];
+                        fidx = e.x & 0xffffu;
+                        const unsigned v0 = e.x >> 16, v1 = e.y & 0xffffu, v2 = e.y >> 16;
+                        float sd, pz;
+                        valid = frag_forward(vx[v0], vy[v0], vz[v0], vx[v1], vy[v1], vz[v1], vx[v2], vy[v2], vz[v2], px, py, true, sd, pz);
+                        if (valid) {
+                            float pp;
+                            frag_prob(sd, pp, mv);
+                            key = __float_as_uint(pz + 0.f);
+                        }
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, valid);
+                    if (valid) ks.put(n + __popc(bal & ltmask), key, mv, (unsigned short)fidx);
+                    n += __popc(bal);
+                }
+                __syncwarp();
+                float P = 1.f;
+                unsigned tk = 0xffffffffu, tf = 0xffffu;
+                if (n > RAST_K) {
+                    P = select_k_nearest(ks, n, lane, tk, tf);
+                    if (lane == 0) { ++n_capped; if (n > KCAP) ++n_spilled; }
+                } else if (n > 0) {
+                    float pr = 1.f;
+                    for (int i = lane; i < n; i += 32) pr *= ks.m(i);
+                    P = warp_prod(pr);
+                }
+                if (lane == q) { myP = P; myTkey = tk; myTfid = tf; }
+                __syncwarp();
+            }
+
+            // E. epilogue: lane = pixel
             float l1 = 0.f;
             if (px_in) {
                 const size_t pi = ((size_t)fr * S + px_y) * S + px_x;
@@ -685,7 +743,7 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
                 const float d = alpha - Tm;
                 l1 = fabsf(d);
                 float coef = 0.f;
-                if (myN > 0 && myP >= P_SKIP && d != 0.f) {
+                if (myP < 1.f && myP >= P_SKIP && d != 0.f) {       // myP < 1 <=> the pixel has fragments
                     const float ga = wt.sil * w.inv_window[fr] * inv_s * inv_s * (d > 0.f ? 1.f : -1.f);
                     coef = ga * myP * (1.f / RAST_SIGMA);
                 }
@@ -756,8 +814,9 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(ModelDev m, Worksp
             const uint2 pr = pix[(size_t)y * S + x];
             const float coef = __uint_as_float(pr.x);
             if (coef == 0.f) continue;
-            // same edge functions / depth as the forward pass (bit-identical keys); the clamped-t
-            // distances differ from the forward's only in the last bits
+            // same edge functions / depth as the forward pass (bit-identical keys); the clamped-t distances
+            // differ from the forward's cross^2/|e|^2 form only in the last bits (measured: frag_backward,
+            // which shares the forward's form, is 15 % slower here)
             Fragment frag;
             if (!face_eval(fs, pix_to_ndc(x, inv_s), pix_to_ndc(y, inv_s), frag)) continue;
             if (pr.y != 0xffffffffu) {

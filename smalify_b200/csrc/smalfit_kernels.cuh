@@ -17,6 +17,7 @@ constexpr int TILE_W = 32, TILE_H = 32;     // CTA work item: 32 regions, pulled
 constexpr int REGIONS_PER_TILE = (TILE_W / REGION_W) * (TILE_H / REGION_H);
 constexpr int KCAP = 256;                   // fragment selection buffer per warp (shared memory part)
 constexpr int SLCAP = 448;                  // region sub-list entries kept in shared memory
+constexpr int PAIRCAP = 1024;               // (pixel, entry) pairs of one 32-entry block (32 x 32)
 constexpr int MAX_TILES = 1024;             // 32x32 tiles per frame (image side <= 1024)
 constexpr int MAX_LEVELS = 16;
 constexpr float P_SKIP = 2.98023224e-8f;    // 2^-25: below this 1-P rounds to 1.0f in fp32

@@ -401,6 +401,47 @@ SMF_HD bool frag_forward(float x0, float y0, float z0, float x1, float y1, float
     return true;
 }
 
+// Backward-side fragment test: the same acceptance arithmetic as frag_forward (edge functions, depth,
+// |a|^2 / cross^2/|e|^2 distances -- here with the set-up's exact 1/|e|^2), plus, for the closest edge only
+// (ties 01 -> 02 -> 12, PointTriangleDistanceBackward), the clamped parameter and (p_proj - p).
+SMF_HD bool frag_backward(const FaceSetup& f, float px, float py, bool want_pz, Fragment& fr) {
+    if (f.valid == 0.f) return false;
+    const float ax = fsub(px, f.x0), ay = fsub(py, f.y0);
+    const float bx = fsub(px, f.x1), by = fsub(py, f.y1);
+    const float cx = fsub(px, f.x2), cy = fsub(py, f.y2);
+    const float n0 = cross2(bx, by, f.e12x, f.e12y);
+    const float n1 = cross2(f.e02x, f.e02y, cx, cy);
+    const float n2 = cross2(ax, ay, f.e01x, f.e01y);
+    fr.pz = 0.f;
+    if (want_pz) {
+        const float w0 = fmul(n0, f.rden), w1 = fmul(n1, f.rden), w2 = fmul(n2, f.rden);
+        fr.pz = ffma(w2, f.z2, ffma(w1, f.z1, fmul(w0, f.z0)));
+        if (fr.pz < 0.f) return false;
+    } else {
+        const float sn = ffma(n2, f.z2, ffma(n1, f.z1, fmul(n0, f.z0)));
+        if ((sn < 0.f && f.rden > 0.f) || (sn > 0.f && f.rden < 0.f)) return false;
+    }
+    const bool inside = (f.rden > 0.f) ? (n0 > 0.f && n1 > 0.f && n2 > 0.f) : (n0 < 0.f && n1 < 0.f && n2 < 0.f);
+    const float da = dot2(ax, ay, ax, ay), db = dot2(bx, by, bx, by), dc = dot2(cx, cy, cx, cy);
+    const float p01 = dot2(f.e01x, f.e01y, ax, ay), p02 = dot2(f.e02x, f.e02y, ax, ay), p12 = dot2(f.e12x, f.e12y, bx, by);
+    // rl == 0 marks a degenerate edge (distance to its end point); p * rl >= 1 <=> projection beyond the end
+    const float t01 = fmul(p01, f.rl01), t02 = fmul(p02, f.rl02), t12 = fmul(p12, f.rl12);
+    const float d01 = (f.rl01 == 0.f || t01 >= 1.f) ? db : (p01 <= 0.f ? da : fmul(fmul(n2, n2), f.rl01));
+    const float d02 = (f.rl02 == 0.f || t02 >= 1.f) ? dc : (p02 <= 0.f ? da : fmul(fmul(n1, n1), f.rl02));
+    const float d12 = (f.rl12 == 0.f || t12 >= 1.f) ? dc : (p12 <= 0.f ? db : fmul(fmul(n0, n0), f.rl12));
+    float d, t, ex, ey, sx, sy;
+    if (d01 <= d02 && d01 <= d12) { fr.edge = 0; d = d01; t = t01; ex = f.e01x; ey = f.e01y; sx = ax; sy = ay; if (f.rl01 == 0.f) t = 1.f; }
+    else if (d02 <= d01 && d02 <= d12) { fr.edge = 1; d = d02; t = t02; ex = f.e02x; ey = f.e02y; sx = ax; sy = ay; if (f.rl02 == 0.f) t = 1.f; }
+    else { fr.edge = 2; d = d12; t = t12; ex = f.e12x; ey = f.e12y; sx = bx; sy = by; if (f.rl12 == 0.f) t = 1.f; }
+    if (!inside && d >= RAST_BLUR) return false;
+    t = fsat(t);
+    fr.t = t;
+    fr.qx = ffma(t, ex, -sx);
+    fr.qy = ffma(t, ey, -sy);
+    fr.sd = inside ? -d : d;
+    return true;
+}
+
 // Closest edge of an accepted fragment with its clamped parameter and (p_proj - p), the
 // quantities PointTriangleDistanceBackward differentiates (ties 01 -> 02 -> 12).
 SMF_HD void closest_edge(const FaceSetup& f, float px, float py, Fragment& fr) {

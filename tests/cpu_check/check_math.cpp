@@ -59,6 +59,15 @@ int chk_frag_forward(const float* tri, float px, float py, int want_pz, float* o
     return ok ? 1 : 0;
 }
 
+// backward variant: out = (pz, sd, t, qx, qy), returns edge + 1 (0 = no fragment)
+int chk_frag_backward(const float* tri, float px, float py, int want_pz, float* out) {
+    const FaceSetup fs = face_setup(tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8]);
+    Fragment fr;
+    if (!frag_backward(fs, px, py, want_pz != 0, fr)) return 0;
+    out[0] = fr.pz; out[1] = fr.sd; out[2] = fr.t; out[3] = fr.qx; out[4] = fr.qy;
+    return fr.edge + 1;
+}
+
 int chk_face_rect(const float* tri, int S, int* rect) {
     const FaceSetup fs = face_setup(tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8]);
     return face_pixel_rect(fs, S, rect[0], rect[1], rect[2], rect[3]) ? 1 : 0;
