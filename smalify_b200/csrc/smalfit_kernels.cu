@@ -441,29 +441,63 @@ __device__ __forceinline__ unsigned transpose32(unsigned v, int lane) {
 
 // Exact K nearest by (key, face id).  Returns the product of m over the selected set and the
 // threshold (tkey, tfid): selected <=> key < tkey || (key == tkey && fid <= tfid).
-__device__ float select_k_nearest(const KeyStore& ks, int n, int lane, unsigned& tkey, unsigned& tfid) {
+// Bisection on the key bits for the K-th order statistic, stopping early when a split of exactly K
+// appears.  Pixels whose fragments spilled past KCAP first bisect on the whole set (shared + global)
+// only until at most KCAP keys remain in the bracket, compact those into `scratch` and finish like
+// everyone else on keys cached in registers.
+__device__ float select_k_nearest(const KeyStore& ks, int n, int lane, unsigned* scratch /* >= KCAP words */,
+                                  unsigned& tkey, unsigned& tfid) {
     constexpr int NR = KCAP / 32;
-    unsigned kr[NR];                       // keys of the shared-memory part, cached in registers
-#pragma unroll
-    for (int r = 0; r < NR; ++r) { const int i = r * 32 + lane; kr[r] = (i < n) ? ks.s->key[i] : 0xffffffffu; }
+    const unsigned ltmask = lanemask_lt();
     unsigned lo = 0xffffffffu, hi = 0u;
-#pragma unroll
-    for (int r = 0; r < NR; ++r) { lo = min(lo, kr[r]); if (r * 32 + lane < n) hi = max(hi, kr[r]); }
-    for (int i = KCAP + lane; i < n; i += 32) { const unsigned k = ks.gkey[i - KCAP]; lo = min(lo, k); hi = max(hi, k); }
+    for (int i = lane; i < n; i += 32) { const unsigned k = ks.key(i); lo = min(lo, k); hi = max(hi, k); }
     lo = __reduce_min_sync(0xffffffffu, lo);
     hi = __reduce_max_sync(0xffffffffu, hi);
-    // smallest t with count(key <= t) >= K; stop early when a split of exactly K is found
     bool exact = false;
     unsigned t = hi;
-    while (lo < hi) {
-        const unsigned mid = lo + ((hi - lo) >> 1);
-        int c = 0;
+    int below = 0;                       // keys < lo
+    int want = RAST_K;                   // rank looked for among the keys of the register phase
+    const unsigned* src = ks.s->key;
+    int m = n;
+    if (n > KCAP) {
+        int c_hi = n;                    // keys <= hi
+        while (c_hi - below > KCAP && lo < hi) {
+            const unsigned mid = lo + ((hi - lo) >> 1);
+            int c = 0;
+            for (int i = lane; i < n; i += 32) c += (ks.key(i) <= mid) ? 1 : 0;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c == RAST_K) { t = mid; exact = true; break; }
+            if (c > RAST_K) { hi = mid; c_hi = c; } else { lo = mid + 1; below = c; }
+        }
+        m = 0;
+        if (!exact && lo < hi) {
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                unsigned k = 0u;
+                bool in = false;
+                if (i < n) { k = ks.key(i); in = (k >= lo && k <= hi); }
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (in) scratch[m + __popc(bal & ltmask)] = k;
+                m += __popc(bal);
+            }
+            __syncwarp();
+            src = scratch;
+            want = RAST_K - below;
+        }
+    }
+    if (!exact && lo < hi) {
+        unsigned kr[NR];                 // keys of the register phase; padding 0xffffffff is never <= mid
 #pragma unroll
-        for (int r = 0; r < NR; ++r) c += (kr[r] <= mid) ? 1 : 0;       // padding keys are 0xffffffff > mid
-        for (int i = KCAP + lane; i < n; i += 32) c += (ks.gkey[i - KCAP] <= mid) ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c == RAST_K) { t = mid; exact = true; break; }
-        if (c > RAST_K) hi = mid; else lo = mid + 1;
+        for (int r = 0; r < NR; ++r) { const int i = r * 32 + lane; kr[r] = (i < m) ? src[i] : 0xffffffffu; }
+        while (lo < hi) {
+            const unsigned mid = lo + ((hi - lo) >> 1);
+            int c = 0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) c += (kr[r] <= mid) ? 1 : 0;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c == want) { t = mid; exact = true; break; }
+            if (c > want) hi = mid; else lo = mid + 1;
+        }
     }
     unsigned tf = 0xffffu;
     if (!exact) {
@@ -723,7 +757,7 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
                 float P = 1.f;
                 unsigned tk = 0xffffffffu, tf = 0xffffu;
                 if (n > RAST_K) {
-                    P = select_k_nearest(ks, n, lane, tk, tf);
+                    P = select_k_nearest(ks, n, lane, reinterpret_cast<unsigned*>(wsm.pairs), tk, tf);
                     if (lane == 0) { ++n_capped; if (n > KCAP) ++n_spilled; }
                 } else if (n > 0) {
                     float pr = 1.f;
