@@ -93,9 +93,15 @@ def num_threads() -> int:
 
 
 def use_all_cores() -> int:
-    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core."""
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every core this process may
+    run on (the scheduler affinity mask, not os.cpu_count(): oversubscribing OpenMP is far slower)."""
     import os
-    n = os.cpu_count() or 1
-    lib().raster_set_threads(n)
-    torch.set_num_threads(n)
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    if num_threads() < n:
+        lib().raster_set_threads(n)
+    if torch.get_num_threads() < n:
+        torch.set_num_threads(n)
     return num_threads()
