@@ -153,6 +153,65 @@ def test_per_frame_shapes_equal_independent_fits(constants, oracle64, seq):
         assert H.rel_err(getattr(f, k).grad, ref) < 1e-4, k
 
 
+@pytest.mark.parametrize("S", [40, 96])
+def test_edge_cases_clipping_behind_camera_empty_targets(constants, oracle64, S):
+    """Image side not a multiple of the 32-pixel tile; one animal half outside the image, one so close
+    that part of the mesh is behind the camera plane (z < 0 faces / fragments are dropped), an empty
+    target mask and a frame without visible keypoints."""
+    from smalify_b200.smal_fitter import SMALFitter
+    N = 3
+    m = oracle64
+    gt = synthetic.ground_truth_params(constants, N, seed=4)
+    gt["trans"] = torch.tensor([[0.95, 0.3, 0.4], [0.0, 0.1, 2.45], [-0.2, -1.1, 0.9]])
+    data, _ = synthetic.make_sequence(constants, N, S, H.oracle_renderer(m, S), seed=4)
+    rgb, sil, joints, vis = data
+    sil = sil.clone()
+    sil[2] = 0.0                      # empty target
+    vis = vis.clone()
+    vis[1] = 0.0                      # nothing visible
+    data = (rgb, sil, joints, vis)
+    p = O.FitParams(global_rotation=gt["global_rotation"].double(), joint_rotations=gt["joint_rotations"].double(),
+                    betas=gt["betas"].double(), log_beta_scales=gt["log_beta_scales"].double(), trans=gt["trans"].double())
+    w = K.STAGE_SCHEDULE[2][:6]
+    lo, objs_o, go = H.oracle_loss_and_grads(m, p, data, range(N), w, S)
+    f = SMALFitter("cuda", data, N, 1, True, constants=constants)
+    H.load_params_into(f, p)
+    loss, objs = f(list(range(N)), w, 2)
+    loss.backward()
+    assert torch.isfinite(loss)
+    assert abs(float(loss) - lo) <= 3e-5 * abs(lo), (float(loss), lo)
+    for k in ("global_rotation", "trans", "joint_rotations", "betas", "log_beta_scales"):
+        g = getattr(f, k).grad
+        assert torch.isfinite(g).all()
+        assert H.rel_err(g, go[k]) < 1e-4, (k, H.rel_err(g, go[k]))
+    alpha, _ = f.render()
+    theta = torch.cat([p.global_rotation[:, None], p.joint_rotations], 1)
+    vo, _, _ = O.smal_forward(m, p.betas.expand(N, 20), theta, p.log_beta_scales.expand(N, 6))
+    ao = O.render_silhouettes(m, vo + p.trans[:, None], S)
+    err = (alpha.cpu().double() - ao).abs()
+    assert float((err > 5e-5).double().mean()) < 5e-3, float(err.max())
+    assert f.counters()["dropped_bin_entries"] == 0
+
+
+def test_c_abi_rejects_bad_arguments(fitter):
+    """Error behaviour of the boundary: negative return codes + message, never a crash."""
+    import ctypes
+    from smalify_b200 import _cabi
+    from smalify_b200.smal_fitter import _tensors, _ptr, _stream, _weights6
+    h = fitter._handle
+    params = _tensors(fitter.betas, fitter.log_beta_scales, fitter.global_rotation, fitter.joint_rotations, fitter.trans)
+    terms = torch.zeros(8, device=fitter.device)
+    rc = h.lib.smalfit_loss_grad(h.h, ctypes.byref(params), 0, N_SMALL + 1, _weights6(STAGE1), 1, None, _ptr(terms), _stream(fitter.device))
+    assert rc == -1 and b"bad arguments" in h.lib.smalfit_last_error(h.h)
+    bad = _tensors(None, fitter.log_beta_scales, fitter.global_rotation, fitter.joint_rotations, fitter.trans)
+    rc = h.lib.smalfit_loss_grad(h.h, ctypes.byref(bad), 0, 1, _weights6(STAGE1), 1, None, _ptr(terms), _stream(fitter.device))
+    assert rc == -1 and b"NULL" in h.lib.smalfit_last_error(h.h)
+    with pytest.raises(ValueError):
+        fitter([0, 2], STAGE1, 1)          # non-contiguous window
+    with pytest.raises(_cabi.SmalfitError):
+        _cabi.Handle(fitter.constants, fitter.device.index, 4, 2048)      # image side above the supported 1024
+
+
 def test_missing_library_fails_loudly(tmp_path):
     from smalify_b200 import _cabi
     with pytest.raises(_cabi.SmalfitError):
