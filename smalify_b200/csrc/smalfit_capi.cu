@@ -219,8 +219,10 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     w.tile_pool = P.alloc<uint4>(N * (size_t)w.pool_cap);
     w.tile_off = P.alloc<unsigned>(N * (tiles + 1), true);
     w.tile_order = P.alloc<unsigned short>(N * tiles, true);
-    w.frame_next = P.alloc<unsigned>(N + 1, true);
+    w.frame_next = P.alloc<unsigned>(2 * N + 1, true);
     w.frames_done = w.frame_next + N;
+    w.frame_active = w.frame_next + N + 1;
+    w.frame_busy = P.alloc<unsigned>(N, true);
     w.pix = P.alloc<uint2>(N * SS, true);
     w.pix_tfid = P.alloc<uint16_t>(N * SS, true);
     w.region_l1 = P.alloc<float>(N * tiles * REGIONS_PER_TILE, true);

@@ -305,6 +305,11 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
             if (t == T - 1) toff[T] = run;
         }
     }
+    if (tid == 0) {
+        unsigned busy = 0;
+        for (int t = 0; t < T; ++t) busy += (tot[t] > 0u) ? 1u : 0u;
+        w.frame_busy[fr] = busy * REGIONS_PER_TILE;
+    }
     // hand-out order of the tiles: longest list first, so a frame's last regions are the cheap ones
     unsigned short* order = w.tile_order + (size_t)fr * T;
     for (int t = tid; t < T; t += BIN_THREADS) {
@@ -560,26 +565,58 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
     const int R = T * REGIONS_PER_TILE;
     const unsigned ltmask = lanemask_lt();
     unsigned long long n_capped = 0, n_spilled = 0;
-    int cur = (int)(((long long)blockIdx.x * n_frames) / gridDim.x);
+    int cur = (int)(((long long)blockIdx.x * n_frames) / gridDim.x);      // first visit: CTAs spread over the frames
+    __shared__ int s_cur;
 
-    for (int visited = 0; visited < n_frames; ++visited, cur = (cur + 1 == n_frames) ? 0 : cur + 1) {
-        const int fr = frame0 + cur;
+    for (int visit = 0;; ++visit) {
         __syncthreads();           // every warp is past the previous frame's vertices
-        if (tid == 0) {
+        if (wid == 0) {
+            // Pick the frame to work on: after the first visit, the one with the most non-trivial regions
+            // left per CTA already on it (frame_busy = regions of tiles that hold faces; the regions after
+            // them in hand-out order are empty).  Falls back to any frame with regions left.
             int st = 0;
-            if (*(volatile unsigned*)(w.frames_done) >= (unsigned)n_frames) st = 2;
-            else if (*(volatile unsigned*)(w.frame_next + fr) >= (unsigned)R) st = 1;
-            s_state = st;
-            if (st == 0) {
-                const unsigned bytes = (unsigned)(m.Vp * sizeof(float));
-                const float* src = ndc_soa + (size_t)fr * 3 * m.Vp;
-                mbar_expect_tx(&bar, 3 * bytes);
-                tma_load_1d(vx, src, bytes, &bar);
-                tma_load_1d(vy, src + m.Vp, bytes, &bar);
-                tma_load_1d(vz, src + 2 * m.Vp, bytes, &bar);
+            if (visit > 0) {
+                if (lane == 0 && cur >= 0) atomicSub(w.frame_active + frame0 + cur, 1u);
+                float best = -1.f;
+                int best_f = -1;
+                for (int f = lane; f < n_frames; f += 32) {
+                    const unsigned nx = *(volatile unsigned*)(w.frame_next + frame0 + f);
+                    if (nx >= (unsigned)R) continue;
+                    const unsigned busy = w.frame_busy[frame0 + f];
+                    const unsigned act = *(volatile unsigned*)(w.frame_active + frame0 + f);
+                    // per-CTA jitter (0.75 .. 1.25) keeps CTAs that finish together from herding onto one frame
+                    const float jit = 0.75f + (float)(((blockIdx.x * 2654435761u + (unsigned)f * 40503u) >> 20) & 0xffu) * (0.5f / 255.f);
+                    const float score = jit * (busy > nx ? (float)(busy - nx) : 0.f) / (float)(1u + act) + 1e-3f;
+                    if (score > best) { best = score; best_f = f; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int of = __shfl_xor_sync(0xffffffffu, best_f, o);
+                    if (ob > best || (ob == best && of >= 0 && (best_f < 0 || of < best_f))) { best = ob; best_f = of; }
+                }
+                cur = best_f;
+                if (best_f < 0) st = (*(volatile unsigned*)(w.frames_done) >= (unsigned)n_frames) ? 2 : 1;
+            }
+            if (lane == 0) {
+                if (st == 0) {
+                    atomicAdd(w.frame_active + frame0 + cur, 1u);
+                    const unsigned bytes = (unsigned)(m.Vp * sizeof(float));
+                    const float* src = ndc_soa + (size_t)(frame0 + cur) * 3 * m.Vp;
+                    mbar_expect_tx(&bar, 3 * bytes);
+                    tma_load_1d(vx, src, bytes, &bar);
+                    tma_load_1d(vy, src + m.Vp, bytes, &bar);
+                    tma_load_1d(vz, src + 2 * m.Vp, bytes, &bar);
+                } else if (st == 1) {
+                    __nanosleep(500);      // the last regions are being drawn elsewhere; look again
+                }
+                s_state = st;
+                s_cur = cur;
             }
         }
         __syncthreads();
+        cur = s_cur;
+        const int fr = frame0 + cur;
         const int st = s_state;
         if (st == 2) break;
         if (st == 1) continue;
@@ -816,7 +853,7 @@ void launch_ndc_soa(const ModelDev& m, const Workspace& w, float* ndc_soa, int f
 
 void launch_raster_forward(const ModelDev& m, const Workspace& w, const RasterScratch& sc, float* ndc_soa,
                            int frame0, int n, Weights wt, float* alpha_out, int n_ctas, cudaStream_t st) {
-    cudaMemsetAsync(w.frame_next, 0, sizeof(unsigned) * (size_t)(w.N + 1), st);      // + frames_done
+    cudaMemsetAsync(w.frame_next, 0, sizeof(unsigned) * (size_t)(2 * w.N + 1), st);  // + frames_done + frame_active
     raster_forward_kernel<<<n_ctas, RAST_THREADS, raster_smem_bytes(m), st>>>(m, w, sc, frame0, n, wt, ndc_soa, alpha_out);
 }
 

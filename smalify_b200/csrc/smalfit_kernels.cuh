@@ -73,6 +73,8 @@ struct Workspace {
     int pool_cap;
     unsigned* frame_next;       // [N] next region to hand out   (followed by frames_done)
     unsigned* frames_done;      // [1] frames whose counter ran past the end
+    unsigned* frame_active;     // [N] CTAs currently working on the frame
+    unsigned* frame_busy;       // [N] regions of tiles that hold faces (they come first in hand-out order)
     uint2* pix;                 // [N][S*S] (float coef, u32 tkey)
     uint16_t* pix_tfid;         // [N][S*S] tie face id (capped pixels only)
     float* region_l1;           // [N][tiles*32] per-region sum |alpha - T|
