@@ -125,7 +125,7 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
 
     smalfit_ctx* h = new smalfit_ctx();
     h->device = device; h->N = max_frames; h->S = image_size; h->n_sm = prop.multiProcessorCount;
-    h->raster_ctas = h->n_sm;
+    h->raster_ctas = RAST_CTAS_PER_SM * h->n_sm;
     const int V = md->n_verts, F = md->n_faces;
     ModelDev& m = h->m;
     m.V = V; m.F = F; m.Fp = (F + 31) / 32 * 32; m.Vp = (V + 3) / 4 * 4;

@@ -418,7 +418,6 @@ struct RasterWarpSmem {
     unsigned mask[SLCAP];
     unsigned short pairs[PAIRCAP]; // packed (pixel << 5 | entry) pairs of one 32-entry block; also the
                                    // candidate list of a capped pixel (PAIRCAP >= SLCAP)
-    float acc[32];                 // running product per pixel of the region
 };
 
 struct KeyStore {           // fragment buffer: shared memory first, global spill beyond KCAP
@@ -534,7 +533,7 @@ __device__ float select_k_nearest(const KeyStore& ks, int n, int lane, unsigned*
     return warp_prod(prod);
 }
 
-__global__ void __launch_bounds__(RAST_THREADS, 1)
+__global__ void __launch_bounds__(RAST_THREADS, RAST_CTAS_PER_SM)
 raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int n_frames, Weights wt,
                       const float* ndc_soa /* [N][3][Vp] */, float* alpha_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -705,7 +704,8 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
             //    packed 32 per batch across pixel boundaries, one pair per lane; the per-pixel products
             //    come out of a segmented scan (pairs are sorted by pixel)
             if (__any_sync(0xffffffffu, packed_q)) {
-                wsm.acc[lane] = 1.f;
+                float* acc = wsm.mval;             // running product per pixel (the key buffer is idle in this phase)
+                acc[lane] = 1.f;
                 __syncwarp();
                 for (int base = 0; base < L; base += 32) {
                     const unsigned mj = (base + lane < L) ? emask[base + lane] : 0u;
@@ -744,11 +744,11 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
                             if (lane >= d && qy == q) val *= y;
                         }
                         const unsigned qn = __shfl_down_sync(0xffffffffu, q, 1);
-                        if (i < total && (lane == 31 || qn != q)) wsm.acc[q] *= val;      // one tail lane per pixel
+                        if (i < total && (lane == 31 || qn != q)) acc[q] *= val;          // one tail lane per pixel
                         __syncwarp();
                     }
                 }
-                if (packed_q) myP = wsm.acc[lane];
+                if (packed_q) myP = acc[lane];
             }
 
             // D. pixels with more than K candidates: one at a time, fragments buffered, exact K-nearest rule
