@@ -223,9 +223,11 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     w.frames_done = w.frame_next + N;
     w.frame_active = w.frame_next + N + 1;
     w.frame_busy = P.alloc<unsigned>(N, true);
+    w.frame_heavy = P.alloc<unsigned>(N, true);
+    w.frame_items = P.alloc<unsigned>(N, true);
     w.pix = P.alloc<uint2>(N * SS, true);
     w.pix_tfid = P.alloc<uint16_t>(N * SS, true);
-    w.region_l1 = P.alloc<float>(N * tiles * REGIONS_PER_TILE, true);
+    w.region_l1 = P.alloc<float>(N * tiles * REGIONS_PER_TILE * REGION_H, true);
     w.face_grad = P.alloc<float>(N * m.Fp * 8, true);
     w.dvs = P.alloc<float>(N * V * 3, true);
     w.gJ = P.alloc<float>(N * NJ * 3, true);
@@ -235,7 +237,7 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     h->sil = P.alloc<uint8_t>(N * SS, true);
     h->kp_target = P.alloc<float>(N * NKP * 2, true);
     h->vis = P.alloc<uint8_t>(N * NKP, true);
-    h->region_tsum = P.alloc<float>(N * tiles * REGIONS_PER_TILE, true);
+    h->region_tsum = P.alloc<float>(N * tiles * REGIONS_PER_TILE * REGION_H, true);
     std::vector<float> ones(N > 102 ? N : 102, 1.0f);
     std::vector<float> invw(N, 1.0f / (float)N);
     h->inv_window = P.upload(invw.data(), N);
@@ -340,7 +342,7 @@ static int run_forward(smalfit_t h, const Params& p, int frame0, int n, Weights 
     h->n_launches += 2;
     h->mark(1, st);
     if (raster) {
-        launch_bin_faces(h->m, h->w, frame0, n, st);
+        launch_bin_faces(h->m, h->w, frame0, n, h->n_sm, st);
         launch_ndc_soa(h->m, h->w, h->ndc_soa, frame0, n, st);
         h->mark(2, st);
         launch_raster_forward(h->m, h->w, h->sc, h->ndc_soa, frame0, n, wt, alpha_out, h->raster_ctas, st);

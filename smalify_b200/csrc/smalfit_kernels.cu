@@ -306,9 +306,13 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
         }
     }
     if (tid == 0) {
-        unsigned busy = 0;
-        for (int t = 0; t < T; ++t) busy += (tot[t] > 0u) ? 1u : 0u;
-        w.frame_busy[fr] = busy * REGIONS_PER_TILE;
+        // tiles with long lists are handed out as single pixel rows (4 items per region), the rest as
+        // whole 8x4 regions: bounds the longest single-warp task
+        unsigned busy = 0, heavy = 0;
+        for (int t = 0; t < T; ++t) { busy += (tot[t] > 0u) ? 1u : 0u; heavy += (tot[t] >= (unsigned)w.heavy_len) ? 1u : 0u; }
+        w.frame_heavy[fr] = heavy;
+        w.frame_items[fr] = heavy * (REGIONS_PER_TILE * REGION_H) + ((unsigned)T - heavy) * REGIONS_PER_TILE;
+        w.frame_busy[fr] = heavy * (REGIONS_PER_TILE * REGION_H) + (busy - heavy) * REGIONS_PER_TILE;
     }
     // hand-out order of the tiles: longest list first, so a frame's last regions are the cheap ones
     unsigned short* order = w.tile_order + (size_t)fr * T;
@@ -362,7 +366,11 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
 
 size_t bin_smem_bytes(const Workspace& w) { return (size_t)(BIN_WARPS + 1) * w.tiles_x * w.tiles_y * sizeof(unsigned); }
 
-void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st) {
+void launch_bin_faces(const ModelDev& m, const Workspace& w_in, int frame0, int n, int n_sm, cudaStream_t st) {
+    // Row-granular items cost ~10 % extra work on the tiles they apply to; they pay off only when there are
+    // too few frames per GPU for the longest single-warp task to hide behind other work (sharded runs).
+    Workspace w = w_in;
+    w.heavy_len = (n * 3 <= n_sm) ? HEAVY_TILE_LEN : (1 << 30);
     bin_faces_kernel<<<n, BIN_THREADS, bin_smem_bytes(w), st>>>(m, w, frame0);
 }
 
@@ -580,7 +588,7 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
                 int best_f = -1;
                 for (int f = lane; f < n_frames; f += 32) {
                     const unsigned nx = *(volatile unsigned*)(w.frame_next + frame0 + f);
-                    if (nx >= (unsigned)R) continue;
+                    if (nx >= w.frame_items[frame0 + f]) continue;
                     const unsigned busy = w.frame_busy[frame0 + f];
                     const unsigned act = *(volatile unsigned*)(w.frame_active + frame0 + f);
                     // per-CTA jitter (0.75 .. 1.25) keeps CTAs that finish together from herding onto one frame
@@ -622,6 +630,8 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
         mbar_wait(&bar, parity);
         parity ^= 1u;
 
+        const unsigned n_items = w.frame_items[fr];
+        const unsigned n_heavy_items = w.frame_heavy[fr] * (unsigned)(REGIONS_PER_TILE * REGION_H);
         const unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
         const unsigned short* torder = w.tile_order + (size_t)fr * T;
         const uint4* pool = w.tile_pool + (size_t)fr * w.pool_cap;
@@ -629,26 +639,39 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
         unsigned next_reg = 0;
         if (lane == 0) {
             next_reg = atomicAdd(w.frame_next + fr, 1u);
-            if (next_reg == (unsigned)R) atomicAdd(w.frames_done, 1u);          // first draw past the end
+            if (next_reg == n_items) atomicAdd(w.frames_done, 1u);              // first draw past the end
         }
         for (;;) {
             const unsigned reg = __shfl_sync(0xffffffffu, next_reg, 0);
-            if (reg >= (unsigned)R) break;
+            if (reg >= n_items) break;
             if (lane == 0) {
                 next_reg = atomicAdd(w.frame_next + fr, 1u);
-                if (next_reg == (unsigned)R) atomicAdd(w.frames_done, 1u);
+                if (next_reg == n_items) atomicAdd(w.frames_done, 1u);
             }
-            const int tile = (int)torder[(int)reg / REGIONS_PER_TILE], sub = (int)reg % REGIONS_PER_TILE;
+            // item -> (tile, region, pixel rows): the frame's heavy tiles come first, one pixel row per item
+            int tile, sub, row0, nrow;
+            if (reg < n_heavy_items) {
+                tile = (int)torder[reg / (REGIONS_PER_TILE * REGION_H)];
+                sub = (int)(reg % (REGIONS_PER_TILE * REGION_H)) / REGION_H;
+                row0 = (int)(reg % REGION_H); nrow = 1;
+            } else {
+                const unsigned r2 = reg - n_heavy_items;
+                tile = (int)torder[w.frame_heavy[fr] + r2 / REGIONS_PER_TILE];
+                sub = (int)(r2 % REGIONS_PER_TILE);
+                row0 = 0; nrow = REGION_H;
+            }
+            const unsigned pmask = (nrow == REGION_H) ? 0xffffffffu : (0xffu << (8 * row0));    // pixels of this item
             const unsigned oreg = (unsigned)(tile * REGIONS_PER_TILE + sub);      // storage index of the region
             const int lx0 = (sub % (TILE_W / REGION_W)) * REGION_W, ly0 = (sub / (TILE_W / REGION_W)) * REGION_H;
             const int x0 = (tile % w.tiles_x) * TILE_W + lx0, y0 = (tile / w.tiles_x) * TILE_H + ly0;
             const unsigned off = toff[tile];
             const int len = (int)(min(toff[tile + 1], (unsigned)w.pool_cap) - min(off, (unsigned)w.pool_cap));
             const int px_x = x0 + (lane & 7), px_y = y0 + (lane >> 3);
-            const bool px_in = (px_x < S) && (px_y < S);
+            const bool px_in = (px_x < S) && (px_y < S) && ((pmask >> lane) & 1u);
+            float* l1_out = w.region_l1 + ((size_t)fr * R + oreg) * REGION_H;      // one slot per pixel row
             if (len == 0 || x0 >= S || y0 >= S) {
                 // no face reaches the tile: alpha = 0, |alpha - T| = T; pix is never read here
-                if (lane == 0) w.region_l1[(size_t)fr * R + oreg] = w.region_tsum[(size_t)fr * R + oreg];
+                if (lane < REGION_H) l1_out[lane] = w.region_tsum[((size_t)fr * R + oreg) * REGION_H + lane];
                 if (alpha_out && px_in) alpha_out[((size_t)(fr - frame0) * S + px_y) * S + px_x] = 0.f;
                 continue;
             }
@@ -666,12 +689,13 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
                     e_next = make_uint4(0u, 0u, 0xffffffffu, 0u);
                     if (j + 32 < len) e_next = pool[off + j + 32];          // next block in flight while this one is filtered
                     const int c0 = (int)(e.z & 0xffu), c1 = (int)((e.z >> 8) & 0xffu), r0 = (int)((e.z >> 16) & 0xffu), r1 = (int)(e.z >> 24);
-                    const bool ov = (j < len) && (c0 <= lx0 + REGION_W - 1) && (c1 >= lx0) && (r0 <= ly0 + REGION_H - 1) && (r1 >= ly0);
+                    const bool ov = (j < len) && (c0 <= lx0 + REGION_W - 1) && (c1 >= lx0) &&
+                                    (r0 <= ly0 + row0 + nrow - 1) && (r1 >= ly0 + row0);
                     const unsigned bal = __ballot_sync(0xffffffffu, ov);
                     if (ov) {
                         const int a = max(c0 - lx0, 0), b = min(c1 - lx0, REGION_W - 1);
                         const unsigned cm = ((1u << (b + 1)) - 1u) & ~((1u << a) - 1u);       // 8-bit column mask
-                        const int ra = max(r0 - ly0, 0), rb = min(r1 - ly0, REGION_H - 1);
+                        const int ra = max(r0 - ly0, row0), rb = min(r1 - ly0, row0 + nrow - 1);
                         const unsigned rows = ((1u << (rb + 1)) - 1u) & ~((1u << ra) - 1u);   // 4-bit row mask
                         const unsigned mk = cm * ((rows * 0x00204081u) & 0x01010101u);         // one byte of cm per selected row
                         const int pos = L + __popc(bal & ltmask);
@@ -822,8 +846,11 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
                 if (myTkey != 0xffffffffu) w.pix_tfid[pi] = (unsigned short)myTfid;
                 if (alpha_out) alpha_out[((size_t)(fr - frame0) * S + px_y) * S + px_x] = alpha;
             }
-            l1 = warp_sum(l1);
-            if (lane == 0) w.region_l1[(size_t)fr * R + oreg] = l1;
+            // per-row sums (8 lanes each), fixed order
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 4);
+            if ((lane & 7) == 0 && ((pmask >> lane) & 1u)) l1_out[lane >> 3] = l1;
         }
     }
     if (lane == 0 && (n_capped | n_spilled)) {
@@ -1068,8 +1095,8 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
     lsplay = block_sum(lsplay, S.red);
     float lsil = 0.f;
     if (use_sil) {
-        const int R = w.tiles_x * w.tiles_y * REGIONS_PER_TILE;
-        for (int r = tid; r < R; r += blockDim.x) lsil += w.region_l1[(size_t)fr * R + r];
+        const int R4 = w.tiles_x * w.tiles_y * REGIONS_PER_TILE * REGION_H;
+        for (int r = tid; r < R4; r += blockDim.x) lsil += w.region_l1[(size_t)fr * R4 + r];
         lsil = block_sum(lsil, S.red) * wt.sil * invw / ((float)w.S * (float)w.S);
     }
     if (tid == 0) { w.frame_loss[fr * 4 + 1] = lpose; w.frame_loss[fr * 4 + 2] = lsplay; w.frame_loss[fr * 4 + 3] = lsil; }
@@ -1337,8 +1364,10 @@ __global__ void __launch_bounds__(256) region_tsum_kernel(Workspace w, int frame
     const int y = (tile / w.tiles_x) * TILE_H + (sub / (TILE_W / REGION_W)) * REGION_H + (lane >> 3);
     float v = 0.f;
     if (x < w.S && y < w.S) v = (float)w.sil[((size_t)fr * w.S + y) * w.S + x];
-    v = warp_sum(v);
-    if (lane == 0) out[(size_t)fr * R + reg] = v;
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if ((lane & 7) == 0) out[((size_t)fr * R + reg) * REGION_H + (lane >> 3)] = v;      // one sum per pixel row
 }
 
 void launch_region_tsum(const Workspace& w, int frame0, int n, float* region_tsum, cudaStream_t st) {

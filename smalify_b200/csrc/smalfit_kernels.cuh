@@ -18,6 +18,7 @@ constexpr int TILE_W = 32, TILE_H = 32;     // CTA work item: 32 regions, pulled
 constexpr int REGIONS_PER_TILE = (TILE_W / REGION_W) * (TILE_H / REGION_H);
 constexpr int KCAP = 256;                   // fragment selection buffer per warp (shared memory part)
 constexpr int SLCAP = 448;                  // region sub-list entries kept in shared memory
+constexpr int HEAVY_TILE_LEN = 1400;             // tiles with at least this many faces are handed out one pixel row at a time
 constexpr int PAIRCAP = 1024;               // (pixel, entry) pairs of one 32-entry block (32 x 32)
 constexpr int MAX_TILES = 1024;             // 32x32 tiles per frame (image side <= 1024)
 constexpr int MAX_LEVELS = 16;
@@ -75,10 +76,13 @@ struct Workspace {
     unsigned* frame_next;       // [N] next region to hand out   (followed by frames_done)
     unsigned* frames_done;      // [1] frames whose counter ran past the end
     unsigned* frame_active;     // [N] CTAs currently working on the frame
-    unsigned* frame_busy;       // [N] regions of tiles that hold faces (they come first in hand-out order)
+    unsigned* frame_busy;       // [N] items of tiles that hold faces (they come first in hand-out order)
+    int heavy_len;              // tiles with at least this many faces count as heavy (set per launch)
+    unsigned* frame_heavy;      // [N] number of heavy tiles (handed out row by row)
+    unsigned* frame_items;      // [N] work items of the frame
     uint2* pix;                 // [N][S*S] (float coef, u32 tkey)
     uint16_t* pix_tfid;         // [N][S*S] tie face id (capped pixels only)
-    float* region_l1;           // [N][tiles*32] per-region sum |alpha - T|
+    float* region_l1;           // [N][tiles*32*4] per region and pixel row: sum |alpha - T|
     float* face_grad;           // [N][Fp][8] (gx0,gy0,gx1,gy1,gx2,gy2,-,-)
     float* dvs;                 // [N][V*3]  per-frame dL/dv_shaped
     float* gJ;                  // [N][105]  per-frame dL/dJ(rest joints)
@@ -89,7 +93,7 @@ struct Workspace {
     const uint8_t* sil;         // [N][S*S]
     const float* kp_target;     // [N][25*2]
     const uint8_t* vis;         // [N][25]
-    const float* region_tsum;   // [N][tiles*32] per-region sum of the target mask
+    const float* region_tsum;   // [N][tiles*32*4] per region and pixel row: sum of the target mask
     const float* inv_window;    // [N] 1 / frames_per_window
     const float* gmask;         // [3]
     const float* rmask;         // [102]
@@ -116,7 +120,7 @@ size_t raster_smem_bytes(const ModelDev& m);
 void launch_shape_forward(const ModelDev& m, const Workspace& w, const Params& p, cudaStream_t st);
 void launch_frame_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n,
                           Weights wt, float* verts_out, cudaStream_t st);
-void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st);
+void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, int n_sm, cudaStream_t st);
 void launch_ndc_soa(const ModelDev& m, const Workspace& w, float* ndc_soa, int frame0, int n, cudaStream_t st);
 void launch_raster_forward(const ModelDev& m, const Workspace& w, const RasterScratch& sc, float* ndc_soa,
                            int frame0, int n, Weights wt, float* alpha_out, int n_ctas, cudaStream_t st);
