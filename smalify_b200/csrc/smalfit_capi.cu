@@ -52,6 +52,9 @@ struct smalfit_ctx {
     ModelDev m{};
     Workspace w{};
     RasterScratch sc{};
+    TileScratch ts{};
+    int tile_ctas = 0;
+    bool use_tile = true;       // SMALFIT_RASTER=v4 selects the region rasteriser (kept for A/B measurements)
     float* ndc_soa = nullptr;
     AdamState* adam_state = nullptr;
     // mutable target buffers (Workspace holds const views)
@@ -217,6 +220,18 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
         w.pool_cap = mult * m.Fp;
     }
     w.tile_pool = P.alloc<uint4>(N * (size_t)w.pool_cap);
+    {
+        const char* sel = getenv("SMALFIT_RASTER");
+        h->use_tile = !(sel && strcmp(sel, "v4") == 0);
+    }
+    w.tile_rec = h->use_tile ? P.alloc<float4>(N * (size_t)w.pool_cap * 4) : nullptr;
+    if (h->use_tile) {
+        h->tile_ctas = h->n_sm * RT_CTAS_PER_SM;
+        h->ts.list_cap = 48 * 1024;
+        h->ts.list_stride = h->ts.list_cap + m.Fp;
+        h->ts.list = P.alloc<uint4>((size_t)h->tile_ctas * h->ts.list_stride);
+        h->ts.item_next = P.alloc<unsigned>(1, true);
+    }
     w.tile_off = P.alloc<unsigned>(N * (tiles + 1), true);
     w.tile_order = P.alloc<unsigned short>(N * tiles, true);
     w.frame_next = P.alloc<unsigned>(2 * N + 1, true);
@@ -343,10 +358,16 @@ static int run_forward(smalfit_t h, const Params& p, int frame0, int n, Weights 
     h->mark(1, st);
     if (raster) {
         launch_bin_faces(h->m, h->w, frame0, n, h->n_sm, st);
-        launch_ndc_soa(h->m, h->w, h->ndc_soa, frame0, n, st);
-        h->mark(2, st);
-        launch_raster_forward(h->m, h->w, h->sc, h->ndc_soa, frame0, n, wt, alpha_out, h->raster_ctas, st);
-        h->n_launches += 3;
+        if (h->use_tile) {
+            h->mark(2, st);
+            launch_raster_tile_forward(h->m, h->w, h->ts, frame0, n, wt, alpha_out, h->tile_ctas, st);
+            h->n_launches += 2;
+        } else {
+            launch_ndc_soa(h->m, h->w, h->ndc_soa, frame0, n, st);
+            h->mark(2, st);
+            launch_raster_forward(h->m, h->w, h->sc, h->ndc_soa, frame0, n, wt, alpha_out, h->raster_ctas, st);
+            h->n_launches += 3;
+        }
     } else {
         h->mark(2, st);
     }

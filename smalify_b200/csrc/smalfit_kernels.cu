@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
     // pass 2: fill, in face order within a warp
     const unsigned ltmask = lanemask_lt();
     uint4* pool = w.tile_pool + (size_t)fr * w.pool_cap;
+    float4* recs = w.tile_rec ? w.tile_rec + (size_t)fr * w.pool_cap * 4 : nullptr;
     unsigned dropped = 0;
     for (int base = f_lo; base < f_hi; base += 32) {
         const int f = base + lane;
@@ -337,6 +338,8 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
         const int nt = ok ? ntw * (r1 / TILE_H - tr0 + 1) : 0;
         const int maxnt = __reduce_max_sync(0xffffffffu, nt);
         const ushort4 f4 = m.faces4[f];
+        FaceSetup fs = face_setup(0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+        if (nt > 0 && recs) fs = load_face(ndc, f4);
         for (int k = 0; k < maxnt; ++k) {
             int t = -1, tx = 0, ty = 0;
             if (k < nt) { ty = tr0 + k / ntw; tx = tc0 + k % ntw; t = ty * w.tiles_x + tx; }
@@ -353,8 +356,15 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
                     const int x0 = tx * TILE_W, y0 = ty * TILE_H;
                     const unsigned lc0 = (unsigned)max(c0 - x0, 0), lc1 = (unsigned)min(c1 - x0, TILE_W - 1);
                     const unsigned lr0 = (unsigned)max(r0 - y0, 0), lr1 = (unsigned)min(r1 - y0, TILE_H - 1);
-                    pool[pos] = make_uint4((unsigned)f | ((unsigned)f4.x << 16), (unsigned)f4.y | ((unsigned)f4.z << 16),
-                                           lc0 | (lc1 << 8) | (lr0 << 16) | (lr1 << 24), 0u);
+                    const unsigned rect = lc0 | (lc1 << 8) | (lr0 << 16) | (lr1 << 24);
+                    pool[pos] = make_uint4((unsigned)f | ((unsigned)f4.x << 16), (unsigned)f4.y | ((unsigned)f4.z << 16), rect, 0u);
+                    if (recs) {
+                        float4* r = recs + (size_t)pos * 4;
+                        r[0] = make_float4(fs.x0, fs.y0, fs.x1, fs.y1);
+                        r[1] = make_float4(fs.x2, fs.y2, fs.z0, fs.z1);
+                        r[2] = make_float4(fs.z2, fs.rden, fs.rl01, fs.rl02);
+                        r[3] = make_float4(fs.rl12, __uint_as_float((unsigned)f), __uint_as_float(rect), 0.f);
+                    }
                 } else {
                     ++dropped;
                 }
@@ -862,6 +872,10 @@ raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int
 size_t raster_smem_bytes(const ModelDev& m) {
     return (size_t)3 * m.Vp * sizeof(float) + (size_t)RAST_WARPS * sizeof(RasterWarpSmem);
 }
+
+}  // namespace smf
+#include "smalfit_raster_tile.cuh"
+namespace smf {
 
 // SoA copy of the NDC vertices for the TMA loads (x[], y[], z[] per frame)
 __global__ void __launch_bounds__(256) ndc_soa_kernel(ModelDev m, Workspace w, int frame0, float* soa) {
@@ -1383,6 +1397,8 @@ cudaError_t configure_kernels(const ModelDev& m) {
     e = cudaFuncSetAttribute(frame_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(bin_faces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (BIN_WARPS + 1) * MAX_TILES * (int)sizeof(unsigned));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(raster_tile_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_tile_smem_bytes());
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(raster_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes(m));
 }

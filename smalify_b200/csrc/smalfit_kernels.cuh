@@ -20,6 +20,11 @@ constexpr int KCAP = 256;                   // fragment selection buffer per war
 constexpr int SLCAP = 448;                  // region sub-list entries kept in shared memory
 constexpr int HEAVY_TILE_LEN = 1400;             // tiles with at least this many faces are handed out one pixel row at a time
 constexpr int PAIRCAP = 1024;               // (pixel, entry) pairs of one 32-entry block (32 x 32)
+constexpr int RT_WARPS = 8, RT_THREADS = RT_WARPS * 32;   // tile rasteriser CTA
+constexpr int RT_CTAS_PER_SM = 3;
+constexpr int RT_PITCH = TILE_W + 1;        // row pitch of a per-warp pixel plane (bank-conflict free in both directions)
+constexpr int RT_PLANE = RT_PITCH * (TILE_H + 1) + 3;      // words per plane (33 x 33 corner grid of the box counts)
+constexpr int RT_BLK = 16;                  // prepared faces per TMA block
 constexpr int MAX_TILES = 1024;             // 32x32 tiles per frame (image side <= 1024)
 constexpr int MAX_LEVELS = 16;
 constexpr float P_SKIP = 2.98023224e-8f;    // 2^-25: below this 1-P rounds to 1.0f in fp32
@@ -70,6 +75,8 @@ struct Workspace {
     float* kp_proj;             // [N][25*2]
     uint2* face_rect;           // [N][Fp]  (c0 | c1<<16, r0 | r1<<16), empty: c0 > c1
     uint4* tile_pool;           // [N][pool_cap] binned faces (fid|v0<<16, v1|v2<<16, tile-local rect, -)
+    float4* tile_rec;           // [N][pool_cap][4] the same entries as prepared faces for the tile rasteriser:
+                                //   (x0,y0,x1,y1) (x2,y2,z0,z1) (z2, 1/(area+eps), 1/|e01|^2, 1/|e02|^2) (1/|e12|^2, fid, rect, -)
     unsigned* tile_off;         // [N][tiles+1] offsets into the frame's pool
     unsigned short* tile_order; // [N][tiles] tiles sorted by decreasing list length (hand-out order)
     int pool_cap;
@@ -108,6 +115,13 @@ struct Weights { float j2d, sil, betas, pose, limit, splay; };
 struct AdamState { int step; float bc1; float bc2_sqrt; int pad; };
 struct AdamSegments { float* p[5]; const float* g[5]; float* m[5]; float* v[5]; int len[5]; int train[5]; };
 
+struct TileScratch {        // tile rasteriser: per resident CTA
+    uint4* list;            // [n_ctas][list_cap + Fp] fragments (depth key, 1-p, face id, -) of the pixels with more than K candidates
+    int list_cap;           // entries one pass may use before the tile is split into further passes
+    int list_stride;        // list_cap + Fp
+    unsigned* item_next;    // [1] next (frame, tile) item to hand out
+};
+
 struct RasterScratch {      // per resident warp, [n_raster_warps][Fp] each
     unsigned* key; float* m; unsigned short* fid;          // fragments beyond KCAP of a pixel
     uint2* ent; unsigned* mask; unsigned short* plist;     // sub-lists longer than SLCAP
@@ -124,6 +138,9 @@ void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, 
 void launch_ndc_soa(const ModelDev& m, const Workspace& w, float* ndc_soa, int frame0, int n, cudaStream_t st);
 void launch_raster_forward(const ModelDev& m, const Workspace& w, const RasterScratch& sc, float* ndc_soa,
                            int frame0, int n, Weights wt, float* alpha_out, int n_ctas, cudaStream_t st);
+size_t raster_tile_smem_bytes();
+void launch_raster_tile_forward(const ModelDev& m, const Workspace& w, const TileScratch& ts, int frame0, int n, Weights wt,
+                                float* alpha_out, int n_ctas, cudaStream_t st);
 void launch_raster_backward(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st);
 void launch_frame_backward(const ModelDev& m, const Workspace& w, const Params& p, const Grads& g,
                            int frame0, int n, Weights wt, cudaStream_t st);

@@ -442,6 +442,33 @@ SMF_HD bool frag_backward(const FaceSetup& f, float px, float py, bool want_pz, 
     return true;
 }
 
+// Forward-side fragment test against a prepared face (edges, 1/(area+eps) and 1/|e|^2 from
+// face_setup): the acceptance arithmetic of frag_backward without the closest-edge bookkeeping.
+// The depth is always formed, with the same operations as face_eval, so that the K-nearest
+// thresholds of the forward and the keys of the backward agree bit for bit.
+SMF_HD bool frag_setup_forward(const FaceSetup& f, float px, float py, float& sd, float& pz) {
+    const float ax = fsub(px, f.x0), ay = fsub(py, f.y0);
+    const float bx = fsub(px, f.x1), by = fsub(py, f.y1);
+    const float cx = fsub(px, f.x2), cy = fsub(py, f.y2);
+    const float n0 = cross2(bx, by, f.e12x, f.e12y);
+    const float n1 = cross2(f.e02x, f.e02y, cx, cy);
+    const float n2 = cross2(ax, ay, f.e01x, f.e01y);
+    const float w0 = fmul(n0, f.rden), w1 = fmul(n1, f.rden), w2 = fmul(n2, f.rden);
+    pz = ffma(w2, f.z2, ffma(w1, f.z1, fmul(w0, f.z0)));
+    if (pz < 0.f) return false;
+    const bool inside = (f.rden > 0.f) ? (n0 > 0.f && n1 > 0.f && n2 > 0.f) : (n0 < 0.f && n1 < 0.f && n2 < 0.f);
+    const float da = dot2(ax, ay, ax, ay), db = dot2(bx, by, bx, by), dc = dot2(cx, cy, cx, cy);
+    const float p01 = dot2(f.e01x, f.e01y, ax, ay), p02 = dot2(f.e02x, f.e02y, ax, ay), p12 = dot2(f.e12x, f.e12y, bx, by);
+    const float t01 = fmul(p01, f.rl01), t02 = fmul(p02, f.rl02), t12 = fmul(p12, f.rl12);
+    const float d01 = (f.rl01 == 0.f || t01 >= 1.f) ? db : (p01 <= 0.f ? da : fmul(fmul(n2, n2), f.rl01));
+    const float d02 = (f.rl02 == 0.f || t02 >= 1.f) ? dc : (p02 <= 0.f ? da : fmul(fmul(n1, n1), f.rl02));
+    const float d12 = (f.rl12 == 0.f || t12 >= 1.f) ? dc : (p12 <= 0.f ? db : fmul(fmul(n0, n0), f.rl12));
+    const float d = fminf(d01, fminf(d02, d12));
+    if (!inside && d >= RAST_BLUR) return false;
+    sd = inside ? -d : d;
+    return true;
+}
+
 // Closest edge of an accepted fragment with its clamped parameter and (p_proj - p), the
 // quantities PointTriangleDistanceBackward differentiates (ties 01 -> 02 -> 12).
 SMF_HD void closest_edge(const FaceSetup& f, float px, float py, Fragment& fr) {

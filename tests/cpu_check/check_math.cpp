@@ -68,6 +68,16 @@ int chk_frag_backward(const float* tri, float px, float py, int want_pz, float* 
     return fr.edge + 1;
 }
 
+// tile-rasteriser forward variant (prepared face): out = (pz, sd)
+int chk_frag_setup_forward(const float* tri, float px, float py, float* out) {
+    const FaceSetup fs = face_setup(tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8]);
+    if (fs.valid == 0.f) return 0;
+    float sd = 0.f, pz = 0.f;
+    const bool ok = frag_setup_forward(fs, px, py, sd, pz);
+    out[0] = pz; out[1] = sd;
+    return ok ? 1 : 0;
+}
+
 int chk_face_rect(const float* tri, int S, int* rect) {
     const FaceSetup fs = face_setup(tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8]);
     return face_pixel_rect(fs, S, rect[0], rect[1], rect[2], rect[3]) ? 1 : 0;

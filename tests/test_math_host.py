@@ -129,6 +129,35 @@ def test_face_eval_decisions_and_gradient(lib):
     assert nfrag > 1000
 
 
+def test_frag_setup_forward_matches_face_eval(lib):
+    """The tile rasteriser's fragment test accepts what face_eval (the backward) accepts, with a
+    bit-identical depth (the K-nearest threshold is compared across the two) and the same signed
+    distance up to rounding; disagreements are confined to the blur boundary."""
+    lib.chk_frag_setup_forward.argtypes = [fp, ctypes.c_float, ctypes.c_float, fp]
+    rng = np.random.default_rng(11)
+    n_both = n_diff = 0
+    for _ in range(400):
+        ctr = rng.uniform(-0.8, 0.8, size=2)
+        tri = np.zeros((3, 3))
+        tri[:, :2] = ctr + rng.normal(size=(3, 2)) * rng.choice([0.01, 0.03, 0.1])
+        tri[:, 2] = rng.uniform(1.5, 3.5, size=3)
+        tri32 = tri.astype(np.float32).reshape(-1).copy()
+        out_a, grad, out_b = np.zeros(4, np.float32), np.zeros(6, np.float32), np.zeros(2, np.float32)
+        for _ in range(40):
+            p = (ctr + rng.normal(size=2) * 0.05).astype(np.float32)
+            a = lib.chk_face_eval(F(tri32), p[0], p[1], F(out_a), F(grad))
+            b = lib.chk_frag_setup_forward(F(tri32), p[0], p[1], F(out_b))
+            if a and b:
+                n_both += 1
+                assert out_a[0].tobytes() == out_b[0].tobytes()          # depth key, bit for bit
+                assert abs(out_a[1] - out_b[1]) <= 2e-5 * abs(out_a[1]) + 1e-10          # 1e-6 in sd / sigma
+            elif a != b:
+                n_diff += 1
+                sd = out_a[1] if a else out_b[1]
+                assert abs(sd - O.BLUR_RADIUS) < 1e-8                     # only at the acceptance boundary
+    assert n_both > 2000 and n_diff <= 2
+
+
 def test_face_rect_is_conservative(lib):
     rng = np.random.default_rng(3)
     S = 64
