@@ -13,7 +13,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmalfit.so")
+# SMALFIT_LIB points tools/ab_bench.py at an experiment build of the same library (never a fallback:
+# a missing file raises below)
+LIB_PATH = os.environ.get("SMALFIT_LIB") or os.path.join(_HERE, "libsmalfit.so")
 
 ABI_VERSION = 1
 L_JOINT, L_SIL, L_BETAS, L_POSE, L_LIMIT, L_SPLAY, L_TEMPORAL, L_TOTAL = range(8)

@@ -227,9 +227,9 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     w.tile_rec = h->use_tile ? P.alloc<float4>(N * (size_t)w.pool_cap * 4) : nullptr;
     if (h->use_tile) {
         h->tile_ctas = h->n_sm * RT_CTAS_PER_SM;
-        h->ts.list_cap = 48 * 1024;
+        h->ts.list_cap = 192 * 1024;        // 1.5 MB per CTA: a 32x32 tile with ~190 candidates on every pixel in one pass
         h->ts.list_stride = h->ts.list_cap + m.Fp;
-        h->ts.list = P.alloc<uint4>((size_t)h->tile_ctas * h->ts.list_stride);
+        h->ts.list = P.alloc<uint2>((size_t)h->tile_ctas * h->ts.list_stride);
         h->ts.item_next = P.alloc<unsigned>(1, true);
     }
     w.tile_off = P.alloc<unsigned>(N * (tiles + 1), true);

@@ -21,7 +21,10 @@ constexpr int SLCAP = 448;                  // region sub-list entries kept in s
 constexpr int HEAVY_TILE_LEN = 1400;             // tiles with at least this many faces are handed out one pixel row at a time
 constexpr int PAIRCAP = 1024;               // (pixel, entry) pairs of one 32-entry block (32 x 32)
 constexpr int RT_WARPS = 8, RT_THREADS = RT_WARPS * 32;   // tile rasteriser CTA
-constexpr int RT_CTAS_PER_SM = 3;
+#ifndef RT_CTAS
+#define RT_CTAS 3
+#endif
+constexpr int RT_CTAS_PER_SM = RT_CTAS;
 constexpr int RT_PITCH = TILE_W + 1;        // row pitch of a per-warp pixel plane (bank-conflict free in both directions)
 constexpr int RT_PLANE = RT_PITCH * (TILE_H + 1) + 3;      // words per plane (33 x 33 corner grid of the box counts)
 constexpr int RT_BLK = 16;                  // prepared faces per TMA block
@@ -116,7 +119,7 @@ struct AdamState { int step; float bc1; float bc2_sqrt; int pad; };
 struct AdamSegments { float* p[5]; const float* g[5]; float* m[5]; float* v[5]; int len[5]; int train[5]; };
 
 struct TileScratch {        // tile rasteriser: per resident CTA
-    uint4* list;            // [n_ctas][list_cap + Fp] fragments (depth key, 1-p, face id, -) of the pixels with more than K candidates
+    uint2* list;            // [n_ctas][list_cap + Fp] fragments (depth key, 1-p) of the pixels with more than K candidates
     int list_cap;           // entries one pass may use before the tile is split into further passes
     int list_stride;        // list_cap + Fp
     unsigned* item_next;    // [1] next (frame, tile) item to hand out

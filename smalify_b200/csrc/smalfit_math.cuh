@@ -443,9 +443,10 @@ SMF_HD bool frag_backward(const FaceSetup& f, float px, float py, bool want_pz, 
 }
 
 // Forward-side fragment test against a prepared face (edges, 1/(area+eps) and 1/|e|^2 from
-// face_setup): the acceptance arithmetic of frag_backward without the closest-edge bookkeeping.
-// The depth is always formed, with the same operations as face_eval, so that the K-nearest
-// thresholds of the forward and the keys of the backward agree bit for bit.
+// face_setup): face_eval without the bounding-box test (implied by the distance test) and without
+// the closest-edge bookkeeping.  Depth and signed distance are formed with exactly face_eval's
+// operations, so the forward's K-nearest thresholds and acceptance decisions agree bit for bit
+// with what the backward recomputes.  Branch-free after the depth test.
 SMF_HD bool frag_setup_forward(const FaceSetup& f, float px, float py, float& sd, float& pz) {
     const float ax = fsub(px, f.x0), ay = fsub(py, f.y0);
     const float bx = fsub(px, f.x1), by = fsub(py, f.y1);
@@ -456,14 +457,17 @@ SMF_HD bool frag_setup_forward(const FaceSetup& f, float px, float py, float& sd
     const float w0 = fmul(n0, f.rden), w1 = fmul(n1, f.rden), w2 = fmul(n2, f.rden);
     pz = ffma(w2, f.z2, ffma(w1, f.z1, fmul(w0, f.z0)));
     if (pz < 0.f) return false;
-    const bool inside = (f.rden > 0.f) ? (n0 > 0.f && n1 > 0.f && n2 > 0.f) : (n0 < 0.f && n1 < 0.f && n2 < 0.f);
-    const float da = dot2(ax, ay, ax, ay), db = dot2(bx, by, bx, by), dc = dot2(cx, cy, cx, cy);
-    const float p01 = dot2(f.e01x, f.e01y, ax, ay), p02 = dot2(f.e02x, f.e02y, ax, ay), p12 = dot2(f.e12x, f.e12y, bx, by);
-    const float t01 = fmul(p01, f.rl01), t02 = fmul(p02, f.rl02), t12 = fmul(p12, f.rl12);
-    const float d01 = (f.rl01 == 0.f || t01 >= 1.f) ? db : (p01 <= 0.f ? da : fmul(fmul(n2, n2), f.rl01));
-    const float d02 = (f.rl02 == 0.f || t02 >= 1.f) ? dc : (p02 <= 0.f ? da : fmul(fmul(n1, n1), f.rl02));
-    const float d12 = (f.rl12 == 0.f || t12 >= 1.f) ? dc : (p12 <= 0.f ? db : fmul(fmul(n0, n0), f.rl12));
+    const float t01 = (f.rl01 == 0.f) ? 1.f : fsat(fmul(dot2(f.e01x, f.e01y, ax, ay), f.rl01));
+    const float q01x = ffma(t01, f.e01x, -ax), q01y = ffma(t01, f.e01y, -ay);
+    const float d01 = dot2(q01x, q01y, q01x, q01y);
+    const float t02 = (f.rl02 == 0.f) ? 1.f : fsat(fmul(dot2(f.e02x, f.e02y, ax, ay), f.rl02));
+    const float q02x = ffma(t02, f.e02x, -ax), q02y = ffma(t02, f.e02y, -ay);
+    const float d02 = dot2(q02x, q02y, q02x, q02y);
+    const float t12 = (f.rl12 == 0.f) ? 1.f : fsat(fmul(dot2(f.e12x, f.e12y, bx, by), f.rl12));
+    const float q12x = ffma(t12, f.e12x, -bx), q12y = ffma(t12, f.e12y, -by);
+    const float d12 = dot2(q12x, q12y, q12x, q12y);
     const float d = fminf(d01, fminf(d02, d12));
+    const bool inside = (w0 > 0.f) && (w1 > 0.f) && (w2 > 0.f);
     if (!inside && d >= RAST_BLUR) return false;
     sd = inside ? -d : d;
     return true;
@@ -491,7 +495,9 @@ SMF_HD void closest_edge(const FaceSetup& f, float px, float py, Fragment& fr) {
 // 1 - sigmoid(-sd/sigma) the way the reference forms it in fp32: p = sigmoid(x), m = 1 - p.
 SMF_HD void frag_prob(float sd, float& p, float& m) {
 #if defined(__CUDA_ARCH__)
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(1.f + __expf(sd * (1.f / RAST_SIGMA))));
+    float e;      // exp(sd / sigma) as one scaled MUFU.EX2 (flushes to 0 / overflows to inf at the ends: p = 1 / p = 0)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(sd * (1.4426950408889634f / RAST_SIGMA)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(1.f + e));
 #else
     p = 1.f / (1.f + expf(sd * (1.f / RAST_SIGMA)));
 #endif

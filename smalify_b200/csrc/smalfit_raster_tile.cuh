@@ -34,6 +34,9 @@ constexpr unsigned RT_SKIP = 0xffffffffu;       // plane value: pixel not handle
 constexpr unsigned RT_LISTED = 0x80000000u;     // plane value: write cursor of a listed pixel (low 31 bits)
 constexpr int RT_SELCAP = 256;                  // keys of one pixel held in registers
 constexpr int RT_PIX = TILE_W * TILE_H;
+constexpr unsigned char RT_CLS_DIRECT = 0, RT_CLS_LISTED = 1, RT_CLS_IDLE = 2;
+constexpr int RT_MAXCHUNK = 512;                // tile lists up to 8192 faces are split by cost, longer ones evenly
+constexpr unsigned RT_FACE_COST = 16u;          // per-face overhead of the sweep, in pair evaluations
 
 struct RtSmem {
     unsigned plane[RT_WARPS][RT_PLANE];
@@ -44,38 +47,69 @@ struct RtSmem {
     unsigned short active[RT_PIX];
     unsigned long long bar[RT_WARPS][2];
     unsigned warp_tot[RT_WARPS];
+    unsigned chunk[RT_MAXCHUNK];         // cost of each RT_BLK-entry chunk of the tile list, then its exclusive prefix
+    unsigned char cls[RT_PIX];           // pixel class in the current pass
+    unsigned cost_total;
     int item;
-    unsigned n_active;
+    unsigned n_active, total;
+    int t_f, t_tile, t_len;              // current item (kept here across the sweep, which needs the registers)
+    unsigned t_off;
+    unsigned n_capped, n_big;
 };
 
-// Product of (1 - p) over the K nearest valid fragments of one pixel's list L[0..c) (slots of rejected
-// pairs carry key 0xffffffff and m = 1).  Threshold (tkey, tfid): selected <=> key < tkey ||
-// (key == tkey && fid <= tfid); (0xffffffff, 0xffff) when every valid fragment is selected.
-__device__ float rt_select(const uint4* __restrict__ L, int c, int lane, unsigned* scratch /* >= RT_SELCAP words */,
-                           unsigned& tkey, unsigned& tfid, bool& capped) {
+// Face id of the slot-th (0-based) entry of the tile list whose rectangle covers pixel (lx, ly): list
+// slots of a pixel are in tile-list order, so this recovers the face behind a slot (ties only).
+__device__ unsigned rt_slot_to_fid(const uint4* __restrict__ pool, int len, int lx, int ly, int slot, int lane) {
+    int run = 0;
+    for (int base = 0; base < len; base += 32) {
+        const int e = base + lane;
+        bool cover = false;
+        unsigned fid = 0u;
+        if (e < len) {
+            const uint4 en = pool[e];
+            const int c0 = (int)(en.z & 0xffu), c1 = (int)((en.z >> 8) & 0xffu), r0 = (int)((en.z >> 16) & 0xffu), r1 = (int)(en.z >> 24);
+            cover = lx >= c0 && lx <= c1 && ly >= r0 && ly <= r1;
+            fid = en.x & 0xffffu;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, cover);
+        const int n = __popc(bal);
+        if (slot < run + n) return __shfl_sync(0xffffffffu, fid, (int)__fns(bal, 0u, slot - run + 1));
+        run += n;
+    }
+    return 0xffffu;
+}
+
+// Product of (1 - p) over the K nearest valid fragments of one pixel's list L[0..c) (key, 1 - p); slots of
+// rejected pairs carry key 0xffffffff and m = 1.  Slots are in face order, so "lower face id first" among
+// equal depths is "lower slot first".  Returns the threshold: selected <=> key < tkey || (key == tkey &&
+// slot <= tslot); tkey = 0xffffffff when every valid fragment is selected, tslot = -1 when no tie is cut.
+__device__ float rt_select(const uint2* __restrict__ L, int c, int lane, unsigned* scratch /* >= RT_SELCAP words */,
+                           unsigned& tkey, int& tslot, bool& capped) {
     constexpr int NR = RT_SELCAP / 32;
     const unsigned ltmask = lanemask_lt();
     unsigned kr[NR];
-    tkey = 0xffffffffu; tfid = 0xffffu; capped = false;
+    float mr[NR];
+    tkey = 0xffffffffu; tslot = -1; capped = false;
     unsigned lo = 0xffffffffu, hi = 0u;
     int nv = 0;
-    if (c <= RT_SELCAP) {
+    const bool small = c <= RT_SELCAP;
+    {
         float pr = 1.f;
+        if (small) {
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const int i = r * 32 + lane;
-            kr[r] = 0xffffffffu;
-            if (i < c) { const uint4 e = L[i]; kr[r] = e.x; pr *= __uint_as_float(e.y); }
-            if (kr[r] != 0xffffffffu) { lo = min(lo, kr[r]); hi = max(hi, kr[r]); ++nv; }
-        }
-        nv = __reduce_add_sync(0xffffffffu, nv);
-        if (nv <= RAST_K) return warp_prod(pr);
-    } else {
-        float pr = 1.f;
-        for (int i = lane; i < c; i += 32) {
-            const uint4 e = L[i];
-            pr *= __uint_as_float(e.y);
-            if (e.x != 0xffffffffu) { lo = min(lo, e.x); hi = max(hi, e.x); ++nv; }
+            for (int r = 0; r < NR; ++r) {
+                const int i = r * 32 + lane;
+                kr[r] = 0xffffffffu; mr[r] = 1.f;
+                if (i < c) { const uint2 e = L[i]; kr[r] = e.x; mr[r] = __uint_as_float(e.y); }
+                pr *= mr[r];
+                if (kr[r] != 0xffffffffu) { lo = min(lo, kr[r]); hi = max(hi, kr[r]); ++nv; }
+            }
+        } else {
+            for (int i = lane; i < c; i += 32) {
+                const uint2 e = L[i];
+                pr *= __uint_as_float(e.y);
+                if (e.x != 0xffffffffu) { lo = min(lo, e.x); hi = max(hi, e.x); ++nv; }
+            }
         }
         nv = __reduce_add_sync(0xffffffffu, nv);
         if (nv <= RAST_K) return warp_prod(pr);
@@ -87,7 +121,7 @@ __device__ float rt_select(const uint4* __restrict__ L, int c, int lane, unsigne
     unsigned t = hi;
     int below = 0;                       // keys < lo
     int want = RAST_K;                   // rank looked for among the keys of the register phase
-    if (c > RT_SELCAP) {
+    if (!small) {
         // narrow the bracket on the whole list until at most RT_SELCAP keys remain in it
         int c_hi = nv;
         while (c_hi - below > RT_SELCAP && lo < hi) {
@@ -127,7 +161,7 @@ __device__ float rt_select(const uint4* __restrict__ L, int c, int lane, unsigne
             if (n > want) hi = mid; else lo = mid + 1;
         }
     }
-    unsigned tf = 0xffffu;
+    int ts = -1;
     if (!exact) {
         t = lo;
         int clt = 0, cle = 0;
@@ -135,74 +169,157 @@ __device__ float rt_select(const uint4* __restrict__ L, int c, int lane, unsigne
         clt = __reduce_add_sync(0xffffffffu, clt);
         cle = __reduce_add_sync(0xffffffffu, cle);
         if (cle > RAST_K) {
-            // ties on the depth at the cut: keep the (K - clt) lowest face ids among key == t
-            const int need = RAST_K - clt;
-            unsigned flo = 0u, fhi = 0xffffu;
-            while (flo < fhi) {
-                const unsigned mid = flo + ((fhi - flo) >> 1);
-                int n = 0;
-                for (int i = lane; i < c; i += 32) { const uint4 e = L[i]; n += (e.x == t && e.z <= mid) ? 1 : 0; }
-                n = __reduce_add_sync(0xffffffffu, n);
-                if (n >= need) fhi = mid; else flo = mid + 1;
+            // ties on the depth at the cut: keep the first (K - clt) slots among key == t
+            int need = RAST_K - clt;
+            for (int base = 0; base < c; base += 32) {
+                const int i = base + lane;
+                const unsigned bal = __ballot_sync(0xffffffffu, i < c && L[i].x == t);
+                const int n = __popc(bal);
+                if (need <= n) { ts = base + (int)__fns(bal, 0u, need); break; }
+                need -= n;
             }
-            tf = flo;
         }
     }
     float prod = 1.f;
-    for (int i = lane; i < c; i += 32) {
-        const uint4 e = L[i];
-        if (e.x < t || (e.x == t && e.z <= tf)) prod *= __uint_as_float(e.y);
+    if (small) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int i = r * 32 + lane;
+            // (in the small case kr[] still holds the pixel's own keys)
+            if (kr[r] < t || (kr[r] == t && (ts < 0 || i <= ts))) prod *= mr[r];
+        }
+    } else {
+        for (int i = lane; i < c; i += 32) {
+            const uint2 e = L[i];
+            if (e.x < t || (e.x == t && (ts < 0 || i <= ts))) prod *= __uint_as_float(e.y);
+        }
     }
-    tkey = t; tfid = tf;
+    tkey = t; tslot = ts;
     return warp_prod(prod);
+}
+
+// One prepared face (64-byte record in the warp's stage) against the pixels of its rectangle, 32 per step.
+// SKIPS: some pixels of the tile are not handled in this pass (multi-pass tiles only).
+template <bool SKIPS>
+__device__ __forceinline__ void rt_sweep_face(const float4* __restrict__ rec, unsigned* __restrict__ plane, uint2* __restrict__ list,
+                                              int lane, int x0, int y0, float inv_s) {
+    const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3];
+    FaceSetup fs;
+    fs.x0 = q0.x; fs.y0 = q0.y; fs.x1 = q0.z; fs.y1 = q0.w; fs.x2 = q1.x; fs.y2 = q1.y;
+    fs.z0 = q1.z; fs.z1 = q1.w; fs.z2 = q2.x; fs.rden = q2.y;
+    fs.rl01 = q2.z; fs.rl02 = q2.w; fs.rl12 = q3.x;
+    fs.e01x = fsub(fs.x1, fs.x0); fs.e01y = fsub(fs.y1, fs.y0);
+    fs.e02x = fsub(fs.x2, fs.x0); fs.e02y = fsub(fs.y2, fs.y0);
+    fs.e12x = fsub(fs.x2, fs.x1); fs.e12y = fsub(fs.y2, fs.y1);
+    const unsigned rect = __float_as_uint(q3.z);
+    const int c0 = (int)(rect & 0xffu), c1 = (int)((rect >> 8) & 0xffu), r0 = (int)((rect >> 16) & 0xffu), r1 = (int)(rect >> 24);
+    const int wd = c1 - c0 + 1, npx = wd * (r1 - r0 + 1);
+    float inv_w;      // MUFU reciprocal: (i + 0.5) / wd is at least 0.5 / 32 away from an integer
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_w) : "f"((float)wd));
+    for (int i = lane; i < npx; i += 32) {
+        const int rr = (int)(((float)i + 0.5f) * inv_w);
+        const int lx = c0 + (i - rr * wd), ly = r0 + rr;
+        const int idx = ly * RT_PITCH + lx;
+        const unsigned v = plane[idx];
+        if (SKIPS && v == RT_SKIP) continue;
+        float sd, pz, mv = 1.f;
+        const bool ok = frag_setup_forward(fs, pix_to_ndc(x0 + lx, inv_s), pix_to_ndc(y0 + ly, inv_s), sd, pz);
+        if (ok) { float pp; frag_prob(sd, pp, mv); }
+        if (v & RT_LISTED) {
+            plane[idx] = v + 1u;
+            list[v & 0x7fffffffu] = make_uint2(ok ? __float_as_uint(pz + 0.f) : 0xffffffffu, __float_as_uint(mv));
+        } else if (ok) {
+            plane[idx] = __float_as_uint(__uint_as_float(v) * mv);
+        }
+    }
+    __syncwarp();        // the next face's lanes may touch the same pixels
 }
 
 __global__ void __launch_bounds__(RT_THREADS, RT_CTAS_PER_SM)
 raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, int n_frames, Weights wt, float* alpha_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RtSmem& sm = *reinterpret_cast<RtSmem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int S = w.S;
-    const float inv_s = 1.f / (float)S;
-    const int T = w.tiles_x * w.tiles_y;
-    const int R = T * REGIONS_PER_TILE;
-    const unsigned n_items = (unsigned)n_frames * (unsigned)T;
-    const unsigned cap = (unsigned)ts.list_cap;
-    uint4* list = ts.list + (size_t)blockIdx.x * ts.list_stride;
+    int lane;                            // (asm volatile: kept in a register instead of being re-derived from S2R in the inner loops)
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int wid = threadIdx.x >> 5;
     unsigned* plane = sm.plane[wid];
     if (lane == 0) { mbar_init(&sm.bar[wid][0], 1); mbar_init(&sm.bar[wid][1], 1); mbar_fence_init(); }
+    if (threadIdx.x == 0) { sm.n_capped = 0u; sm.n_big = 0u; }
     unsigned phase = 0;                  // bit b: parity the warp waits for next on its stage buffer b
-    unsigned long long n_capped = 0, n_big = 0;
 
+    // Values that are only needed again after the sweep live in sm.t across it (the sweep needs the registers).
     for (;;) {
         __syncthreads();                 // the previous item's shared state is no longer read
-        if (tid == 0) sm.item = (int)atomicAdd(ts.item_next, 1u);
+        if (threadIdx.x == 0) sm.item = (int)atomicAdd(ts.item_next, 1u);
         __syncthreads();
         const unsigned item = (unsigned)sm.item;
-        if (item >= n_items) break;
-        const int rank = (int)(item / (unsigned)n_frames), f = (int)(item % (unsigned)n_frames), fr = frame0 + f;
-        const int tile = (int)w.tile_order[(size_t)fr * T + rank];
+        const int T = w.tiles_x * w.tiles_y;
+        if (item >= (unsigned)n_frames * (unsigned)T) break;
+        const int f = (int)(item % (unsigned)n_frames), fr = frame0 + f;
+        const int tile = (int)w.tile_order[(size_t)fr * T + (int)(item / (unsigned)n_frames)];
         const unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
         const unsigned off = min(toff[tile], (unsigned)w.pool_cap);
         const int len = (int)(min(toff[tile + 1], (unsigned)w.pool_cap) - off);
         const int x0 = (tile % w.tiles_x) * TILE_W, y0 = (tile / w.tiles_x) * TILE_H;
-        const size_t slot0 = ((size_t)fr * R + (size_t)tile * REGIONS_PER_TILE) * REGION_H;
+        if (threadIdx.x == 0) { sm.t_f = f; sm.t_tile = tile; sm.t_len = len; sm.t_off = off; }
         if (len == 0) {
             // no face reaches the tile: alpha = 0, |alpha - T| = T; pix is never read here
-            if (tid < REGIONS_PER_TILE * REGION_H) w.region_l1[slot0 + tid] = w.region_tsum[slot0 + tid];
+            const size_t slot0 = ((size_t)fr * T + (size_t)tile) * (REGIONS_PER_TILE * REGION_H);
+            if (threadIdx.x < REGIONS_PER_TILE * REGION_H) w.region_l1[slot0 + threadIdx.x] = w.region_tsum[slot0 + threadIdx.x];
             if (alpha_out) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int x = x0 + lane, y = y0 + wid + RT_WARPS * k;
-                    if (x < S && y < S) alpha_out[((size_t)f * S + y) * S + x] = 0.f;
+                    if (x < w.S && y < w.S) alpha_out[((size_t)f * w.S + y) * w.S + x] = 0.f;
                 }
             }
             continue;
         }
-        const int per = (len + RT_WARPS - 1) / RT_WARPS;
-        const int lo = min(wid * per, len), hi = min(lo + per, len);
         const uint4* pool = w.tile_pool + (size_t)fr * w.pool_cap + off;
-        const float4* recs = w.tile_rec + ((size_t)fr * w.pool_cap + off) * 4;
+        // Split the list into RT_WARPS contiguous ranges of about equal cost (pairs + a per-face overhead),
+        // at RT_BLK granularity: the warps meet at CTA barriers, the slowest one sets the pace.
+        int lo, hi;
+        const int nchunk = (len + RT_BLK - 1) / RT_BLK;
+        if (nchunk <= RT_MAXCHUNK) {
+            for (int base = 0; base < nchunk * RT_BLK; base += RT_THREADS) {
+                const int e = base + (int)threadIdx.x;
+                unsigned cost = 0u;
+                if (e < len) {
+                    const unsigned rect = pool[e].z;
+                    cost = (((rect >> 8) & 0xffu) - (rect & 0xffu) + 1u) * ((rect >> 24) - ((rect >> 16) & 0xffu) + 1u) + RT_FACE_COST;
+                }
+#pragma unroll
+                for (int o = RT_BLK / 2; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+                if ((lane & (RT_BLK - 1)) == 0 && e < nchunk * RT_BLK) sm.chunk[e / RT_BLK] = cost;
+            }
+            __syncthreads();
+            if (wid == 0) {
+                constexpr int PER = RT_MAXCHUNK / 32;
+                unsigned loc[PER];
+                unsigned sum = 0u;
+#pragma unroll
+                for (int k = 0; k < PER; ++k) { const int ch = lane * PER + k; loc[k] = (ch < nchunk) ? sm.chunk[ch] : 0u; sum += loc[k]; }
+                unsigned incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+                unsigned run = incl - sum;
+#pragma unroll
+                for (int k = 0; k < PER; ++k) { const int ch = lane * PER + k; if (ch < nchunk) sm.chunk[ch] = run; run += loc[k]; }
+                if (lane == 31) sm.cost_total = incl;
+            }
+            __syncthreads();
+            const unsigned long long tot = sm.cost_total;
+            const unsigned t_lo = (unsigned)((tot * (unsigned)wid) / RT_WARPS), t_hi = (unsigned)((tot * (unsigned)(wid + 1)) / RT_WARPS);
+            int n_lo = 0, n_hi = 0;          // chunks that start before the target: the exclusive prefix is non-decreasing
+            for (int ch = lane; ch < nchunk; ch += 32) { const unsigned v = sm.chunk[ch]; n_lo += (v < t_lo) ? 1 : 0; n_hi += (v < t_hi) ? 1 : 0; }
+            n_lo = __reduce_add_sync(0xffffffffu, n_lo);
+            n_hi = __reduce_add_sync(0xffffffffu, n_hi);
+            if (wid == RT_WARPS - 1) n_hi = nchunk;
+            lo = min(n_lo * RT_BLK, len); hi = min(n_hi * RT_BLK, len);
+        } else {
+            const int per = ((nchunk + RT_WARPS - 1) / RT_WARPS) * RT_BLK;
+            lo = min(wid * per, len); hi = min(lo + per, len);
+        }
 
         for (unsigned round = 0;; ++round) {
             // ---- P0: candidates per (warp, pixel) = integral of the rectangles' corner grid
@@ -231,63 +348,73 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
             __syncthreads();
 
             // ---- P0b: classify the pixels (thread: column = lane, rows wid + 8k), lay out the lists
-            unsigned cnt4[4];
-            unsigned mysum = 0u;
+            {
+                const unsigned cap = (unsigned)ts.list_cap;
+                unsigned cnt4[4];
+                unsigned mysum = 0u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int idx = (wid + RT_WARPS * k) * RT_PITCH + lane;
-                unsigned c = 0u;
+                for (int k = 0; k < 4; ++k) {
+                    const int idx = (wid + RT_WARPS * k) * RT_PITCH + lane;
+                    unsigned c = 0u;
 #pragma unroll
-                for (int q = 0; q < RT_WARPS; ++q) c += sm.plane[q][idx];
-                cnt4[k] = c;
-                if (c > (unsigned)RAST_K) mysum += c;
-            }
-            unsigned incl = mysum;
+                    for (int q = 0; q < RT_WARPS; ++q) c += sm.plane[q][idx];
+                    cnt4[k] = c;
+                    if (c > (unsigned)RAST_K) mysum += c;
+                }
+                unsigned incl = mysum;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
-            if (lane == 31) sm.warp_tot[wid] = incl;
-            if (tid == 0) sm.n_active = 0u;
-            __syncthreads();
-            unsigned base = 0u, total = 0u;
+                for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+                if (lane == 31) sm.warp_tot[wid] = incl;
+                if (threadIdx.x == 0) sm.n_active = 0u;
+                __syncthreads();
+                unsigned base = 0u, total = 0u;
 #pragma unroll
-            for (int q = 0; q < RT_WARPS; ++q) { const unsigned v = sm.warp_tot[q]; if (q < wid) base += v; total += v; }
-            unsigned run = base + incl - mysum;
-            const unsigned win_lo = round * cap;
-            unsigned actmask = 0u;
+                for (int q = 0; q < RT_WARPS; ++q) { const unsigned v = sm.warp_tot[q]; if (q < wid) base += v; total += v; }
+                if (threadIdx.x == 0) sm.total = total;
+                unsigned run = base + incl - mysum;
+                const unsigned win_lo = round * cap;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int row = wid + RT_WARPS * k;
-                const int idx = row * RT_PITCH + lane, px = row * TILE_W + lane;
-                const unsigned c = cnt4[k];
-                if (c > (unsigned)RAST_K) {
-                    const unsigned o = run;
-                    run += c;
-                    const bool act = (o >= win_lo) && (o - win_lo < cap);
-                    unsigned cur = RT_LISTED | (o - win_lo);
+                for (int k = 0; k < 4; ++k) {
+                    const int row = wid + RT_WARPS * k;
+                    const int idx = row * RT_PITCH + lane, px = row * TILE_W + lane;
+                    const unsigned c = cnt4[k];
+                    unsigned char cls;
+                    if (c > (unsigned)RAST_K) {
+                        const unsigned o = run;
+                        run += c;
+                        const bool act = (o >= win_lo) && (o - win_lo < cap);
+                        unsigned cur = RT_LISTED | (o - win_lo);
 #pragma unroll
-                    for (int q = 0; q < RT_WARPS; ++q) {
-                        const unsigned cw = sm.plane[q][idx];
-                        sm.plane[q][idx] = act ? cur : RT_SKIP;
-                        cur += cw;
+                        for (int q = 0; q < RT_WARPS; ++q) {
+                            const unsigned cw = sm.plane[q][idx];
+                            sm.plane[q][idx] = act ? cur : RT_SKIP;
+                            cur += cw;
+                        }
+                        if (act) {
+                            const unsigned a = atomicAdd(&sm.n_active, 1u);
+                            sm.active[a] = (unsigned short)px;
+                            sm.list_off[px] = o - win_lo;
+                            sm.list_cnt[px] = (unsigned short)c;
+                        }
+                        cls = act ? RT_CLS_LISTED : RT_CLS_IDLE;
+                    } else {
+                        const unsigned v = (round == 0u) ? 0x3f800000u : RT_SKIP;
+#pragma unroll
+                        for (int q = 0; q < RT_WARPS; ++q) sm.plane[q][idx] = v;
+                        cls = (round == 0u) ? RT_CLS_DIRECT : RT_CLS_IDLE;
                     }
-                    if (act) {
-                        const unsigned a = atomicAdd(&sm.n_active, 1u);
-                        sm.active[a] = (unsigned short)px;
-                        sm.list_off[px] = o - win_lo;
-                        sm.list_cnt[px] = (unsigned short)c;
-                        actmask |= 1u << k;
-                    }
-                } else {
-                    const unsigned v = (round == 0u) ? 0x3f800000u : RT_SKIP;
-#pragma unroll
-                    for (int q = 0; q < RT_WARPS; ++q) sm.plane[q][idx] = v;
+                    sm.cls[px] = cls;
                 }
             }
             __syncthreads();
 
             // ---- P1: sweep this warp's faces (TMA double buffer of RT_BLK prepared faces)
             {
+                const float4* recs = w.tile_rec + ((size_t)fr * w.pool_cap + off) * 4;
+                uint2* list = ts.list + (size_t)blockIdx.x * ts.list_stride;
+                const float inv_s = 1.f / (float)w.S;
                 const int nblk = (hi - lo + RT_BLK - 1) / RT_BLK;
+                const bool skips = (round != 0u) || (sm.total > (unsigned)ts.list_cap);       // otherwise no plane holds RT_SKIP
                 if (nblk > 0 && lane == 0) {
                     // the stage doubles as P2's scratch (generic-proxy writes): order them before the bulk copies
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -306,37 +433,8 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                     phase ^= 1u << (b & 1);
                     const int nrec = min(RT_BLK, hi - e0);
                     const float4* st = sm.stage[wid][b & 1];
-                    for (int j = 0; j < nrec; ++j) {
-                        const float4 q0 = st[j * 4 + 0], q1 = st[j * 4 + 1], q2 = st[j * 4 + 2], q3 = st[j * 4 + 3];
-                        FaceSetup fs;
-                        fs.x0 = q0.x; fs.y0 = q0.y; fs.x1 = q0.z; fs.y1 = q0.w; fs.x2 = q1.x; fs.y2 = q1.y;
-                        fs.z0 = q1.z; fs.z1 = q1.w; fs.z2 = q2.x; fs.rden = q2.y;
-                        fs.rl01 = q2.z; fs.rl02 = q2.w; fs.rl12 = q3.x;
-                        fs.e01x = fsub(fs.x1, fs.x0); fs.e01y = fsub(fs.y1, fs.y0);
-                        fs.e02x = fsub(fs.x2, fs.x0); fs.e02y = fsub(fs.y2, fs.y0);
-                        fs.e12x = fsub(fs.x2, fs.x1); fs.e12y = fsub(fs.y2, fs.y1);
-                        const unsigned fid = __float_as_uint(q3.y), rect = __float_as_uint(q3.z);
-                        const int c0 = (int)(rect & 0xffu), c1 = (int)((rect >> 8) & 0xffu), r0 = (int)((rect >> 16) & 0xffu), r1 = (int)(rect >> 24);
-                        const int wd = c1 - c0 + 1, npx = wd * (r1 - r0 + 1);
-                        const float inv_w = 1.f / (float)wd;
-                        for (int i = lane; i < npx; i += 32) {
-                            const int rr = (int)(((float)i + 0.5f) * inv_w);
-                            const int lx = c0 + (i - rr * wd), ly = r0 + rr;
-                            const int idx = ly * RT_PITCH + lx;
-                            const unsigned v = plane[idx];
-                            if (v == RT_SKIP) continue;
-                            float sd, pz, mv = 1.f;
-                            const bool ok = frag_setup_forward(fs, pix_to_ndc(x0 + lx, inv_s), pix_to_ndc(y0 + ly, inv_s), sd, pz);
-                            if (ok) { float pp; frag_prob(sd, pp, mv); }
-                            if (v & RT_LISTED) {
-                                plane[idx] = v + 1u;
-                                list[v & 0x7fffffffu] = make_uint4(ok ? __float_as_uint(pz + 0.f) : 0xffffffffu, __float_as_uint(mv), fid, 0u);
-                            } else if (ok) {
-                                plane[idx] = __float_as_uint(__uint_as_float(v) * mv);
-                            }
-                        }
-                        __syncwarp();        // the next face's lanes may touch the same pixels
-                    }
+                    if (skips) { for (int j = 0; j < nrec; ++j) rt_sweep_face<true>(st + j * 4, plane, list, lane, x0, y0, inv_s); }
+                    else       { for (int j = 0; j < nrec; ++j) rt_sweep_face<false>(st + j * 4, plane, list, lane, x0, y0, inv_s); }
                 }
             }
             __syncthreads();
@@ -344,73 +442,85 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
             // ---- P2: listed pixels of this pass, one warp each
             {
                 const unsigned na = sm.n_active;
+                const uint2* list = ts.list + (size_t)blockIdx.x * ts.list_stride;
                 unsigned* scratch = reinterpret_cast<unsigned*>(sm.stage[wid][0]);     // the stage is idle here
                 for (unsigned a = (unsigned)wid; a < na; a += RT_WARPS) {
                     const int px = (int)sm.active[a];
                     const int c = (int)sm.list_cnt[px];
-                    unsigned tk, tf;
+                    unsigned tk, tf = 0xffffu;
+                    int tslot;
                     bool capped;
-                    const float P = rt_select(list + sm.list_off[px], c, lane, scratch, tk, tf, capped);
+                    const float P = rt_select(list + sm.list_off[px], c, lane, scratch, tk, tslot, capped);
+                    if (tslot >= 0)
+                        tf = rt_slot_to_fid(w.tile_pool + (size_t)(frame0 + sm.t_f) * w.pool_cap + sm.t_off, sm.t_len, px % TILE_W, px / TILE_W, tslot, lane);
                     __syncwarp();
                     if (lane == 0) {
                         sm.plane[0][(px / TILE_W) * RT_PITCH + (px % TILE_W)] = __float_as_uint(P);
                         sm.list_off[px] = tk;
                         sm.list_cnt[px] = (unsigned short)tf;
-                        if (capped) ++n_capped;
-                        if (c > RT_SELCAP) ++n_big;
+                        if (capped) atomicAdd(&sm.n_capped, 1u);
+                        if (c > RT_SELCAP) atomicAdd(&sm.n_big, 1u);
                     }
                 }
             }
             __syncthreads();
 
             // ---- P3: finish the pixels of this pass
+            {
+                const int S = w.S, f2 = sm.t_f, fr2 = frame0 + f2, tile2 = sm.t_tile;
+                const int x = (tile2 % w.tiles_x) * TILE_W + lane;
+                const float inv_s = 1.f / (float)S;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int row = wid + RT_WARPS * k;
-                const int idx = row * RT_PITCH + lane, px = row * TILE_W + lane;
-                const bool listed = cnt4[k] > (unsigned)RAST_K;
-                if (listed ? !((actmask >> k) & 1u) : (round != 0u)) continue;
-                float P = 1.f;
-                unsigned tk = 0xffffffffu, tf = 0xffffu;
-                if (listed) {
-                    P = __uint_as_float(sm.plane[0][idx]); tk = sm.list_off[px]; tf = sm.list_cnt[px];
-                } else if (cnt4[k] > 0u) {
+                for (int k = 0; k < 4; ++k) {
+                    const int row = wid + RT_WARPS * k;
+                    const int idx = row * RT_PITCH + lane, px = row * TILE_W + lane;
+                    const unsigned cls = sm.cls[px];
+                    if (cls == RT_CLS_IDLE) continue;
+                    float P;
+                    unsigned tk = 0xffffffffu, tf = 0xffffu;
+                    if (cls == RT_CLS_LISTED) {
+                        P = __uint_as_float(sm.plane[0][idx]); tk = sm.list_off[px]; tf = sm.list_cnt[px];
+                    } else {
+                        P = __uint_as_float(sm.plane[0][idx]);
 #pragma unroll
-                    for (int q = 0; q < RT_WARPS; ++q) P *= __uint_as_float(sm.plane[q][idx]);
-                }
-                const int x = x0 + lane, y = y0 + row;
-                float l1 = 0.f;
-                if (x < S && y < S) {
-                    const size_t pi = ((size_t)fr * S + y) * S + x;
-                    const float alpha = 1.f - P;
-                    const float d = alpha - (float)w.sil[pi];
-                    l1 = fabsf(d);
-                    float coef = 0.f;
-                    if (P < 1.f && P >= P_SKIP && d != 0.f) {        // P < 1 <=> the pixel has fragments
-                        const float ga = wt.sil * w.inv_window[fr] * inv_s * inv_s * (d > 0.f ? 1.f : -1.f);
-                        coef = ga * P * (1.f / RAST_SIGMA);
+                        for (int q = 1; q < RT_WARPS; ++q) P *= __uint_as_float(sm.plane[q][idx]);
                     }
-                    w.pix[pi] = make_uint2(__float_as_uint(coef), tk);
-                    if (tk != 0xffffffffu) w.pix_tfid[pi] = (unsigned short)tf;
-                    if (alpha_out) alpha_out[((size_t)f * S + y) * S + x] = alpha;
+                    const int y = (tile2 / w.tiles_x) * TILE_H + row;
+                    float l1 = 0.f;
+                    if (x < S && y < S) {
+                        const size_t pi = ((size_t)fr2 * S + y) * S + x;
+                        const float alpha = 1.f - P;
+                        const float d = alpha - (float)w.sil[pi];
+                        l1 = fabsf(d);
+                        float coef = 0.f;
+                        if (P < 1.f && P >= P_SKIP && d != 0.f) {        // P < 1 <=> the pixel has fragments
+                            const float ga = wt.sil * w.inv_window[fr2] * inv_s * inv_s * (d > 0.f ? 1.f : -1.f);
+                            coef = ga * P * (1.f / RAST_SIGMA);
+                        }
+                        w.pix[pi] = make_uint2(__float_as_uint(coef), tk);
+                        if (tk != 0xffffffffu) w.pix_tfid[pi] = (unsigned short)tf;
+                        if (alpha_out) alpha_out[((size_t)f2 * S + y) * S + x] = alpha;
+                    }
+                    sm.l1[px] = l1;
                 }
-                sm.l1[px] = l1;
             }
-            if (total <= (round + 1u) * cap) break;      // every listed pixel started inside a window already done
+            if (sm.total <= (round + 1u) * (unsigned)ts.list_cap) break;      // every listed pixel started inside a window already done
             __syncthreads();                             // planes are rebuilt by the next pass
         }
         __syncthreads();
         // per region row (8 pixels), fixed order
-        if (tid < REGIONS_PER_TILE * REGION_H) {
-            const int sub = tid / REGION_H, row = tid % REGION_H;
+        if (threadIdx.x < REGIONS_PER_TILE * REGION_H) {
+            const int sub = threadIdx.x / REGION_H, row = threadIdx.x % REGION_H;
             const int lx0 = (sub % (TILE_W / REGION_W)) * REGION_W, ly0 = (sub / (TILE_W / REGION_W)) * REGION_H;
             const float* p = sm.l1 + (ly0 + row) * TILE_W + lx0;
-            w.region_l1[slot0 + tid] = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+            const size_t slot0 = ((size_t)(frame0 + sm.t_f) * (w.tiles_x * w.tiles_y) + (size_t)sm.t_tile) * (REGIONS_PER_TILE * REGION_H);
+            w.region_l1[slot0 + threadIdx.x] = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
         }
     }
-    if (lane == 0 && (n_capped | n_big)) {
-        atomicAdd(w.counters + 0, n_capped);
-        atomicAdd(w.counters + 1, n_big);
+    __syncthreads();
+    if (threadIdx.x == 0 && (sm.n_capped | sm.n_big)) {
+        atomicAdd(w.counters + 0, (unsigned long long)sm.n_capped);
+        atomicAdd(w.counters + 1, (unsigned long long)sm.n_big);
     }
 }
 

@@ -131,8 +131,7 @@ def test_face_eval_decisions_and_gradient(lib):
 
 def test_frag_setup_forward_matches_face_eval(lib):
     """The tile rasteriser's fragment test accepts what face_eval (the backward) accepts, with a
-    bit-identical depth (the K-nearest threshold is compared across the two) and the same signed
-    distance up to rounding; disagreements are confined to the blur boundary."""
+    bit-identical depth (the K-nearest threshold is compared across the two) and signed distance."""
     lib.chk_frag_setup_forward.argtypes = [fp, ctypes.c_float, ctypes.c_float, fp]
     rng = np.random.default_rng(11)
     n_both = n_diff = 0
@@ -150,12 +149,10 @@ def test_frag_setup_forward_matches_face_eval(lib):
             if a and b:
                 n_both += 1
                 assert out_a[0].tobytes() == out_b[0].tobytes()          # depth key, bit for bit
-                assert abs(out_a[1] - out_b[1]) <= 2e-5 * abs(out_a[1]) + 1e-10          # 1e-6 in sd / sigma
-            elif a != b:
-                n_diff += 1
-                sd = out_a[1] if a else out_b[1]
-                assert abs(sd - O.BLUR_RADIUS) < 1e-8                     # only at the acceptance boundary
-    assert n_both > 2000 and n_diff <= 2
+                assert out_a[1].tobytes() == out_b[1].tobytes()          # signed distance too
+            else:
+                n_diff += int(a != b)
+    assert n_both > 2000 and n_diff == 0
 
 
 def test_face_rect_is_conservative(lib):
