@@ -212,6 +212,7 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     w.gjoint = P.alloc<float>(N * NMJ * 3, true);
     w.kp_proj = P.alloc<float>(N * NKP * 2, true);
     w.face_rect = P.alloc<uint2>(N * m.Fp);
+    w.face_rec = P.alloc<float4>(N * m.Fp * 4);
     {   // (face, tile) entries per frame grow with the face size in pixels: ~Fp * ((bbox_px + 32) / 32)^2
         const float bbox_px = 18.f * (float)image_size / 256.f;
         const float per_face = ((bbox_px + 32.f) / 32.f) * ((bbox_px + 32.f) / 32.f);

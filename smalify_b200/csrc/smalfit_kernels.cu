@@ -265,13 +265,18 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
     for (int f = f_lo + lane; f < f_hi; f += 32) {
         const FaceSetup fs = load_face(ndc, m.faces4[f]);
         int c0, c1, r0, r1;
+        uint2 rc = make_uint2(0xffffu, 0xffffu);
         if (face_pixel_rect(fs, w.S, c0, c1, r0, r1)) {
-            rects[f] = make_uint2((unsigned)c0 | ((unsigned)c1 << 16), (unsigned)r0 | ((unsigned)r1 << 16));
+            rc = make_uint2((unsigned)c0 | ((unsigned)c1 << 16), (unsigned)r0 | ((unsigned)r1 << 16));
             for (int ty = r0 / TILE_H; ty <= r1 / TILE_H; ++ty)
                 for (int tx = c0 / TILE_W; tx <= c1 / TILE_W; ++tx) atomicAdd(&cnt[wid * T + ty * w.tiles_x + tx], 1u);
-        } else {
-            rects[f] = make_uint2(0xffffu, 0xffffu);
         }
+        rects[f] = rc;
+        float4* fr4 = w.face_rec + ((size_t)fr * m.Fp + f) * 4;
+        fr4[0] = make_float4(fs.x0, fs.y0, fs.x1, fs.y1);
+        fr4[1] = make_float4(fs.x2, fs.y2, fs.z0, fs.z1);
+        fr4[2] = make_float4(fs.z2, fs.rden, fs.rl01, fs.rl02);
+        fr4[3] = make_float4(fs.rl12, 0.f, __uint_as_float(rc.x), __uint_as_float(rc.y));
     }
     __syncthreads();
     // prefix over tiles (blocked: each thread owns a run of consecutive tiles)
@@ -906,31 +911,38 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(ModelDev m, Worksp
     const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int fr = frame0 + blockIdx.y;
     if (f >= m.Fp) return;
-    const ushort4 f4 = m.faces4[f];
-    const float4* ndc = w.ndc + (size_t)fr * m.Vp;
-    const float4 A = ndc[f4.x], B = ndc[f4.y], C = ndc[f4.z];
-    FaceSetup fs = face_setup(A.x, A.y, A.z, B.x, B.y, B.z, C.x, C.y, C.z);
-    if (f4.w == 0) fs.valid = 0.f;
+    // prepared face written by bin_faces (the whole warp reads the same 64 bytes)
+    const float4* rec = w.face_rec + ((size_t)fr * m.Fp + f) * 4;
+    const float4 q3 = __ldg(rec + 3);
+    const unsigned rx = __float_as_uint(q3.z), ry = __float_as_uint(q3.w);
+    const int c0 = (int)(rx & 0xffffu), c1 = (int)(rx >> 16), r0 = (int)(ry & 0xffffu), r1 = (int)(ry >> 16);
     float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int c0, c1, r0, r1;
-    if (face_pixel_rect(fs, w.S, c0, c1, r0, r1)) {
+    if (c0 <= c1) {
+        const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+        FaceSetup fs;
+        fs.x0 = q0.x; fs.y0 = q0.y; fs.x1 = q0.z; fs.y1 = q0.w; fs.x2 = q1.x; fs.y2 = q1.y;
+        fs.z0 = q1.z; fs.z1 = q1.w; fs.z2 = q2.x; fs.rden = q2.y;
+        fs.rl01 = q2.z; fs.rl02 = q2.w; fs.rl12 = q3.x;
+        fs.e01x = fsub(fs.x1, fs.x0); fs.e01y = fsub(fs.y1, fs.y0);
+        fs.e02x = fsub(fs.x2, fs.x0); fs.e02y = fsub(fs.y2, fs.y0);
+        fs.e12x = fsub(fs.x2, fs.x1); fs.e12y = fsub(fs.y2, fs.y1);
         const int S = w.S;
         const float inv_s = 1.f / (float)S;
         const int wd = c1 - c0 + 1, npx = wd * (r1 - r0 + 1);
-        const float inv_w = 1.f / (float)wd;
+        float inv_w;      // MUFU reciprocal: (i + 0.5) / wd stays far from an integer for rectangles of sane width
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_w) : "f"((float)wd));
         const uint2* pix = w.pix + (size_t)fr * S * S;
         for (int i = lane; i < npx; i += 32) {
-            const int rr = (int)(((float)i + 0.5f) * inv_w);
-            const int cc = i - rr * wd;
+            int rr = (int)(((float)i + 0.5f) * inv_w);
+            int cc = i - rr * wd;
+            if (cc < 0) { cc += wd; --rr; } else if (cc >= wd) { cc -= wd; ++rr; }      // very wide rectangles: exact anyway
             const int x = c0 + cc, y = r0 + rr;
             const uint2 pr = pix[(size_t)y * S + x];
             const float coef = __uint_as_float(pr.x);
             if (coef == 0.f) continue;
-            // same edge functions / depth as the forward pass (bit-identical keys); the clamped-t distances
-            // differ from the forward's cross^2/|e|^2 form only in the last bits (measured: frag_backward,
-            // which shares the forward's form, is 15 % slower here)
+            // the same arithmetic as the forward's fragment test: bit-identical acceptance and depth keys
             Fragment frag;
-            if (!face_eval(fs, pix_to_ndc(x, inv_s), pix_to_ndc(y, inv_s), frag)) continue;
+            if (!face_eval_core(fs, pix_to_ndc(x, inv_s), pix_to_ndc(y, inv_s), frag)) continue;
             if (pr.y != 0xffffffffu) {
                 const unsigned key = __float_as_uint(frag.pz + 0.f);
                 if (key > pr.y) continue;
@@ -940,13 +952,26 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(ModelDev m, Worksp
             frag_prob(frag.sd, p, mv);
             frag_grad(frag, -coef * p, g);
         }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) g[k] = warp_sum(g[k]);
+        // six sums over the warp with 8 shuffles: every step halves the values a lane carries
+        // (fixed tree: deterministic).  Totals end up in lanes 0, 4, 8 (g0..g2) and 16, 20, 24 (g3..g5).
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        float a0 = b4 ? g[3] : g[0], a1 = b4 ? g[4] : g[1], a2 = b4 ? g[5] : g[2];
+        a0 += __shfl_xor_sync(0xffffffffu, b4 ? g[0] : g[3], 16);
+        a1 += __shfl_xor_sync(0xffffffffu, b4 ? g[1] : g[4], 16);
+        a2 += __shfl_xor_sync(0xffffffffu, b4 ? g[2] : g[5], 16);
+        float h0 = b3 ? a2 : a0, h1 = b3 ? 0.f : a1;
+        h0 += __shfl_xor_sync(0xffffffffu, b3 ? a0 : a2, 8);
+        h1 += __shfl_xor_sync(0xffffffffu, b3 ? a1 : 0.f, 8);
+        float v = b2 ? h1 : h0;
+        v += __shfl_xor_sync(0xffffffffu, b2 ? h0 : h1, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        g[0] = v;
     }
-    if (lane == 0) {
-        float4* o = reinterpret_cast<float4*>(w.face_grad + ((size_t)fr * m.Fp + f) * 8);
-        o[0] = make_float4(g[0], g[1], g[2], g[3]);
-        o[1] = make_float4(g[4], g[5], 0.f, 0.f);
+    // slot of the total a lane holds: (b4, b3, b2) -> 0,1,2,-,3,4,5,-
+    if ((lane & 3) == 0 && (lane & 12) != 12) {
+        const int slot = ((lane & 16) ? 3 : 0) + ((lane & 8) ? 2 : ((lane & 4) ? 1 : 0));
+        w.face_grad[((size_t)fr * m.Fp + f) * 8 + slot] = g[0];
     }
 }
 

@@ -77,6 +77,8 @@ struct Workspace {
     float* gjoint;              // [N][41*3] dL/d(model joints) from the keypoint term
     float* kp_proj;             // [N][25*2]
     uint2* face_rect;           // [N][Fp]  (c0 | c1<<16, r0 | r1<<16), empty: c0 > c1
+    float4* face_rec;           // [N][Fp][4] prepared faces for the backward: (x0,y0,x1,y1) (x2,y2,z0,z1)
+                                //   (z2, 1/(area+eps), 1/|e01|^2, 1/|e02|^2) (1/|e12|^2, -, rect.x, rect.y)
     uint4* tile_pool;           // [N][pool_cap] binned faces (fid|v0<<16, v1|v2<<16, tile-local rect, -)
     float4* tile_rec;           // [N][pool_cap][4] the same entries as prepared faces for the tile rasteriser:
                                 //   (x0,y0,x1,y1) (x2,y2,z0,z1) (z2, 1/(area+eps), 1/|e01|^2, 1/|e02|^2) (1/|e12|^2, fid, rect, -)

@@ -317,9 +317,15 @@ struct Fragment {
 };
 
 // CheckPixelInsideFace.  Returns true when (face, pixel) yields a fragment.
+SMF_HD bool face_eval_core(const FaceSetup& f, float px, float py, Fragment& fr);
 SMF_HD bool face_eval(const FaceSetup& f, float px, float py, Fragment& fr) {
     if (f.valid == 0.f) return false;
     if (px > f.bx1 || px < f.bx0 || py > f.by1 || py < f.by0) return false;
+    return face_eval_core(f, px, py, fr);
+}
+// face_eval without the validity / bounding-box tests (implied for the pixels of a valid face's
+// rectangle by the distance test): needs only the vertices, edges, rden and rl* of the set-up.
+SMF_HD bool face_eval_core(const FaceSetup& f, float px, float py, Fragment& fr) {
     const float ax = fsub(px, f.x0), ay = fsub(py, f.y0);     // p - v0
     const float bx = fsub(px, f.x1), by = fsub(py, f.y1);     // p - v1
     const float cx = fsub(px, f.x2), cy = fsub(py, f.y2);     // p - v2
