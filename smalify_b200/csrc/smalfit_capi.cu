@@ -229,11 +229,20 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     if (h->use_tile) {
         h->tile_ctas = h->n_sm * RT_CTAS_PER_SM;
         h->ts.list_cap = 192 * 1024;        // 1.5 MB per CTA: a 32x32 tile with ~190 candidates on every pixel in one pass
+        { const char* e_cap = getenv("SMALFIT_RT_LISTCAP"); if (e_cap && atoi(e_cap) > 0) h->ts.list_cap = atoi(e_cap); }    // tests force multi-pass tiles
         h->ts.list_stride = h->ts.list_cap + m.Fp;
         h->ts.list = P.alloc<uint2>((size_t)h->tile_ctas * h->ts.list_stride);
-        h->ts.item_next = P.alloc<unsigned>(1, true);
+        h->ts.item_next = P.alloc<unsigned>(2, true);
+        h->ts.n_items = h->ts.item_next + 1;
+        h->ts.items = P.alloc<unsigned>(N * tiles * 8);
+        const char* e_nsub = getenv("SMALFIT_RT_NSUB");         // tuning knobs for measurements
+        const char* e_split = getenv("SMALFIT_RT_SPLITLEN");
+        h->ts.nsub = e_nsub ? atoi(e_nsub) : 0;
+        { const char* e_fair = getenv("SMALFIT_RT_FAIR"); h->ts.fair = e_fair ? atoi(e_fair) : 0; }
+        h->ts.split_len = e_split ? atoi(e_split) : 0;
     }
     w.tile_off = P.alloc<unsigned>(N * (tiles + 1), true);
+    w.tile_cost = P.alloc<unsigned>(N * tiles, true);
     w.tile_order = P.alloc<unsigned short>(N * tiles, true);
     w.frame_next = P.alloc<unsigned>(2 * N + 1, true);
     w.frames_done = w.frame_next + N;
@@ -362,7 +371,7 @@ static int run_forward(smalfit_t h, const Params& p, int frame0, int n, Weights 
         if (h->use_tile) {
             h->mark(2, st);
             launch_raster_tile_forward(h->m, h->w, h->ts, frame0, n, wt, alpha_out, h->tile_ctas, st);
-            h->n_launches += 2;
+            h->n_launches += 3;
         } else {
             launch_ndc_soa(h->m, h->w, h->ndc_soa, frame0, n, st);
             h->mark(2, st);

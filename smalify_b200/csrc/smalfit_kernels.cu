@@ -252,12 +252,14 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
     const int T = w.tiles_x * w.tiles_y;
     unsigned* cnt = reinterpret_cast<unsigned*>(smem_raw);          // [BIN_WARPS][T] counts, then cursors
     unsigned* tot = cnt + BIN_WARPS * T;                                    // [T]
+    unsigned* cost = tot + T;                                               // [T] (pixel, face) pairs per tile
     __shared__ unsigned part[BIN_THREADS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int fr = frame0 + blockIdx.x;
     const float4* ndc = w.ndc + (size_t)fr * m.Vp;
     uint2* rects = w.face_rect + (size_t)fr * m.Fp;
     for (int i = tid; i < BIN_WARPS * T; i += BIN_THREADS) cnt[i] = 0u;
+    for (int i = tid; i < T; i += BIN_THREADS) cost[i] = 0u;
     __syncthreads();
     const int seg = ((m.Fp + BIN_WARPS - 1) / BIN_WARPS + 31) / 32 * 32;
     const int f_lo = min(wid * seg, m.Fp), f_hi = min(f_lo + seg, m.Fp);
@@ -269,7 +271,13 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
         if (face_pixel_rect(fs, w.S, c0, c1, r0, r1)) {
             rc = make_uint2((unsigned)c0 | ((unsigned)c1 << 16), (unsigned)r0 | ((unsigned)r1 << 16));
             for (int ty = r0 / TILE_H; ty <= r1 / TILE_H; ++ty)
-                for (int tx = c0 / TILE_W; tx <= c1 / TILE_W; ++tx) atomicAdd(&cnt[wid * T + ty * w.tiles_x + tx], 1u);
+                for (int tx = c0 / TILE_W; tx <= c1 / TILE_W; ++tx) {
+                    atomicAdd(&cnt[wid * T + ty * w.tiles_x + tx], 1u);
+                    // pixels of the rectangle inside the tile: the tile rasteriser's work estimate
+                    const int ax = min(c1, tx * TILE_W + TILE_W - 1) - max(c0, tx * TILE_W) + 1;
+                    const int ay = min(r1, ty * TILE_H + TILE_H - 1) - max(r0, ty * TILE_H) + 1;
+                    atomicAdd(&cost[ty * w.tiles_x + tx], (unsigned)(ax * ay));
+                }
         }
         rects[f] = rc;
         float4* fr4 = w.face_rec + ((size_t)fr * m.Fp + f) * 4;
@@ -279,6 +287,7 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
         fr4[3] = make_float4(fs.rl12, 0.f, __uint_as_float(rc.x), __uint_as_float(rc.y));
     }
     __syncthreads();
+    for (int t = tid; t < T; t += BIN_THREADS) w.tile_cost[(size_t)fr * T + t] = cost[t];
     // prefix over tiles (blocked: each thread owns a run of consecutive tiles)
     const int per = (T + BIN_THREADS - 1) / BIN_THREADS;
     unsigned local = 0;
@@ -379,7 +388,7 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
     if (dropped) atomicAdd(w.counters + 2, (unsigned long long)dropped);
 }
 
-size_t bin_smem_bytes(const Workspace& w) { return (size_t)(BIN_WARPS + 1) * w.tiles_x * w.tiles_y * sizeof(unsigned); }
+size_t bin_smem_bytes(const Workspace& w) { return (size_t)(BIN_WARPS + 2) * w.tiles_x * w.tiles_y * sizeof(unsigned); }
 
 void launch_bin_faces(const ModelDev& m, const Workspace& w_in, int frame0, int n, int n_sm, cudaStream_t st) {
     // Row-granular items cost ~10 % extra work on the tiles they apply to; they pay off only when there are
@@ -1421,7 +1430,7 @@ cudaError_t configure_kernels(const ModelDev& m) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(frame_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(bin_faces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (BIN_WARPS + 1) * MAX_TILES * (int)sizeof(unsigned));
+    e = cudaFuncSetAttribute(bin_faces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (BIN_WARPS + 2) * MAX_TILES * (int)sizeof(unsigned));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(raster_tile_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_tile_smem_bytes());
     if (e != cudaSuccess) return e;

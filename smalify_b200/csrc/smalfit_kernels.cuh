@@ -83,6 +83,7 @@ struct Workspace {
     float4* tile_rec;           // [N][pool_cap][4] the same entries as prepared faces for the tile rasteriser:
                                 //   (x0,y0,x1,y1) (x2,y2,z0,z1) (z2, 1/(area+eps), 1/|e01|^2, 1/|e02|^2) (1/|e12|^2, fid, rect, -)
     unsigned* tile_off;         // [N][tiles+1] offsets into the frame's pool
+    unsigned* tile_cost;        // [N][tiles] (pixel, face) pairs of the tile
     unsigned short* tile_order; // [N][tiles] tiles sorted by decreasing list length (hand-out order)
     int pool_cap;
     unsigned* frame_next;       // [N] next region to hand out   (followed by frames_done)
@@ -124,7 +125,12 @@ struct TileScratch {        // tile rasteriser: per resident CTA
     uint2* list;            // [n_ctas][list_cap + Fp] fragments (depth key, 1-p) of the pixels with more than K candidates
     int list_cap;           // entries one pass may use before the tile is split into further passes
     int list_stride;        // list_cap + Fp
-    unsigned* item_next;    // [1] next (frame, tile) item to hand out
+    unsigned* item_next;    // [1] next item to hand out
+    unsigned* n_items;      // [1]
+    unsigned* items;        // [N * tiles * 8] frame << 15 | tile << 5 | band << 2 | log2(bands)   (build_items_kernel)
+    int nsub;               // > 0: force this many bands for every list longer than split_len (measurements)
+    int fair;               // a band's list is at most 1/fair of a CTA's fair share of the launch (0: default 3)
+    int split_len;          // > 0: overrides the list length above which a tile is cut into bands
 };
 
 struct RasterScratch {      // per resident warp, [n_raster_warps][Fp] each

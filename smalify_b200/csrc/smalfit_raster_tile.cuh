@@ -36,6 +36,7 @@ constexpr int RT_SELCAP = 256;                  // keys of one pixel held in reg
 constexpr int RT_PIX = TILE_W * TILE_H;
 constexpr unsigned char RT_CLS_DIRECT = 0, RT_CLS_LISTED = 1, RT_CLS_IDLE = 2;
 constexpr int RT_MAXCHUNK = 512;                // tile lists up to 8192 faces are split by cost, longer ones evenly
+constexpr int RT_FAIR = 4;                      // a hand-out item holds at most 1/RT_FAIR of a CTA's fair share of the pairs
 constexpr unsigned RT_FACE_COST = 16u;          // per-face overhead of the sweep, in pair evaluations
 
 struct RtSmem {
@@ -202,8 +203,13 @@ __device__ float rt_select(const uint2* __restrict__ L, int c, int lane, unsigne
 // SKIPS: some pixels of the tile are not handled in this pass (multi-pass tiles only).
 template <bool SKIPS>
 __device__ __forceinline__ void rt_sweep_face(const float4* __restrict__ rec, unsigned* __restrict__ plane, uint2* __restrict__ list,
-                                              int lane, int x0, int y0, float inv_s) {
-    const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3];
+                                              int lane, int x0, int y0, float inv_s, int b0, int b1) {
+    const float4 q3 = rec[3];
+    const unsigned rect = __float_as_uint(q3.z);
+    const int c0 = (int)(rect & 0xffu), c1 = (int)((rect >> 8) & 0xffu);
+    const int r0 = max((int)((rect >> 16) & 0xffu), b0), r1 = min((int)(rect >> 24), b1 - 1);     // rows of this item only
+    if (r0 > r1) return;
+    const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2];
     FaceSetup fs;
     fs.x0 = q0.x; fs.y0 = q0.y; fs.x1 = q0.z; fs.y1 = q0.w; fs.x2 = q1.x; fs.y2 = q1.y;
     fs.z0 = q1.z; fs.z1 = q1.w; fs.z2 = q2.x; fs.rden = q2.y;
@@ -211,8 +217,6 @@ __device__ __forceinline__ void rt_sweep_face(const float4* __restrict__ rec, un
     fs.e01x = fsub(fs.x1, fs.x0); fs.e01y = fsub(fs.y1, fs.y0);
     fs.e02x = fsub(fs.x2, fs.x0); fs.e02y = fsub(fs.y2, fs.y0);
     fs.e12x = fsub(fs.x2, fs.x1); fs.e12y = fsub(fs.y2, fs.y1);
-    const unsigned rect = __float_as_uint(q3.z);
-    const int c0 = (int)(rect & 0xffu), c1 = (int)((rect >> 8) & 0xffu), r0 = (int)((rect >> 16) & 0xffu), r1 = (int)(rect >> 24);
     const int wd = c1 - c0 + 1, npx = wd * (r1 - r0 + 1);
     float inv_w;      // MUFU reciprocal: (i + 0.5) / wd is at least 0.5 / 32 away from an integer
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_w) : "f"((float)wd));
@@ -253,10 +257,12 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
         if (threadIdx.x == 0) sm.item = (int)atomicAdd(ts.item_next, 1u);
         __syncthreads();
         const unsigned item = (unsigned)sm.item;
+        if (item >= *ts.n_items) break;
+        // item = one tile of one frame, or one band of rows of a tile with a long list (build_items)
+        const unsigned code = ts.items[item];
+        const int f = (int)(code >> 15), fr = frame0 + f, tile = (int)((code >> 5) & 0x3ffu);
         const int T = w.tiles_x * w.tiles_y;
-        if (item >= (unsigned)n_frames * (unsigned)T) break;
-        const int f = (int)(item % (unsigned)n_frames), fr = frame0 + f;
-        const int tile = (int)w.tile_order[(size_t)fr * T + (int)(item / (unsigned)n_frames)];
+        const int bh = TILE_H >> (code & 3u), b0 = (int)((code >> 2) & 7u) * bh, b1 = b0 + bh;
         const unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
         const unsigned off = min(toff[tile], (unsigned)w.pool_cap);
         const int len = (int)(min(toff[tile + 1], (unsigned)w.pool_cap) - off);
@@ -286,7 +292,8 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                 unsigned cost = 0u;
                 if (e < len) {
                     const unsigned rect = pool[e].z;
-                    cost = (((rect >> 8) & 0xffu) - (rect & 0xffu) + 1u) * ((rect >> 24) - ((rect >> 16) & 0xffu) + 1u) + RT_FACE_COST;
+                    const int rows = min((int)(rect >> 24), b1 - 1) - max((int)((rect >> 16) & 0xffu), b0) + 1;
+                    cost = (((rect >> 8) & 0xffu) - (rect & 0xffu) + 1u) * (unsigned)max(rows, 0) + RT_FACE_COST;
                 }
 #pragma unroll
                 for (int o = RT_BLK / 2; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
@@ -327,7 +334,9 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
             __syncwarp();
             for (int e = lo + lane; e < hi; e += 32) {
                 const unsigned rect = pool[e].z;
-                const int c0 = (int)(rect & 0xffu), c1 = (int)((rect >> 8) & 0xffu), r0 = (int)((rect >> 16) & 0xffu), r1 = (int)(rect >> 24);
+                const int c0 = (int)(rect & 0xffu), c1 = (int)((rect >> 8) & 0xffu);
+                const int r0 = max((int)((rect >> 16) & 0xffu), b0), r1 = min((int)(rect >> 24), b1 - 1);
+                if (r0 > r1) continue;
                 atomicAdd(&plane[r0 * RT_PITCH + c0], 1u);
                 atomicAdd(&plane[r0 * RT_PITCH + c1 + 1], 0xffffffffu);
                 atomicAdd(&plane[(r1 + 1) * RT_PITCH + c0], 0xffffffffu);
@@ -433,8 +442,8 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                     phase ^= 1u << (b & 1);
                     const int nrec = min(RT_BLK, hi - e0);
                     const float4* st = sm.stage[wid][b & 1];
-                    if (skips) { for (int j = 0; j < nrec; ++j) rt_sweep_face<true>(st + j * 4, plane, list, lane, x0, y0, inv_s); }
-                    else       { for (int j = 0; j < nrec; ++j) rt_sweep_face<false>(st + j * 4, plane, list, lane, x0, y0, inv_s); }
+                    if (skips) { for (int j = 0; j < nrec; ++j) rt_sweep_face<true>(st + j * 4, plane, list, lane, x0, y0, inv_s, b0, b1); }
+                    else       { for (int j = 0; j < nrec; ++j) rt_sweep_face<false>(st + j * 4, plane, list, lane, x0, y0, inv_s, b0, b1); }
                 }
             }
             __syncthreads();
@@ -475,7 +484,7 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                     const int row = wid + RT_WARPS * k;
                     const int idx = row * RT_PITCH + lane, px = row * TILE_W + lane;
                     const unsigned cls = sm.cls[px];
-                    if (cls == RT_CLS_IDLE) continue;
+                    if (cls == RT_CLS_IDLE || row < b0 || row >= b1) continue;
                     float P;
                     unsigned tk = 0xffffffffu, tf = 0xffffu;
                     if (cls == RT_CLS_LISTED) {
@@ -514,7 +523,8 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
             const int lx0 = (sub % (TILE_W / REGION_W)) * REGION_W, ly0 = (sub / (TILE_W / REGION_W)) * REGION_H;
             const float* p = sm.l1 + (ly0 + row) * TILE_W + lx0;
             const size_t slot0 = ((size_t)(frame0 + sm.t_f) * (w.tiles_x * w.tiles_y) + (size_t)sm.t_tile) * (REGIONS_PER_TILE * REGION_H);
-            w.region_l1[slot0 + threadIdx.x] = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+            if (ly0 >= b0 && ly0 < b1)       // region rows of this item's band
+                w.region_l1[slot0 + threadIdx.x] = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
         }
     }
     __syncthreads();
@@ -526,11 +536,65 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
 
 size_t raster_tile_smem_bytes() { return sizeof(RtSmem); }
 
+// Hand-out list of the tile rasteriser: every (frame, tile) becomes 1, 2, 4 or 8 items (bands of rows) so that no
+// item holds more than about 1/fair of a CTA's fair share of the launch's (pixel, face) pairs (bin_faces counts them
+// per tile), ordered by decreasing pairs per item (counting sort into 256 classes; the order inside a class does not
+// matter: items are independent).  Also resets the hand-out counter.  One CTA.
+constexpr int RT_ITEM_CLASSES = 256;
+__global__ void __launch_bounds__(1024) build_items_kernel(Workspace w, TileScratch ts, int frame0, int n_frames, int n_ctas) {
+    __shared__ unsigned hist[RT_ITEM_CLASSES];
+    __shared__ unsigned long long red[32];
+    __shared__ unsigned s_cmax;
+    const int tid = threadIdx.x, T = w.tiles_x * w.tiles_y, NT = n_frames * T;
+    const unsigned* tcost = w.tile_cost + (size_t)frame0 * T;
+    for (int i = tid; i < RT_ITEM_CLASSES; i += blockDim.x) hist[i] = 0u;
+    unsigned long long tot = 0ull;
+    for (int i = tid; i < NT; i += blockDim.x) tot += tcost[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if ((tid & 31) == 0) red[tid >> 5] = tot;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long a = 0ull;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += red[i];
+        const unsigned long long cmax = a / (unsigned long long)((ts.fair > 0 ? ts.fair : RT_FAIR) * n_ctas);
+        s_cmax = ts.split_len > 0 ? (unsigned)ts.split_len : (unsigned)(cmax < 4096ull ? 4096ull : cmax);
+    }
+    __syncthreads();
+    const unsigned cmax = s_cmax;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = tid; i < NT; i += blockDim.x) {
+            const unsigned cost = tcost[i];
+            unsigned lg = 0u;                                   // bands: 1 << lg
+            while (lg < 3u && ((cost >> lg) > cmax || (cost >> lg) > (unsigned)ts.list_cap)) ++lg;     // (and keep the lists in one pass)
+            if (ts.nsub > 0) { lg = 0u; while ((1 << lg) < ts.nsub) ++lg; if (cost <= cmax) lg = 0u; }      // forced (measurements)
+            const unsigned long long per = cost >> lg;
+            const unsigned cls = (RT_ITEM_CLASSES - 1) - (unsigned)min(per * 128ull / cmax, (unsigned long long)(RT_ITEM_CLASSES - 1));   // big items first
+            if (pass == 0) {
+                atomicAdd(&hist[cls], 1u << lg);
+            } else {
+                const unsigned pos = atomicAdd(&hist[cls], 1u << lg);
+                for (unsigned b = 0; b < (1u << lg); ++b) ts.items[pos + b] = ((unsigned)(i / T) << 15) | ((unsigned)(i % T) << 5) | (b << 2) | lg;
+            }
+        }
+        __syncthreads();
+        if (pass == 0) {
+            if (tid == 0) {
+                unsigned run = 0u;
+                for (int c = 0; c < RT_ITEM_CLASSES; ++c) { const unsigned v = hist[c]; hist[c] = run; run += v; }
+                *ts.n_items = run;
+                *ts.item_next = 0u;
+            }
+            __syncthreads();
+        }
+    }
+}
+
 void launch_raster_tile_forward(const ModelDev& m, const Workspace& w, const TileScratch& ts, int frame0, int n, Weights wt,
                                 float* alpha_out, int n_ctas, cudaStream_t st) {
-    cudaMemsetAsync(ts.item_next, 0, sizeof(unsigned), st);
-    const long long items = (long long)n * w.tiles_x * w.tiles_y;
-    const int grid = (int)(items < n_ctas ? items : n_ctas);
+    build_items_kernel<<<1, 1024, 0, st>>>(w, ts, frame0, n, n_ctas);
+    const long long tiles = (long long)n * w.tiles_x * w.tiles_y;
+    const int grid = (int)(tiles < n_ctas ? tiles : n_ctas);
     raster_tile_forward_kernel<<<grid, RT_THREADS, raster_tile_smem_bytes(), st>>>(m, w, ts, frame0, n, wt, alpha_out);
 }
 
