@@ -201,6 +201,12 @@ SMALFIT_API int smalfit_get_profile(smalfit_t h, float ms[8]);
  * counters[3] = kernel launches since create.  counters[0..2] are reset by the call. */
 SMALFIT_API int smalfit_counters(smalfit_t h, int64_t counters[4], void* stream);
 
+/* Diagnostics (synchronises): work of the last rasterised pass over frames [frame0, frame0 + n).
+ * counts[0] = (pixel, face) pairs that passed the bounding-box test (what PyTorch3D's fine rasteriser
+ *             evaluates after its coarse pass; each is evaluated once in the forward and once in the backward)
+ * counts[1] = (face, 32x32 tile) entries binned. */
+SMALFIT_API int smalfit_work_counts(smalfit_t h, int frame0, int n, int64_t counts[2], void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "smalfit_set_profiling": ([vp, C.c_int], C.c_int),
         "smalfit_get_profile": ([vp, _f32p], C.c_int),
         "smalfit_counters": ([vp, C.POINTER(C.c_int64), vp], C.c_int),
+        "smalfit_work_counts": ([vp, C.c_int, C.c_int, C.POINTER(C.c_int64), vp], C.c_int),
     }
     for name, (args, res) in protos.items():
         fn = getattr(lib, name)          # AttributeError here = symbol missing from the .so
@@ -102,7 +103,7 @@ EXPORTED_SYMBOLS = (
     "smalfit_abi_version", "smalfit_create", "smalfit_destroy", "smalfit_last_error", "smalfit_set_targets",
     "smalfit_set_visibility", "smalfit_set_masks", "smalfit_set_windows", "smalfit_set_per_frame_shapes",
     "smalfit_loss_grad", "smalfit_temporal", "smalfit_adam_step", "smalfit_adam_reset", "smalfit_render", "smalfit_vertices",
-    "smalfit_counters", "smalfit_set_profiling", "smalfit_get_profile",
+    "smalfit_counters", "smalfit_work_counts", "smalfit_set_profiling", "smalfit_get_profile",
 )
 
 

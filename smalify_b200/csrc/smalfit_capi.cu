@@ -230,7 +230,8 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
         h->tile_ctas = h->n_sm * RT_CTAS_PER_SM;
         h->ts.list_cap = 192 * 1024;        // 1.5 MB per CTA: a 32x32 tile with ~190 candidates on every pixel in one pass
         { const char* e_cap = getenv("SMALFIT_RT_LISTCAP"); if (e_cap && atoi(e_cap) > 0) h->ts.list_cap = atoi(e_cap); }    // tests force multi-pass tiles
-        h->ts.list_stride = h->ts.list_cap + m.Fp;
+        h->ts.list_cap = (h->ts.list_cap + 15) / 16 * 16;            // lists start on 128-byte lines
+        h->ts.list_stride = h->ts.list_cap + (m.Fp + 15) / 16 * 16 + 16;
         h->ts.list = P.alloc<uint2>((size_t)h->tile_ctas * h->ts.list_stride);
         h->ts.item_next = P.alloc<unsigned>(2, true);
         h->ts.n_items = h->ts.item_next + 1;
@@ -503,6 +504,23 @@ int smalfit_get_profile(smalfit_t h, float ms[8]) {
     e = cudaEventElapsedTime(&ms[6], h->ev[0], h->ev[6]);
     ms[7] = 0.f;
     return check_cuda(h, e, "cudaEventElapsedTime");
+}
+
+int smalfit_work_counts(smalfit_t h, int frame0, int n, int64_t counts[2], void* stream) {
+    if (!h || !counts) return SMALFIT_EINVAL;
+    if (!range_ok(h, frame0, n)) return fail(h, SMALFIT_EINVAL, "smalfit_work_counts: bad frame range");
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t tiles = (size_t)h->w.tiles_x * h->w.tiles_y;
+    std::vector<unsigned> cost((size_t)n * tiles), off((size_t)n * (tiles + 1));
+    cudaError_t e = cudaMemcpyAsync(cost.data(), h->w.tile_cost + (size_t)frame0 * tiles, cost.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(off.data(), h->w.tile_off + (size_t)frame0 * (tiles + 1), off.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return check_cuda(h, e, "smalfit_work_counts");
+    counts[0] = counts[1] = 0;
+    for (unsigned c : cost) counts[0] += c;
+    for (int f = 0; f < n; ++f) counts[1] += off[(size_t)f * (tiles + 1) + tiles];
+    return SMALFIT_OK;
 }
 
 int smalfit_counters(smalfit_t h, int64_t counters[4], void* stream) {

@@ -349,6 +349,14 @@ class SMALFitter(nn.Module):
         h.check(h.lib.smalfit_counters(h.h, arr, _stream(self.device)), "smalfit_counters")
         return dict(capped_pixels=arr[0], spilled_pixels=arr[1], dropped_bin_entries=arr[2], launches=arr[3])
 
+    def work_counts(self, frame0=0, n=None):
+        """(pixel, face) pairs and (face, tile) entries of the last rasterised pass (diagnostic, synchronises)."""
+        arr = (ctypes.c_int64 * 2)()
+        h = self._handle
+        n = self.num_images - frame0 if n is None else n
+        h.check(h.lib.smalfit_work_counts(h.h, frame0, n, arr, _stream(self.device)), "smalfit_work_counts")
+        return dict(pairs=arr[0], tile_entries=arr[1])
+
     # ------------------------------------------------------------------
     def export_parameters(self, frame_id):
         """The per-frame dict ImageExporter pickles (smal_fitter.py:213-219,268)."""
