@@ -48,14 +48,11 @@ struct DevPool {                 // every allocation of a handle, freed together
 struct smalfit_ctx {
     int device = 0;
     int N = 0, S = 0;
-    int n_sm = 0, raster_ctas = 0;
+    int n_sm = 0;
     ModelDev m{};
     Workspace w{};
-    RasterScratch sc{};
     TileScratch ts{};
     int tile_ctas = 0;
-    bool use_tile = true;       // SMALFIT_RASTER=v4 selects the region rasteriser (kept for A/B measurements)
-    float* ndc_soa = nullptr;
     AdamState* adam_state = nullptr;
     // mutable target buffers (Workspace holds const views)
     uint8_t* sil = nullptr; float* kp_target = nullptr; uint8_t* vis = nullptr;
@@ -128,7 +125,6 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
 
     smalfit_ctx* h = new smalfit_ctx();
     h->device = device; h->N = max_frames; h->S = image_size; h->n_sm = prop.multiProcessorCount;
-    h->raster_ctas = RAST_CTAS_PER_SM * h->n_sm;
     const int V = md->n_verts, F = md->n_faces;
     ModelDev& m = h->m;
     m.V = V; m.F = F; m.Fp = (F + 31) / 32 * 32; m.Vp = (V + 3) / 4 * 4;
@@ -208,7 +204,6 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     const int n_blocks = (V * 3 + 255) / 256;
     w.v_shaped = P.alloc<float>(N * V * 3);          // sized for per-frame shapes too
     w.ndc = P.alloc<float4>(N * m.Vp);
-    h->ndc_soa = P.alloc<float>(N * 3 * m.Vp);
     w.gjoint = P.alloc<float>(N * NMJ * 3, true);
     w.kp_proj = P.alloc<float>(N * NKP * 2, true);
     w.face_rect = P.alloc<uint2>(N * m.Fp);
@@ -221,12 +216,8 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
         w.pool_cap = mult * m.Fp;
     }
     w.tile_pool = P.alloc<uint4>(N * (size_t)w.pool_cap);
+    w.tile_rec = P.alloc<float4>(N * (size_t)w.pool_cap * 4);
     {
-        const char* sel = getenv("SMALFIT_RASTER");
-        h->use_tile = !(sel && strcmp(sel, "v4") == 0);
-    }
-    w.tile_rec = h->use_tile ? P.alloc<float4>(N * (size_t)w.pool_cap * 4) : nullptr;
-    if (h->use_tile) {
         h->tile_ctas = h->n_sm * RT_CTAS_PER_SM;
         h->ts.list_cap = 192 * 1024;        // 1.5 MB per CTA: a 32x32 tile with ~190 candidates on every pixel in one pass
         { const char* e_cap = getenv("SMALFIT_RT_LISTCAP"); if (e_cap && atoi(e_cap) > 0) h->ts.list_cap = atoi(e_cap); }    // tests force multi-pass tiles
@@ -244,13 +235,8 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     }
     w.tile_off = P.alloc<unsigned>(N * (tiles + 1), true);
     w.tile_cost = P.alloc<unsigned>(N * tiles, true);
-    w.tile_order = P.alloc<unsigned short>(N * tiles, true);
-    w.frame_next = P.alloc<unsigned>(2 * N + 1, true);
-    w.frames_done = w.frame_next + N;
-    w.frame_active = w.frame_next + N + 1;
-    w.frame_busy = P.alloc<unsigned>(N, true);
-    w.frame_heavy = P.alloc<unsigned>(N, true);
-    w.frame_items = P.alloc<unsigned>(N, true);
+    w.bin_cnt = P.alloc<unsigned>(N * BIN_WARPS * tiles, true);
+    w.bin_cost = P.alloc<unsigned>(N * BIN_PARTS * tiles, true);
     w.pix = P.alloc<uint2>(N * SS, true);
     w.pix_tfid = P.alloc<uint16_t>(N * SS, true);
     w.region_l1 = P.alloc<float>(N * tiles * REGIONS_PER_TILE * REGION_H, true);
@@ -271,13 +257,6 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     h->rmask = P.upload(ones.data(), (NJ - 1) * 3);
     w.sil = h->sil; w.kp_target = h->kp_target; w.vis = h->vis; w.region_tsum = h->region_tsum;
     w.inv_window = h->inv_window; w.gmask = h->gmask; w.rmask = h->rmask;
-    const size_t n_warps = (size_t)h->raster_ctas * RAST_WARPS;
-    h->sc.ent = P.alloc<uint2>(n_warps * m.Fp);
-    h->sc.mask = P.alloc<unsigned>(n_warps * m.Fp);
-    h->sc.plist = P.alloc<unsigned short>(n_warps * m.Fp);
-    h->sc.key = P.alloc<unsigned>(n_warps * m.Fp);
-    h->sc.m = P.alloc<float>(n_warps * m.Fp);
-    h->sc.fid = P.alloc<unsigned short>(n_warps * m.Fp);
     h->adam_state = P.alloc<AdamState>(1, true);
     w.temporal_partial = P.alloc<float>(((size_t)N * 108 + 255) / 256 * 3 + 3, true);
     w.temporal_ticket = P.alloc<unsigned>(1, true);
@@ -368,17 +347,10 @@ static int run_forward(smalfit_t h, const Params& p, int frame0, int n, Weights 
     h->n_launches += 2;
     h->mark(1, st);
     if (raster) {
-        launch_bin_faces(h->m, h->w, frame0, n, h->n_sm, st);
-        if (h->use_tile) {
-            h->mark(2, st);
-            launch_raster_tile_forward(h->m, h->w, h->ts, frame0, n, wt, alpha_out, h->tile_ctas, st);
-            h->n_launches += 3;
-        } else {
-            launch_ndc_soa(h->m, h->w, h->ndc_soa, frame0, n, st);
-            h->mark(2, st);
-            launch_raster_forward(h->m, h->w, h->sc, h->ndc_soa, frame0, n, wt, alpha_out, h->raster_ctas, st);
-            h->n_launches += 3;
-        }
+        launch_bin_faces(h->m, h->w, frame0, n, st);
+        h->mark(2, st);
+        launch_raster_tile_forward(h->m, h->w, h->ts, frame0, n, wt, alpha_out, h->tile_ctas, st);
+        h->n_launches += 5;
     } else {
         h->mark(2, st);
     }

@@ -7,8 +7,8 @@
 //   frame_forward      per frame: rest joints, Rodrigues, kinematic chain, sparse LBS,
 //                      camera, 41 model joints, keypoint projection + loss     (smal_torch.py:125-184,
 //                      and dL/d(joints)                                         smal_fitter.py:129-144)
-//   face_rects         per face: validity + conservative pixel rectangle
-//   raster_forward     soft silhouette (PyTorch3D 0.2.5 semantics, exact K=100 nearest-z
+//   bin_faces          per face: prepared form + conservative pixel rectangle, binned into 32x32 tiles
+//   raster_tile_fwd    soft silhouette (PyTorch3D 0.2.5 semantics, exact K=100 nearest-z
 //                      rule) fused with the L1 silhouette loss                 (p3d_renderer.py:26-39,66;
 //                      writes per pixel (coef, z-threshold) for the backward    smal_fitter.py:172-173)
 //   raster_backward    face-parallel analytic backward -> per-face xy gradients (RasterizeMeshesBackward)
@@ -233,12 +233,15 @@ void launch_frame_forward(const ModelDev& m, const Workspace& w, const Params& p
 }
 
 // ---------------------------------------------------------------------------
-// bin_faces: one CTA per frame.  Every face gets its conservative pixel rectangle; faces are
-// binned into the 32x32-pixel tiles they touch.  Deterministic (no global atomics): each warp
-// owns a contiguous range of faces, pass 1 counts per (warp, tile), a prefix turns the counts
-// into cursors, pass 2 fills in face order (lanes that hit the same tile in the same step are
-// ranked with match_any).  Pool entry (16 B): face id + its three vertex ids + the rectangle in
-// tile-local pixel coordinates, so the rasteriser needs no further gathers to build its lists.
+// bin_faces: every face gets its prepared form (face_setup) and its conservative pixel rectangle; faces are
+// binned into the 32x32-pixel tiles they touch.  Deterministic (no global atomics): the faces of a frame are
+// cut into BIN_WARPS contiguous segments, one per warp, spread over BIN_PARTS CTAs;
+//   bin_count  counts per (segment, tile), writes the per-face records and rectangles,
+//   bin_scan   (one CTA per frame) turns the counts into tile offsets and per-(segment, tile) cursors,
+//   bin_fill   fills in face order within a segment (lanes that hit the same tile in the same step are
+//              ranked with match_any), so every tile list is in ascending face order.
+// Pool entry (16 B): face id + its three vertex ids + the rectangle in tile-local pixel coordinates;
+// tile_rec (64 B): the prepared face for the tile rasteriser's TMA stage.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ FaceSetup load_face(const float4* ndc, ushort4 f4) {
     const float4 a = ndc[f4.x], b = ndc[f4.y], c = ndc[f4.z];
@@ -247,23 +250,25 @@ __device__ __forceinline__ FaceSetup load_face(const float4* ndc, ushort4 f4) {
     return fs;
 }
 
-__global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Workspace w, int frame0) {
+__device__ __forceinline__ void bin_segment(const ModelDev& m, int seg_id, int& f_lo, int& f_hi) {
+    const int seg = ((m.Fp + BIN_WARPS - 1) / BIN_WARPS + 31) / 32 * 32;
+    f_lo = min(seg_id * seg, m.Fp);
+    f_hi = min(f_lo + seg, m.Fp);
+}
+
+__global__ void __launch_bounds__(BIN_PART_THREADS) bin_count_kernel(ModelDev m, Workspace w, int frame0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = w.tiles_x * w.tiles_y;
-    unsigned* cnt = reinterpret_cast<unsigned*>(smem_raw);          // [BIN_WARPS][T] counts, then cursors
-    unsigned* tot = cnt + BIN_WARPS * T;                                    // [T]
-    unsigned* cost = tot + T;                                               // [T] (pixel, face) pairs per tile
-    __shared__ unsigned part[BIN_THREADS];
+    unsigned* cnt = reinterpret_cast<unsigned*>(smem_raw);          // [BIN_PART_WARPS][T]
+    unsigned* cost = cnt + BIN_PART_WARPS * T;                      // [T] (pixel, face) pairs per tile, this CTA's faces
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int fr = frame0 + blockIdx.x;
+    const int fr = frame0 + blockIdx.y, seg_id = blockIdx.x * BIN_PART_WARPS + wid;
     const float4* ndc = w.ndc + (size_t)fr * m.Vp;
     uint2* rects = w.face_rect + (size_t)fr * m.Fp;
-    for (int i = tid; i < BIN_WARPS * T; i += BIN_THREADS) cnt[i] = 0u;
-    for (int i = tid; i < T; i += BIN_THREADS) cost[i] = 0u;
+    for (int i = tid; i < (BIN_PART_WARPS + 1) * T; i += BIN_PART_THREADS) cnt[i] = 0u;
     __syncthreads();
-    const int seg = ((m.Fp + BIN_WARPS - 1) / BIN_WARPS + 31) / 32 * 32;
-    const int f_lo = min(wid * seg, m.Fp), f_hi = min(f_lo + seg, m.Fp);
-    // pass 1: rectangles + counts
+    int f_lo, f_hi;
+    bin_segment(m, seg_id, f_lo, f_hi);
     for (int f = f_lo + lane; f < f_hi; f += 32) {
         const FaceSetup fs = load_face(ndc, m.faces4[f]);
         int c0, c1, r0, r1;
@@ -287,24 +292,37 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
         fr4[3] = make_float4(fs.rl12, 0.f, __uint_as_float(rc.x), __uint_as_float(rc.y));
     }
     __syncthreads();
-    for (int t = tid; t < T; t += BIN_THREADS) w.tile_cost[(size_t)fr * T + t] = cost[t];
-    // prefix over tiles (blocked: each thread owns a run of consecutive tiles)
-    const int per = (T + BIN_THREADS - 1) / BIN_THREADS;
-    unsigned local = 0;
+    unsigned* gcnt = w.bin_cnt + ((size_t)fr * BIN_WARPS + (size_t)blockIdx.x * BIN_PART_WARPS) * T;
+    for (int i = tid; i < BIN_PART_WARPS * T; i += BIN_PART_THREADS) gcnt[i] = cnt[i];
+    unsigned* gcost = w.bin_cost + ((size_t)fr * BIN_PARTS + blockIdx.x) * T;
+    for (int i = tid; i < T; i += BIN_PART_THREADS) gcost[i] = cost[i];
+}
+
+__global__ void __launch_bounds__(256) bin_scan_kernel(Workspace w, int frame0) {
+    __shared__ unsigned part[256];
+    const int T = w.tiles_x * w.tiles_y, tid = threadIdx.x;
+    const int fr = frame0 + blockIdx.x;
+    unsigned* gcnt = w.bin_cnt + (size_t)fr * BIN_WARPS * T;
+    const unsigned* gcost = w.bin_cost + (size_t)fr * BIN_PARTS * T;
+    // blocked prefix over tiles: each thread owns a run of consecutive tiles
+    const int per = (T + 255) / 256;
+    unsigned local = 0u;
     for (int k = 0; k < per; ++k) {
         const int t = tid * per + k;
         if (t < T) {
-            unsigned a = 0;
-            for (int q = 0; q < BIN_WARPS; ++q) a += cnt[q * T + t];
-            tot[t] = a;
+            unsigned a = 0u;
+            for (int q = 0; q < BIN_WARPS; ++q) a += gcnt[q * T + t];
             local += a;
+            unsigned c = 0u;
+            for (int q = 0; q < BIN_PARTS; ++q) c += gcost[q * T + t];
+            w.tile_cost[(size_t)fr * T + t] = c;
         }
     }
     part[tid] = local;
     __syncthreads();
     if (tid == 0) {
-        unsigned run = 0;
-        for (int i = 0; i < BIN_THREADS; ++i) { const unsigned v = part[i]; part[i] = run; run += v; }
+        unsigned run = 0u;
+        for (int i = 0; i < 256; ++i) { const unsigned v = part[i]; part[i] = run; run += v; }
     }
     __syncthreads();
     unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
@@ -313,34 +331,27 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
         const int t = tid * per + k;
         if (t < T) {
             toff[t] = run;
-            unsigned r2 = run;
-            for (int q = 0; q < BIN_WARPS; ++q) { const unsigned c = cnt[q * T + t]; cnt[q * T + t] = r2; r2 += c; }
-            run += tot[t];
+            for (int q = 0; q < BIN_WARPS; ++q) { const unsigned c = gcnt[q * T + t]; gcnt[q * T + t] = run; run += c; }   // counts -> cursors
             if (t == T - 1) toff[T] = run;
         }
     }
-    if (tid == 0) {
-        // tiles with long lists are handed out as single pixel rows (4 items per region), the rest as
-        // whole 8x4 regions: bounds the longest single-warp task
-        unsigned busy = 0, heavy = 0;
-        for (int t = 0; t < T; ++t) { busy += (tot[t] > 0u) ? 1u : 0u; heavy += (tot[t] >= (unsigned)w.heavy_len) ? 1u : 0u; }
-        w.frame_heavy[fr] = heavy;
-        w.frame_items[fr] = heavy * (REGIONS_PER_TILE * REGION_H) + ((unsigned)T - heavy) * REGIONS_PER_TILE;
-        w.frame_busy[fr] = heavy * (REGIONS_PER_TILE * REGION_H) + (busy - heavy) * REGIONS_PER_TILE;
-    }
-    // hand-out order of the tiles: longest list first, so a frame's last regions are the cheap ones
-    unsigned short* order = w.tile_order + (size_t)fr * T;
-    for (int t = tid; t < T; t += BIN_THREADS) {
-        const unsigned c = tot[t];
-        int rank = 0;
-        for (int u = 0; u < T; ++u) { const unsigned cu = tot[u]; rank += (cu > c || (cu == c && u < t)) ? 1 : 0; }
-        order[rank] = (unsigned short)t;
-    }
+}
+
+__global__ void __launch_bounds__(BIN_PART_THREADS) bin_fill_kernel(ModelDev m, Workspace w, int frame0) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = w.tiles_x * w.tiles_y;
+    unsigned* cur = reinterpret_cast<unsigned*>(smem_raw);          // [BIN_PART_WARPS][T] write cursors
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int fr = frame0 + blockIdx.y, seg_id = blockIdx.x * BIN_PART_WARPS + wid;
+    const uint2* rects = w.face_rect + (size_t)fr * m.Fp;
+    const unsigned* gcur = w.bin_cnt + ((size_t)fr * BIN_WARPS + (size_t)blockIdx.x * BIN_PART_WARPS) * T;
+    for (int i = tid; i < BIN_PART_WARPS * T; i += BIN_PART_THREADS) cur[i] = gcur[i];
     __syncthreads();
-    // pass 2: fill, in face order within a warp
+    int f_lo, f_hi;
+    bin_segment(m, seg_id, f_lo, f_hi);
     const unsigned ltmask = lanemask_lt();
     uint4* pool = w.tile_pool + (size_t)fr * w.pool_cap;
-    float4* recs = w.tile_rec ? w.tile_rec + (size_t)fr * w.pool_cap * 4 : nullptr;
+    float4* recs = w.tile_rec + (size_t)fr * w.pool_cap * 4;
     unsigned dropped = 0;
     for (int base = f_lo; base < f_hi; base += 32) {
         const int f = base + lane;
@@ -352,17 +363,21 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
         const int nt = ok ? ntw * (r1 / TILE_H - tr0 + 1) : 0;
         const int maxnt = __reduce_max_sync(0xffffffffu, nt);
         const ushort4 f4 = m.faces4[f];
-        FaceSetup fs = face_setup(0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
-        if (nt > 0 && recs) fs = load_face(ndc, f4);
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
+        float rl12 = 0.f;
+        if (nt > 0) {        // the prepared face bin_count wrote
+            const float4* fr4 = w.face_rec + ((size_t)fr * m.Fp + f) * 4;
+            q0 = fr4[0]; q1 = fr4[1]; q2 = fr4[2]; rl12 = fr4[3].x;
+        }
         for (int k = 0; k < maxnt; ++k) {
             int t = -1, tx = 0, ty = 0;
             if (k < nt) { ty = tr0 + k / ntw; tx = tc0 + k % ntw; t = ty * w.tiles_x + tx; }
             const unsigned mm = __match_any_sync(0xffffffffu, t);
             unsigned basepos = 0;
             const int rank = __popc(mm & ltmask);
-            if (t >= 0) basepos = cnt[wid * T + t];
+            if (t >= 0) basepos = cur[wid * T + t];
             __syncwarp();
-            if (t >= 0 && rank == 0) cnt[wid * T + t] = basepos + (unsigned)__popc(mm);
+            if (t >= 0 && rank == 0) cur[wid * T + t] = basepos + (unsigned)__popc(mm);
             __syncwarp();
             if (t >= 0) {
                 const unsigned pos = basepos + (unsigned)rank;
@@ -372,13 +387,9 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
                     const unsigned lr0 = (unsigned)max(r0 - y0, 0), lr1 = (unsigned)min(r1 - y0, TILE_H - 1);
                     const unsigned rect = lc0 | (lc1 << 8) | (lr0 << 16) | (lr1 << 24);
                     pool[pos] = make_uint4((unsigned)f | ((unsigned)f4.x << 16), (unsigned)f4.y | ((unsigned)f4.z << 16), rect, 0u);
-                    if (recs) {
-                        float4* r = recs + (size_t)pos * 4;
-                        r[0] = make_float4(fs.x0, fs.y0, fs.x1, fs.y1);
-                        r[1] = make_float4(fs.x2, fs.y2, fs.z0, fs.z1);
-                        r[2] = make_float4(fs.z2, fs.rden, fs.rl01, fs.rl02);
-                        r[3] = make_float4(fs.rl12, __uint_as_float((unsigned)f), __uint_as_float(rect), 0.f);
-                    }
+                    float4* rr = recs + (size_t)pos * 4;
+                    rr[0] = q0; rr[1] = q1; rr[2] = q2;
+                    rr[3] = make_float4(rl12, __uint_as_float((unsigned)f), __uint_as_float(rect), 0.f);
                 } else {
                     ++dropped;
                 }
@@ -388,14 +399,13 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_faces_kernel(ModelDev m, Work
     if (dropped) atomicAdd(w.counters + 2, (unsigned long long)dropped);
 }
 
-size_t bin_smem_bytes(const Workspace& w) { return (size_t)(BIN_WARPS + 2) * w.tiles_x * w.tiles_y * sizeof(unsigned); }
+size_t bin_smem_bytes(const Workspace& w) { return (size_t)(BIN_PART_WARPS + 1) * w.tiles_x * w.tiles_y * sizeof(unsigned); }
 
-void launch_bin_faces(const ModelDev& m, const Workspace& w_in, int frame0, int n, int n_sm, cudaStream_t st) {
-    // Row-granular items cost ~10 % extra work on the tiles they apply to; they pay off only when there are
-    // too few frames per GPU for the longest single-warp task to hide behind other work (sharded runs).
-    Workspace w = w_in;
-    w.heavy_len = (n * 3 <= n_sm) ? HEAVY_TILE_LEN : (1 << 30);
-    bin_faces_kernel<<<n, BIN_THREADS, bin_smem_bytes(w), st>>>(m, w, frame0);
+void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st) {
+    const dim3 grid(BIN_PARTS, n);
+    bin_count_kernel<<<grid, BIN_PART_THREADS, bin_smem_bytes(w), st>>>(m, w, frame0);
+    bin_scan_kernel<<<n, 256, 0, st>>>(w, frame0);
+    bin_fill_kernel<<<grid, BIN_PART_THREADS, bin_smem_bytes(w), st>>>(m, w, frame0);
 }
 
 // ---------------------------------------------------------------------------
@@ -425,492 +435,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     __trap();      // a lost TMA would otherwise hang the GPU
 }
 
-// ---------------------------------------------------------------------------
-// raster_forward
-//
-// Persistent CTAs of 16 warps, one per SM.  A CTA keeps one frame's NDC vertices (x[], y[], z[],
-// 15.6 KB each) in shared memory, staged by three TMA bulk copies; its warps are otherwise fully
-// independent: each pulls 8x4-pixel regions of that frame from the frame's counter, and when the
-// frame runs dry the CTA hops to the next frame (the only CTA-wide barrier).  Per region a warp
-//   A. filters the region's tile list (bin_faces) into a sub-list (face id, vertex ids, 32-bit mask
-//      of region pixels inside the face rectangle) held in shared memory,
-//   B. per pixel: compacts the entries whose bit is set and evaluates them one per lane (vertices
-//      gathered from shared memory).  With at most K candidates every fragment is selected: the
-//      running product is kept and the pixel stops once it falls below 2^-25 (alpha == 1.0f exactly,
-//      no gradient).  Otherwise fragments go to the warp's (key, m, face) buffer and
-//   C. n > K: exact K-th order statistic of (pz, face id) by warp-cooperative bisection on the key
-//      bits (keys cached in registers), product over the selected set,
-//   D. lane q finishes pixel q: alpha, L1 term, coef = dL/dalpha * P / sigma, z-threshold.
-// ---------------------------------------------------------------------------
-struct RasterWarpSmem {
-    unsigned key[KCAP];
-    float mval[KCAP];
-    unsigned short fid[KCAP];
-    uint2 ent[SLCAP];              // (fid | v0 << 16, v1 | v2 << 16)
-    unsigned mask[SLCAP];
-    unsigned short pairs[PAIRCAP]; // packed (pixel << 5 | entry) pairs of one 32-entry block; also the
-                                   // candidate list of a capped pixel (PAIRCAP >= SLCAP)
-};
-
-struct KeyStore {           // fragment buffer: shared memory first, global spill beyond KCAP
-    RasterWarpSmem* s;
-    unsigned* gkey; float* gm; unsigned short* gfid;
-    __device__ __forceinline__ void put(int i, unsigned k, float mv, unsigned short f) const {
-        if (i < KCAP) { s->key[i] = k; s->mval[i] = mv; s->fid[i] = f; }
-        else { gkey[i - KCAP] = k; gm[i - KCAP] = mv; gfid[i - KCAP] = f; }
-    }
-    __device__ __forceinline__ unsigned key(int i) const { return i < KCAP ? s->key[i] : gkey[i - KCAP]; }
-    __device__ __forceinline__ float m(int i) const { return i < KCAP ? s->mval[i] : gm[i - KCAP]; }
-    __device__ __forceinline__ unsigned short f(int i) const { return i < KCAP ? s->fid[i] : gfid[i - KCAP]; }
-};
-
-// 32x32 bit-matrix transpose across the warp: lane q ends up with bit j = (lane j's v >> q) & 1.
-__device__ __forceinline__ unsigned transpose32(unsigned v, int lane) {
-#pragma unroll
-    for (int k = 16; k >= 1; k >>= 1) {
-        const unsigned m = (k == 16) ? 0x0000ffffu : (k == 8) ? 0x00ff00ffu : (k == 4) ? 0x0f0f0f0fu : (k == 2) ? 0x33333333u : 0x55555555u;
-        const unsigned y = __shfl_xor_sync(0xffffffffu, v, k);
-        v = (lane & k) ? ((v & ~m) | ((y >> k) & m)) : ((v & m) | ((y << k) & ~m));
-    }
-    return v;
-}
-
-// Exact K nearest by (key, face id).  Returns the product of m over the selected set and the
-// threshold (tkey, tfid): selected <=> key < tkey || (key == tkey && fid <= tfid).
-// Bisection on the key bits for the K-th order statistic, stopping early when a split of exactly K
-// appears.  Pixels whose fragments spilled past KCAP first bisect on the whole set (shared + global)
-// only until at most KCAP keys remain in the bracket, compact those into `scratch` and finish like
-// everyone else on keys cached in registers.
-__device__ float select_k_nearest(const KeyStore& ks, int n, int lane, unsigned* scratch /* >= KCAP words */,
-                                  unsigned& tkey, unsigned& tfid) {
-    constexpr int NR = KCAP / 32;
-    const unsigned ltmask = lanemask_lt();
-    unsigned lo = 0xffffffffu, hi = 0u;
-    for (int i = lane; i < n; i += 32) { const unsigned k = ks.key(i); lo = min(lo, k); hi = max(hi, k); }
-    lo = __reduce_min_sync(0xffffffffu, lo);
-    hi = __reduce_max_sync(0xffffffffu, hi);
-    bool exact = false;
-    unsigned t = hi;
-    int below = 0;                       // keys < lo
-    int want = RAST_K;                   // rank looked for among the keys of the register phase
-    const unsigned* src = ks.s->key;
-    int m = n;
-    if (n > KCAP) {
-        int c_hi = n;                    // keys <= hi
-        while (c_hi - below > KCAP && lo < hi) {
-            const unsigned mid = lo + ((hi - lo) >> 1);
-            int c = 0;
-            for (int i = lane; i < n; i += 32) c += (ks.key(i) <= mid) ? 1 : 0;
-            c = __reduce_add_sync(0xffffffffu, c);
-            if (c == RAST_K) { t = mid; exact = true; break; }
-            if (c > RAST_K) { hi = mid; c_hi = c; } else { lo = mid + 1; below = c; }
-        }
-        m = 0;
-        if (!exact && lo < hi) {
-            for (int base = 0; base < n; base += 32) {
-                const int i = base + lane;
-                unsigned k = 0u;
-                bool in = false;
-                if (i < n) { k = ks.key(i); in = (k >= lo && k <= hi); }
-                const unsigned bal = __ballot_sync(0xffffffffu, in);
-                if (in) scratch[m + __popc(bal & ltmask)] = k;
-                m += __popc(bal);
-            }
-            __syncwarp();
-            src = scratch;
-            want = RAST_K - below;
-        }
-    }
-    if (!exact && lo < hi) {
-        unsigned kr[NR];                 // keys of the register phase; padding 0xffffffff is never <= mid
-#pragma unroll
-        for (int r = 0; r < NR; ++r) { const int i = r * 32 + lane; kr[r] = (i < m) ? src[i] : 0xffffffffu; }
-        while (lo < hi) {
-            const unsigned mid = lo + ((hi - lo) >> 1);
-            int c = 0;
-#pragma unroll
-            for (int r = 0; r < NR; ++r) c += (kr[r] <= mid) ? 1 : 0;
-            c = __reduce_add_sync(0xffffffffu, c);
-            if (c == want) { t = mid; exact = true; break; }
-            if (c > want) hi = mid; else lo = mid + 1;
-        }
-    }
-    unsigned tf = 0xffffu;
-    if (!exact) {
-        t = lo;
-        int clt = 0, cle = 0;
-        for (int i = lane; i < n; i += 32) { const unsigned k = ks.key(i); clt += (k < t); cle += (k <= t); }
-        clt = __reduce_add_sync(0xffffffffu, clt);
-        cle = __reduce_add_sync(0xffffffffu, cle);
-        if (cle > RAST_K) {
-            // ties on pz at the cut: keep the (K - clt) lowest face ids among key == t
-            const int need = RAST_K - clt;
-            unsigned flo = 0u, fhi = 0xffffu;
-            while (flo < fhi) {
-                const unsigned mid = flo + ((fhi - flo) >> 1);
-                int c = 0;
-                for (int i = lane; i < n; i += 32) c += (ks.key(i) == t && ks.f(i) <= mid) ? 1 : 0;
-                c = __reduce_add_sync(0xffffffffu, c);
-                if (c >= need) fhi = mid; else flo = mid + 1;
-            }
-            tf = flo;
-        }
-    }
-    float prod = 1.f;
-    for (int i = lane; i < n; i += 32) {
-        const unsigned k = ks.key(i);
-        if (k < t || (k == t && (unsigned)ks.f(i) <= tf)) prod *= ks.m(i);
-    }
-    tkey = t; tfid = tf;
-    return warp_prod(prod);
-}
-
-__global__ void __launch_bounds__(RAST_THREADS, RAST_CTAS_PER_SM)
-raster_forward_kernel(ModelDev m, Workspace w, RasterScratch sc, int frame0, int n_frames, Weights wt,
-                      const float* ndc_soa /* [N][3][Vp] */, float* alpha_out) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* vx = reinterpret_cast<float*>(smem_raw);
-    float* vy = vx + m.Vp;
-    float* vz = vy + m.Vp;
-    RasterWarpSmem* wsm_all = reinterpret_cast<RasterWarpSmem*>(vz + m.Vp);
-    __shared__ unsigned long long bar;
-    __shared__ int s_state;        // 0: frame has work, 1: frame exhausted (skip), 2: everything done
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    RasterWarpSmem& wsm = wsm_all[wid];
-    const int gwarp = blockIdx.x * RAST_WARPS + wid;
-    uint2* g_ent = sc.ent + (size_t)gwarp * m.Fp;           // sub-lists longer than SLCAP
-    unsigned* g_mask = sc.mask + (size_t)gwarp * m.Fp;
-    unsigned short* g_plist = sc.plist + (size_t)gwarp * m.Fp;
-    KeyStore ks;
-    ks.s = &wsm;
-    ks.gkey = sc.key + (size_t)gwarp * m.Fp; ks.gm = sc.m + (size_t)gwarp * m.Fp; ks.gfid = sc.fid + (size_t)gwarp * m.Fp;
-
-    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-    __syncthreads();
-    unsigned parity = 0;
-
-    const int S = w.S;
-    const float inv_s = 1.f / (float)S;
-    const int T = w.tiles_x * w.tiles_y;
-    const int R = T * REGIONS_PER_TILE;
-    const unsigned ltmask = lanemask_lt();
-    unsigned long long n_capped = 0, n_spilled = 0;
-    int cur = (int)(((long long)blockIdx.x * n_frames) / gridDim.x);      // first visit: CTAs spread over the frames
-    __shared__ int s_cur;
-
-    for (int visit = 0;; ++visit) {
-        __syncthreads();           // every warp is past the previous frame's vertices
-        if (wid == 0) {
-            // Pick the frame to work on: after the first visit, the one with the most non-trivial regions
-            // left per CTA already on it (frame_busy = regions of tiles that hold faces; the regions after
-            // them in hand-out order are empty).  Falls back to any frame with regions left.
-            int st = 0;
-            if (visit > 0) {
-                if (lane == 0 && cur >= 0) atomicSub(w.frame_active + frame0 + cur, 1u);
-                float best = -1.f;
-                int best_f = -1;
-                for (int f = lane; f < n_frames; f += 32) {
-                    const unsigned nx = *(volatile unsigned*)(w.frame_next + frame0 + f);
-                    if (nx >= w.frame_items[frame0 + f]) continue;
-                    const unsigned busy = w.frame_busy[frame0 + f];
-                    const unsigned act = *(volatile unsigned*)(w.frame_active + frame0 + f);
-                    // per-CTA jitter (0.75 .. 1.25) keeps CTAs that finish together from herding onto one frame
-                    const float jit = 0.75f + (float)(((blockIdx.x * 2654435761u + (unsigned)f * 40503u) >> 20) & 0xffu) * (0.5f / 255.f);
-                    const float score = jit * (busy > nx ? (float)(busy - nx) : 0.f) / (float)(1u + act) + 1e-3f;
-                    if (score > best) { best = score; best_f = f; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int of = __shfl_xor_sync(0xffffffffu, best_f, o);
-                    if (ob > best || (ob == best && of >= 0 && (best_f < 0 || of < best_f))) { best = ob; best_f = of; }
-                }
-                cur = best_f;
-                if (best_f < 0) st = (*(volatile unsigned*)(w.frames_done) >= (unsigned)n_frames) ? 2 : 1;
-            }
-            if (lane == 0) {
-                if (st == 0) {
-                    atomicAdd(w.frame_active + frame0 + cur, 1u);
-                    const unsigned bytes = (unsigned)(m.Vp * sizeof(float));
-                    const float* src = ndc_soa + (size_t)(frame0 + cur) * 3 * m.Vp;
-                    mbar_expect_tx(&bar, 3 * bytes);
-                    tma_load_1d(vx, src, bytes, &bar);
-                    tma_load_1d(vy, src + m.Vp, bytes, &bar);
-                    tma_load_1d(vz, src + 2 * m.Vp, bytes, &bar);
-                } else if (st == 1) {
-                    __nanosleep(500);      // the last regions are being drawn elsewhere; look again
-                }
-                s_state = st;
-                s_cur = cur;
-            }
-        }
-        __syncthreads();
-        cur = s_cur;
-        const int fr = frame0 + cur;
-        const int st = s_state;
-        if (st == 2) break;
-        if (st == 1) continue;
-        mbar_wait(&bar, parity);
-        parity ^= 1u;
-
-        const unsigned n_items = w.frame_items[fr];
-        const unsigned n_heavy_items = w.frame_heavy[fr] * (unsigned)(REGIONS_PER_TILE * REGION_H);
-        const unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
-        const unsigned short* torder = w.tile_order + (size_t)fr * T;
-        const uint4* pool = w.tile_pool + (size_t)fr * w.pool_cap;
-        // the next region index is drawn one region ahead so that the atomic's round trip is hidden
-        unsigned next_reg = 0;
-        if (lane == 0) {
-            next_reg = atomicAdd(w.frame_next + fr, 1u);
-            if (next_reg == n_items) atomicAdd(w.frames_done, 1u);              // first draw past the end
-        }
-        for (;;) {
-            const unsigned reg = __shfl_sync(0xffffffffu, next_reg, 0);
-            if (reg >= n_items) break;
-            if (lane == 0) {
-                next_reg = atomicAdd(w.frame_next + fr, 1u);
-                if (next_reg == n_items) atomicAdd(w.frames_done, 1u);
-            }
-            // item -> (tile, region, pixel rows): the frame's heavy tiles come first, one pixel row per item
-            int tile, sub, row0, nrow;
-            if (reg < n_heavy_items) {
-                tile = (int)torder[reg / (REGIONS_PER_TILE * REGION_H)];
-                sub = (int)(reg % (REGIONS_PER_TILE * REGION_H)) / REGION_H;
-                row0 = (int)(reg % REGION_H); nrow = 1;
-            } else {
-                const unsigned r2 = reg - n_heavy_items;
-                tile = (int)torder[w.frame_heavy[fr] + r2 / REGIONS_PER_TILE];
-                sub = (int)(r2 % REGIONS_PER_TILE);
-                row0 = 0; nrow = REGION_H;
-            }
-            const unsigned pmask = (nrow == REGION_H) ? 0xffffffffu : (0xffu << (8 * row0));    // pixels of this item
-            const unsigned oreg = (unsigned)(tile * REGIONS_PER_TILE + sub);      // storage index of the region
-            const int lx0 = (sub % (TILE_W / REGION_W)) * REGION_W, ly0 = (sub / (TILE_W / REGION_W)) * REGION_H;
-            const int x0 = (tile % w.tiles_x) * TILE_W + lx0, y0 = (tile / w.tiles_x) * TILE_H + ly0;
-            const unsigned off = toff[tile];
-            const int len = (int)(min(toff[tile + 1], (unsigned)w.pool_cap) - min(off, (unsigned)w.pool_cap));
-            const int px_x = x0 + (lane & 7), px_y = y0 + (lane >> 3);
-            const bool px_in = (px_x < S) && (px_y < S) && ((pmask >> lane) & 1u);
-            float* l1_out = w.region_l1 + ((size_t)fr * R + oreg) * REGION_H;      // one slot per pixel row
-            if (len == 0 || x0 >= S || y0 >= S) {
-                // no face reaches the tile: alpha = 0, |alpha - T| = T; pix is never read here
-                if (lane < REGION_H) l1_out[lane] = w.region_tsum[((size_t)fr * R + oreg) * REGION_H + lane];
-                if (alpha_out && px_in) alpha_out[((size_t)(fr - frame0) * S + px_y) * S + px_x] = 0.f;
-                continue;
-            }
-
-            // A. sub-list (shared memory; if it does not fit, a second pass puts it in global scratch)
-            int L = 0;
-            bool in_smem = true;
-            for (int pass = 0; pass < 2; ++pass) {
-                L = 0;
-                uint4 e_next = make_uint4(0u, 0u, 0xffffffffu, 0u);
-                if (lane < len) e_next = pool[off + lane];
-                for (int base = 0; base < len; base += 32) {
-                    const int j = base + lane;
-                    const uint4 e = e_next;
-                    e_next = make_uint4(0u, 0u, 0xffffffffu, 0u);
-                    if (j + 32 < len) e_next = pool[off + j + 32];          // next block in flight while this one is filtered
-                    const int c0 = (int)(e.z & 0xffu), c1 = (int)((e.z >> 8) & 0xffu), r0 = (int)((e.z >> 16) & 0xffu), r1 = (int)(e.z >> 24);
-                    const bool ov = (j < len) && (c0 <= lx0 + REGION_W - 1) && (c1 >= lx0) &&
-                                    (r0 <= ly0 + row0 + nrow - 1) && (r1 >= ly0 + row0);
-                    const unsigned bal = __ballot_sync(0xffffffffu, ov);
-                    if (ov) {
-                        const int a = max(c0 - lx0, 0), b = min(c1 - lx0, REGION_W - 1);
-                        const unsigned cm = ((1u << (b + 1)) - 1u) & ~((1u << a) - 1u);       // 8-bit column mask
-                        const int ra = max(r0 - ly0, row0), rb = min(r1 - ly0, row0 + nrow - 1);
-                        const unsigned rows = ((1u << (rb + 1)) - 1u) & ~((1u << ra) - 1u);   // 4-bit row mask
-                        const unsigned mk = cm * ((rows * 0x00204081u) & 0x01010101u);         // one byte of cm per selected row
-                        const int pos = L + __popc(bal & ltmask);
-                        if (in_smem) { if (pos < SLCAP) { wsm.ent[pos] = make_uint2(e.x, e.y); wsm.mask[pos] = mk; } }
-                        else { g_ent[pos] = make_uint2(e.x, e.y); g_mask[pos] = mk; }
-                    }
-                    L += __popc(bal);
-                }
-                if (L <= SLCAP || !in_smem) break;
-                in_smem = false;
-            }
-            __syncwarp();
-            const uint2* ent = in_smem ? wsm.ent : g_ent;
-            const unsigned* emask = in_smem ? wsm.mask : g_mask;
-            unsigned short* plist = (L <= PAIRCAP) ? wsm.pairs : g_plist;
-
-            // B. candidates per pixel (lane = pixel): transpose the entry x pixel bit matrix block by block
-            int npq = 0;
-            for (int base = 0; base < L; base += 32) {
-                const unsigned mj = (base + lane < L) ? emask[base + lane] : 0u;
-                npq += __popc(transpose32(mj, lane));
-            }
-            const bool capped_q = npq > RAST_K;
-            const bool packed_q = px_in && npq > 0 && !capped_q;
-
-            float myP = 1.f;
-            unsigned myTkey = 0xffffffffu, myTfid = 0xffffu;
-
-            // C. pixels with at most K candidates select every fragment: their (pixel, entry) pairs are
-            //    packed 32 per batch across pixel boundaries, one pair per lane; the per-pixel products
-            //    come out of a segmented scan (pairs are sorted by pixel)
-            if (__any_sync(0xffffffffu, packed_q)) {
-                float* acc = wsm.mval;             // running product per pixel (the key buffer is idle in this phase)
-                acc[lane] = 1.f;
-                __syncwarp();
-                for (int base = 0; base < L; base += 32) {
-                    const unsigned mj = (base + lane < L) ? emask[base + lane] : 0u;
-                    unsigned tq = transpose32(mj, lane);
-                    if (!packed_q) tq = 0u;
-                    const int c = __popc(tq);
-                    int incl = c;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
-                    const int total = __shfl_sync(0xffffffffu, incl, 31);
-                    if (total == 0) continue;
-                    int o = incl - c;
-                    while (tq) { const int j = __ffs(tq) - 1; tq &= tq - 1u; wsm.pairs[o++] = (unsigned short)((lane << 5) | j); }
-                    __syncwarp();
-                    for (int b0 = 0; b0 < total; b0 += 32) {
-                        const int i = b0 + lane;
-                        unsigned q = 255u;
-                        float mv = 1.f;
-                        if (i < total) {
-                            const unsigned pr = wsm.pairs[i];
-                            q = pr >> 5;
-                            const uint2 e = ent[base + (int)(pr & 31u)];
-                            const unsigned v0 = e.x >> 16, v1 = e.y & 0xffffu, v2 = e.y >> 16;
-                            float sd, pz;
-                            if (frag_forward(vx[v0], vy[v0], vz[v0], vx[v1], vy[v1], vz[v1], vx[v2], vy[v2], vz[v2],
-                                             pix_to_ndc(x0 + (int)(q & 7u), inv_s), pix_to_ndc(y0 + (int)(q >> 3), inv_s), false, sd, pz)) {
-                                float pp;
-                                frag_prob(sd, pp, mv);
-                            }
-                        }
-                        float val = mv;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const float y = __shfl_up_sync(0xffffffffu, val, d);
-                            const unsigned qy = __shfl_up_sync(0xffffffffu, q, d);
-                            if (lane >= d && qy == q) val *= y;
-                        }
-                        const unsigned qn = __shfl_down_sync(0xffffffffu, q, 1);
-                        if (i < total && (lane == 31 || qn != q)) acc[q] *= val;          // one tail lane per pixel
-                        __syncwarp();
-                    }
-                }
-                if (packed_q) myP = acc[lane];
-            }
-
-            // D. pixels with more than K candidates: one at a time, fragments buffered, exact K-nearest rule
-            unsigned cmask = __ballot_sync(0xffffffffu, px_in && capped_q);
-            while (cmask) {
-                const int q = __ffs(cmask) - 1;
-                cmask &= cmask - 1u;
-                int np = 0;
-                for (int base = 0; base < L; base += 64) {
-                    const int i0 = base + lane, i1 = i0 + 32;
-                    const unsigned m0 = (i0 < L) ? emask[i0] : 0u, m1 = (i1 < L) ? emask[i1] : 0u;
-                    const bool p0 = (m0 >> q) & 1u, p1 = (m1 >> q) & 1u;
-                    const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
-                    const int n0 = __popc(b0);
-                    if (p0) plist[np + __popc(b0 & ltmask)] = (unsigned short)i0;
-                    if (p1) plist[np + n0 + __popc(b1 & ltmask)] = (unsigned short)i1;
-                    np += n0 + __popc(b1);
-                }
-                __syncwarp();
-                const float px = pix_to_ndc(x0 + (q & 7), inv_s), py = pix_to_ndc(y0 + (q >> 3), inv_s);
-                int n = 0;
-                for (int b0 = 0; b0 < np; b0 += 32) {
-                    const int i = b0 + lane;
-                    bool valid = false;
-                    unsigned key = 0u; float mv = 1.f; unsigned fidx = 0;
-                    if (i < np) {
-                        const uint2 e = ent[plist[i]];
-                        fidx = e.x & 0xffffu;
-                        const unsigned v0 = e.x >> 16, v1 = e.y & 0xffffu, v2 = e.y >> 16;
-                        float sd, pz;
-                        valid = frag_forward(vx[v0], vy[v0], vz[v0], vx[v1], vy[v1], vz[v1], vx[v2], vy[v2], vz[v2], px, py, true, sd, pz);
-                        if (valid) {
-                            float pp;
-                            frag_prob(sd, pp, mv);
-                            key = __float_as_uint(pz + 0.f);
-                        }
-                    }
-                    const unsigned bal = __ballot_sync(0xffffffffu, valid);
-                    if (valid) ks.put(n + __popc(bal & ltmask), key, mv, (unsigned short)fidx);
-                    n += __popc(bal);
-                }
-                __syncwarp();
-                float P = 1.f;
-                unsigned tk = 0xffffffffu, tf = 0xffffu;
-                if (n > RAST_K) {
-                    P = select_k_nearest(ks, n, lane, reinterpret_cast<unsigned*>(wsm.pairs), tk, tf);
-                    if (lane == 0) { ++n_capped; if (n > KCAP) ++n_spilled; }
-                } else if (n > 0) {
-                    float pr = 1.f;
-                    for (int i = lane; i < n; i += 32) pr *= ks.m(i);
-                    P = warp_prod(pr);
-                }
-                if (lane == q) { myP = P; myTkey = tk; myTfid = tf; }
-                __syncwarp();
-            }
-
-            // E. epilogue: lane = pixel
-            float l1 = 0.f;
-            if (px_in) {
-                const size_t pi = ((size_t)fr * S + px_y) * S + px_x;
-                const float alpha = 1.f - myP;
-                const float Tm = (float)w.sil[pi];
-                const float d = alpha - Tm;
-                l1 = fabsf(d);
-                float coef = 0.f;
-                if (myP < 1.f && myP >= P_SKIP && d != 0.f) {       // myP < 1 <=> the pixel has fragments
-                    const float ga = wt.sil * w.inv_window[fr] * inv_s * inv_s * (d > 0.f ? 1.f : -1.f);
-                    coef = ga * myP * (1.f / RAST_SIGMA);
-                }
-                w.pix[pi] = make_uint2(__float_as_uint(coef), myTkey);
-                if (myTkey != 0xffffffffu) w.pix_tfid[pi] = (unsigned short)myTfid;
-                if (alpha_out) alpha_out[((size_t)(fr - frame0) * S + px_y) * S + px_x] = alpha;
-            }
-            // per-row sums (8 lanes each), fixed order
-            l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-            l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-            l1 += __shfl_xor_sync(0xffffffffu, l1, 4);
-            if ((lane & 7) == 0 && ((pmask >> lane) & 1u)) l1_out[lane >> 3] = l1;
-        }
-    }
-    if (lane == 0 && (n_capped | n_spilled)) {
-        atomicAdd(w.counters + 0, n_capped);
-        atomicAdd(w.counters + 1, n_spilled);
-    }
-}
-
-size_t raster_smem_bytes(const ModelDev& m) {
-    return (size_t)3 * m.Vp * sizeof(float) + (size_t)RAST_WARPS * sizeof(RasterWarpSmem);
-}
-
 }  // namespace smf
 #include "smalfit_raster_tile.cuh"
 namespace smf {
-
-// SoA copy of the NDC vertices for the TMA loads (x[], y[], z[] per frame)
-__global__ void __launch_bounds__(256) ndc_soa_kernel(ModelDev m, Workspace w, int frame0, float* soa) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    const int fr = frame0 + blockIdx.y;
-    if (v >= m.Vp) return;
-    const float4 a = w.ndc[(size_t)fr * m.Vp + v];
-    float* o = soa + (size_t)fr * 3 * m.Vp;
-    o[v] = a.x; o[m.Vp + v] = a.y; o[2 * m.Vp + v] = a.z;
-}
-
-void launch_ndc_soa(const ModelDev& m, const Workspace& w, float* ndc_soa, int frame0, int n, cudaStream_t st) {
-    dim3 g((m.Vp + 255) / 256, n);
-    ndc_soa_kernel<<<g, 256, 0, st>>>(m, w, frame0, ndc_soa);
-}
-
-void launch_raster_forward(const ModelDev& m, const Workspace& w, const RasterScratch& sc, float* ndc_soa,
-                           int frame0, int n, Weights wt, float* alpha_out, int n_ctas, cudaStream_t st) {
-    cudaMemsetAsync(w.frame_next, 0, sizeof(unsigned) * (size_t)(2 * w.N + 1), st);  // + frames_done + frame_active
-    raster_forward_kernel<<<n_ctas, RAST_THREADS, raster_smem_bytes(m), st>>>(m, w, sc, frame0, n, wt, ndc_soa, alpha_out);
-}
 
 // ---------------------------------------------------------------------------
 // raster_backward: one warp per (frame, face); lanes sweep the face's pixel rectangle
@@ -1430,11 +957,11 @@ cudaError_t configure_kernels(const ModelDev& m) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(frame_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(bin_faces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (BIN_WARPS + 2) * MAX_TILES * (int)sizeof(unsigned));
+    e = cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (BIN_PART_WARPS + 1) * MAX_TILES * (int)sizeof(unsigned));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(raster_tile_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_tile_smem_bytes());
+    e = cudaFuncSetAttribute(bin_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (BIN_PART_WARPS + 1) * MAX_TILES * (int)sizeof(unsigned));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(raster_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes(m));
+    return cudaFuncSetAttribute(raster_tile_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_tile_smem_bytes());
 }
 
 }  // namespace smf

@@ -8,18 +8,13 @@
 namespace smf {
 
 constexpr int FRAME_FWD_THREADS = 512;
-constexpr int BIN_WARPS = 32, BIN_THREADS = BIN_WARPS * 32;
+constexpr int BIN_WARPS = 32;               // face segments per frame (one warp each)
+constexpr int BIN_PARTS = 4;                // CTAs per frame in bin_count / bin_fill
+constexpr int BIN_PART_WARPS = BIN_WARPS / BIN_PARTS, BIN_PART_THREADS = BIN_PART_WARPS * 32;
 constexpr int FRAME_BWD_THREADS = 1024;
-constexpr int RAST_WARPS = 16;              // warps per raster-forward CTA
-constexpr int RAST_CTAS_PER_SM = 1;         // (2 x 8 warps with SLCAP 320 measured 4 % slower: more sub-lists spill to global)
-constexpr int RAST_THREADS = RAST_WARPS * 32;
-constexpr int REGION_W = 8, REGION_H = 4;   // pixels handled by one warp at a time
-constexpr int TILE_W = 32, TILE_H = 32;     // CTA work item: 32 regions, pulled dynamically by the warps
+constexpr int REGION_W = 8, REGION_H = 4;   // granularity of the per-row silhouette loss sums (region_l1 / region_tsum)
+constexpr int TILE_W = 32, TILE_H = 32;     // rasteriser work item
 constexpr int REGIONS_PER_TILE = (TILE_W / REGION_W) * (TILE_H / REGION_H);
-constexpr int KCAP = 256;                   // fragment selection buffer per warp (shared memory part)
-constexpr int SLCAP = 448;                  // region sub-list entries kept in shared memory
-constexpr int HEAVY_TILE_LEN = 1400;             // tiles with at least this many faces are handed out one pixel row at a time
-constexpr int PAIRCAP = 1024;               // (pixel, entry) pairs of one 32-entry block (32 x 32)
 constexpr int RT_WARPS = 8, RT_THREADS = RT_WARPS * 32;   // tile rasteriser CTA
 #ifndef RT_CTAS
 #define RT_CTAS 3
@@ -84,15 +79,9 @@ struct Workspace {
                                 //   (x0,y0,x1,y1) (x2,y2,z0,z1) (z2, 1/(area+eps), 1/|e01|^2, 1/|e02|^2) (1/|e12|^2, fid, rect, -)
     unsigned* tile_off;         // [N][tiles+1] offsets into the frame's pool
     unsigned* tile_cost;        // [N][tiles] (pixel, face) pairs of the tile
-    unsigned short* tile_order; // [N][tiles] tiles sorted by decreasing list length (hand-out order)
+    unsigned* bin_cnt;          // [N][BIN_WARPS][tiles] per (face segment, tile): count, then write cursor
+    unsigned* bin_cost;         // [N][BIN_PARTS][tiles] pair-count partials
     int pool_cap;
-    unsigned* frame_next;       // [N] next region to hand out   (followed by frames_done)
-    unsigned* frames_done;      // [1] frames whose counter ran past the end
-    unsigned* frame_active;     // [N] CTAs currently working on the frame
-    unsigned* frame_busy;       // [N] items of tiles that hold faces (they come first in hand-out order)
-    int heavy_len;              // tiles with at least this many faces count as heavy (set per launch)
-    unsigned* frame_heavy;      // [N] number of heavy tiles (handed out row by row)
-    unsigned* frame_items;      // [N] work items of the frame
     uint2* pix;                 // [N][S*S] (float coef, u32 tkey)
     uint16_t* pix_tfid;         // [N][S*S] tie face id (capped pixels only)
     float* region_l1;           // [N][tiles*32*4] per region and pixel row: sum |alpha - T|
@@ -133,22 +122,13 @@ struct TileScratch {        // tile rasteriser: per resident CTA
     int split_len;          // > 0: overrides the list length above which a tile is cut into bands
 };
 
-struct RasterScratch {      // per resident warp, [n_raster_warps][Fp] each
-    unsigned* key; float* m; unsigned short* fid;          // fragments beyond KCAP of a pixel
-    uint2* ent; unsigned* mask; unsigned short* plist;     // sub-lists longer than SLCAP
-};
-
 // ---- launch wrappers (defined in smalfit_kernels.cu) ----------------------
 void upload_skeleton(const SkeletonConst& sk);
 cudaError_t configure_kernels(const ModelDev& m);
-size_t raster_smem_bytes(const ModelDev& m);
 void launch_shape_forward(const ModelDev& m, const Workspace& w, const Params& p, cudaStream_t st);
 void launch_frame_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n,
                           Weights wt, float* verts_out, cudaStream_t st);
-void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, int n_sm, cudaStream_t st);
-void launch_ndc_soa(const ModelDev& m, const Workspace& w, float* ndc_soa, int frame0, int n, cudaStream_t st);
-void launch_raster_forward(const ModelDev& m, const Workspace& w, const RasterScratch& sc, float* ndc_soa,
-                           int frame0, int n, Weights wt, float* alpha_out, int n_ctas, cudaStream_t st);
+void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st);
 size_t raster_tile_smem_bytes();
 void launch_raster_tile_forward(const ModelDev& m, const Workspace& w, const TileScratch& ts, int frame0, int n, Weights wt,
                                 float* alpha_out, int n_ctas, cudaStream_t st);

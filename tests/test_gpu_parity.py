@@ -92,6 +92,40 @@ def test_loss_and_gradients(fitter, oracle64, seq, weights, label):
             assert H.rel_err(g, go[k]) < 1e-4, (label, name, k, H.rel_err(g, go[k]))
 
 
+@pytest.mark.parametrize("knobs", [
+    {"SMALFIT_RT_LISTCAP": "2048"},                                    # tiles finished in several passes (RT_SKIP path)
+    {"SMALFIT_RT_NSUB": "8", "SMALFIT_RT_SPLITLEN": "64"},            # every tile cut into 8 row bands
+    {"SMALFIT_RT_LISTCAP": "1024", "SMALFIT_RT_NSUB": "2", "SMALFIT_RT_SPLITLEN": "64"},
+])
+def test_tile_rasteriser_paths_agree(constants, fitter, oracle64, seq, knobs, monkeypatch):
+    """The tile rasteriser's rarely taken paths (multi-pass tiles, row-band items), forced through the
+    create-time knobs, against the default configuration: same silhouettes,
+    loss and gradients (selection is exact in all of them; products are grouped differently: 1e-6)."""
+    from smalify_b200.smal_fitter import SMALFitter
+    data, gt = seq
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    other = SMALFitter("cuda", data, N_SMALL, 1, True, constants=constants)
+    for k in knobs:
+        monkeypatch.delenv(k)
+    for name, p in _states(oracle64, gt).items():
+        res = []
+        for f in (fitter, other):
+            H.load_params_into(f, p)
+            for t in f.parameters():
+                t.grad = None
+                t.requires_grad_(True)
+            loss, _ = f(list(range(N_SMALL)), STAGE1, 1)
+            loss.backward()
+            alpha, _ = f.render()
+            res.append((float(loss), alpha.clone(), {k: getattr(f, k).grad.clone() for k in ("global_rotation", "trans", "joint_rotations", "betas")}))
+        (la, aa, ga), (lb, ab, gb) = res
+        assert abs(la - lb) <= 2e-6 * abs(la), (name, la, lb)
+        assert float((aa - ab).abs().max()) < 2e-6, name
+        for k in ga:
+            assert H.rel_err(gb[k], ga[k].double().cpu()) < 2e-5, (name, k)
+
+
 def test_windows_and_temporal(fitter, oracle64, seq):
     data, gt = seq
     p = H.perturbed_params(oracle64, gt, seed=9)
