@@ -53,7 +53,7 @@ extern "C" {
 #define SMALFIT_L_SIL 1
 #define SMALFIT_L_BETAS 2
 #define SMALFIT_L_POSE 3
-#define SMALFIT_L_LIMIT 4     /* always 0: disabled in the reference (smal_fitter.py:146-151) */
+#define SMALFIT_L_LIMIT 4     /* 0 unless smalfit_set_joint_limits was called: disabled in the reference (smal_fitter.py:146-151) */
 #define SMALFIT_L_SPLAY 5
 #define SMALFIT_L_TEMPORAL 6
 #define SMALFIT_L_TOTAL 7
@@ -137,6 +137,22 @@ SMALFIT_API int smalfit_set_visibility(smalfit_t h, int frame0, int n_frames, co
                            int from_host, void* stream);
 /* rotation masks global_mask[3], rotation_mask[34*3] (smal_fitter.py:92,97); host ptrs */
 SMALFIT_API int smalfit_set_masks(smalfit_t h, const float* global_mask, const float* rotation_mask);
+/* Optional joint-limit term (row 8f-4; the reference ships the limits in
+ * smal_fitter/priors/joint_limits_prior.py but keeps the term commented out at smal_fitter.py:146-151):
+ *   loss_terms[SMALFIT_L_LIMIT] = w_limit * mean over (B, 34, 3) of max(q - max, 0) + max(min - q, 0)
+ * on the masked joint rotations, with its gradient.  min_limits / max_limits: HOST pointers to 34*3
+ * floats (+-INFINITY = unbounded); both NULL disables the term again (the default: weights[4] is then
+ * ignored exactly as the reference ignores w_limit). */
+SMALFIT_API int smalfit_set_joint_limits(smalfit_t h, const float* min_limits, const float* max_limits);
+
+/* Optional focal parameter (row 8f-4; the reference's camera is fixed: OpenGLPerspectiveCameras with the
+ * default fov = 60 degrees at smal_fitter/p3d_renderer.py:22-23, i.e. x_ndc = f x_view / z_view with
+ * f = 1/tan(30 deg)).  focal: DEVICE pointer to one float that replaces f for vertices and keypoints in
+ * every later call (the caller keeps it alive); grad_focal: DEVICE pointer to one float that every
+ * smalfit_loss_grad call overwrites with dL/dfocal over its frame range, or NULL.  focal = NULL restores the
+ * reference camera.  Not part of smalfit_tensors_t: the five reference parameters stay as they are. */
+SMALFIT_API int smalfit_set_focal(smalfit_t h, const float* focal, float* grad_focal);
+
 /* frames_per_window[i] = number of frames in the window that frame i belongs to
  * (the B of every mean() in SMALFitter.forward); host pointer, N entries. Default N. */
 SMALFIT_API int smalfit_set_windows(smalfit_t h, const int32_t* frames_per_window, int n_frames);

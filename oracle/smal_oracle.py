@@ -167,21 +167,21 @@ def smal_forward(m: OracleModel, betas, theta, logscale):
 # --------------------------------------------------------------------------
 # Camera (PyTorch3D 0.2.5 look_at_view_transform(2.7,0,0) + OpenGLPerspective)
 # --------------------------------------------------------------------------
-def world_to_ndc(verts: torch.Tensor) -> torch.Tensor:
+def world_to_ndc(verts: torch.Tensor, focal=None) -> torch.Tensor:
     """(…,3) world -> (x_ndc, y_ndc, z_view).  R = diag(-1,1,-1), T = (0,0,2.7);
     x_ndc = f x_view / z_view with f = 1/tan(30 deg); the rasteriser's z is view z
-    (MeshRasterizer.transform)."""
-    f = 1.0 / math.tan(math.radians(FOV_DEG) / 2.0)
+    (MeshRasterizer.transform).  focal (extension): replaces f."""
+    f = 1.0 / math.tan(math.radians(FOV_DEG) / 2.0) if focal is None else focal
     xv = -verts[..., 0]
     yv = verts[..., 1]
     zv = CAMERA_DISTANCE - verts[..., 2]
     return torch.stack([f * xv / zv, f * yv / zv, zv], dim=-1)
 
 
-def project_points_screen(points: torch.Tensor, image_size: int) -> torch.Tensor:
+def project_points_screen(points: torch.Tensor, image_size: int, focal=None) -> torch.Tensor:
     """cameras.transform_points_screen(points, (S,S))[:, :, [1, 0]]
     (p3d_renderer.py:67-68): returns (row, col)."""
-    ndc = world_to_ndc(points)
+    ndc = world_to_ndc(points, focal)
     col = (image_size - 1.0) / 2.0 * (1.0 - ndc[..., 0])
     row = (image_size - 1.0) / 2.0 * (1.0 - ndc[..., 1])
     return torch.stack([row, col], dim=-1)
@@ -308,9 +308,9 @@ def soft_silhouette(verts_ndc: torch.Tensor, faces: torch.Tensor, S: int,
     return alpha
 
 
-def render_silhouettes(m: OracleModel, verts: torch.Tensor, S: int) -> torch.Tensor:
+def render_silhouettes(m: OracleModel, verts: torch.Tensor, S: int, focal=None) -> torch.Tensor:
     """(B,V,3) world verts -> (B,1,S,S) like Renderer.forward's first output."""
-    ndc = world_to_ndc(verts)
+    ndc = world_to_ndc(verts, focal)
     return torch.stack([soft_silhouette(ndc[b], m.faces, S) for b in range(verts.shape[0])])[:, None]
 
 
@@ -340,10 +340,10 @@ class FitParams:
 
 
 def fitter_forward(m: OracleModel, p: FitParams, sil, target_joints, visibility, batch_range, weights,
-                   image_size: int, return_aux: bool = False, silhouette_fn=None):
+                   image_size: int, return_aux: bool = False, silhouette_fn=None, joint_limits=None, focal=None):
     """SMALFitter.forward.  sil (N,1,S,S), target_joints (N,25,2) (row,col),
     visibility (N,25) {0,1}.  weights = (w_j2d, w_reproj, w_betas, w_pose, w_limit, w_splay)."""
-    w_j2d, w_reproj, w_betas, w_pose, _w_limit, w_splay = [float(w) for w in weights]
+    w_j2d, w_reproj, w_betas, w_pose, w_limit, w_splay = [float(w) for w in weights]
     br = list(batch_range)
     B = len(br)
     g = p.global_rotation[br]
@@ -355,7 +355,7 @@ def fitter_forward(m: OracleModel, p: FitParams, sil, target_joints, visibility,
     verts = verts + p.trans[br][:, None]
     joints = joints + p.trans[br][:, None]
     kp3d = joints[:, list(CANONICAL)]
-    proj = project_points_screen(kp3d, image_size)
+    proj = project_points_screen(kp3d, image_size, focal)
     objs = {}
     aux = {}
     if w_j2d > 0:
@@ -366,6 +366,11 @@ def fitter_forward(m: OracleModel, p: FitParams, sil, target_joints, visibility,
     if w_pose > 0:
         res = ((theta.reshape(B, 105) - m.pose_mean[None]) @ m.pose_prec) * m.pose_use
         objs["pose"] = w_pose * torch.mean(res ** 2)                             # :153-157
+    if w_limit > 0 and joint_limits is not None:
+        # the term the reference keeps commented out (:146-151); joint_limits = (min, max), each (34, 3)
+        lo, hi = (torch.as_tensor(a, dtype=m.dtype) for a in joint_limits)
+        zeros = torch.zeros_like(q)
+        objs["limit"] = w_limit * torch.mean(torch.max(q - hi, zeros) + torch.max(lo - q, zeros))
     if w_splay > 0:
         objs["splay"] = w_splay * torch.sum(q[:, :, [0, 2]] ** 2)                # :159-160
     if w_betas > 0:
@@ -373,7 +378,7 @@ def fitter_forward(m: OracleModel, p: FitParams, sil, target_joints, visibility,
         res = (allb - m.shape_mean[None]) @ m.shape_prec
         objs["betas"] = w_betas * torch.mean(res ** 2)                           # :162-171
     if w_reproj > 0 or return_aux:
-        sil_r = (silhouette_fn or render_silhouettes)(m, verts, image_size)
+        sil_r = silhouette_fn(m, verts, image_size) if silhouette_fn else render_silhouettes(m, verts, image_size, focal)
         aux["silhouettes"] = sil_r
         if w_reproj > 0:
             objs["sil_reproj"] = w_reproj * torch.mean(torch.abs(sil_r - sil[br].to(m.dtype)))   # :172-173

@@ -77,6 +77,8 @@ def load_library(path: str | None = None) -> C.CDLL:
         "smalfit_set_visibility": ([vp, C.c_int, C.c_int, vp, C.c_int, vp], C.c_int),
         "smalfit_set_masks": ([vp, _f32p, _f32p], C.c_int),
         "smalfit_set_windows": ([vp, _i32p, C.c_int], C.c_int),
+        "smalfit_set_joint_limits": ([vp, _f32p, _f32p], C.c_int),
+        "smalfit_set_focal": ([vp, vp, vp], C.c_int),
         "smalfit_set_per_frame_shapes": ([vp, C.c_int], C.c_int),
         "smalfit_loss_grad": ([vp, TP, C.c_int, C.c_int, _f32p, C.c_int, TP, vp, vp], C.c_int),
         "smalfit_temporal": ([vp, TP, C.c_int, C.c_float, TP, vp, vp], C.c_int),
@@ -101,7 +103,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 
 EXPORTED_SYMBOLS = (
     "smalfit_abi_version", "smalfit_create", "smalfit_destroy", "smalfit_last_error", "smalfit_set_targets",
-    "smalfit_set_visibility", "smalfit_set_masks", "smalfit_set_windows", "smalfit_set_per_frame_shapes",
+    "smalfit_set_visibility", "smalfit_set_masks", "smalfit_set_windows", "smalfit_set_joint_limits", "smalfit_set_focal", "smalfit_set_per_frame_shapes",
     "smalfit_loss_grad", "smalfit_temporal", "smalfit_adam_step", "smalfit_adam_reset", "smalfit_render", "smalfit_vertices",
     "smalfit_counters", "smalfit_work_counts", "smalfit_set_profiling", "smalfit_get_profile",
 )

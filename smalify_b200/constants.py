@@ -109,3 +109,55 @@ GLOBAL_ROT_INIT = tuple([-(2.0 * math.pi / 3.0) / math.sqrt(3.0)] * 3)
 
 CROP_SIZE = 256     # config.py:12
 WINDOW_SIZE = 10    # config.py:25
+
+
+# Joint-rotation limits (radians) of smal_fitter/priors/joint_limits_prior.py (`Ranges`, in the order of
+# `LimitPrior.parts`: part id p is joint_rotations row p, i.e. skeleton joint p + 1), as
+# (x_min, x_max, y_min, y_max, z_min, z_max) per joint.  The reference's table has 32 parts; the 35-joint
+# model has 34 pose joints: the two ear joints (rows 32, 33) are left unbounded.  The term is
+# commented out in the reference (smal_fitter.py:146-151) and off by default here.
+_JOINT_LIMIT_ROWS = (
+    (-0.3, 0.3, -1.2, 0.5, -0.1, 0.1),     # pelvis0
+    (-0.4, 0.4, -1.0, 0.9, -0.8, 0.8),     # spine
+    (-0.4, 0.4, -1.0, 0.9, -0.8, 0.8),     # spine0
+    (-0.4, 0.4, -0.5, 1.2, -0.4, 0.4),     # spine1
+    (-0.5, 0.5, -0.4, 1.4, -0.5, 0.5),     # spine2
+    (-0.5, 0.5, -0.6, 1.4, -0.8, 0.8),     # spine3
+    (-0.05, 0.05, -1.3, 0.8, -0.6, 0.6),   # LLeg1
+    (-0.05, 0.05, -1.0, 1.1, -0.6, 0.6),   # LLeg2
+    (-0.4, 0.1, -0.3, 1.4, -0.7, 0.4),     # LLeg3
+    (-0.3, 0.1, -0.4, 1.5, -0.7, 0.3),     # LFoot
+    (-0.05, 0.05, -1.3, 0.8, -0.6, 0.6),   # RLeg1
+    (-0.05, 0.05, -1.0, 0.9, -0.6, 0.6),   # RLeg2
+    (-0.1, 0.4, -0.3, 1.4, -0.4, 0.7),     # RLeg3
+    (-0.1, 0.3, -0.4, 1.5, -0.3, 0.7),     # RFoot
+    (-0.8, 0.8, -1.0, 1.0, -1.1, 1.1),     # Neck
+    (-0.5, 0.5, -1.0, 0.9, -0.9, 0.9),     # Head
+    (-0.2, 0.3, -0.5, 0.8, -0.5, 0.4),     # LLegBack1
+    (-0.2, 0.3, -0.6, 0.8, -0.6, 0.5),     # LLegBack2
+    (-0.3, 0.2, -0.8, 0.2, -0.5, 0.4),     # LLegBack3
+    (-0.3, 0.2, -0.3, 1.1, -0.5, 0.3),     # LFootBack
+    (-0.3, 0.2, -0.5, 0.8, -0.4, 0.5),     # RLegBack1
+    (-0.3, 0.2, -0.6, 0.8, -0.5, 0.6),     # RLegBack2
+    (-0.2, 0.3, -0.8, 0.2, -0.4, 0.5),     # RLegBack3
+    (-0.2, 0.3, -0.3, 1.1, -0.3, 0.5),     # RFootBack
+    (-0.1, 0.1, -1.5, 1.4, -1.2, 1.2),     # Tail1
+    (-0.1, 0.1, -1.0, 1.0, -0.8, 0.8),     # Tail2
+    (-0.1, 0.1, -1.0, 1.0, -0.8, 0.8),     # Tail3
+    (-0.1, 0.1, -1.0, 1.0, -0.8, 0.8),     # Tail4
+    (-0.1, 0.1, -1.0, 1.0, -0.8, 0.8),     # Tail5
+    (-0.1, 0.1, -1.4, 1.4, -1.0, 1.0),     # Tail6
+    (-0.1, 0.1, -0.7, 1.1, -0.9, 0.8),     # Tail7
+    (-0.1, 0.1, -1.1, 0.5, -0.1, 0.1),     # Mouth
+)
+
+
+def joint_limits():
+    """(min, max) float32 arrays of shape (N_POSE, 3); ears unbounded."""
+    import numpy as np
+    lo = np.full((N_POSE, 3), -np.inf, np.float32)
+    hi = np.full((N_POSE, 3), np.inf, np.float32)
+    rows = np.asarray(_JOINT_LIMIT_ROWS, np.float32).reshape(-1, 3, 2)
+    lo[: rows.shape[0]] = rows[:, :, 0]
+    hi[: rows.shape[0]] = rows[:, :, 1]
+    return lo, hi

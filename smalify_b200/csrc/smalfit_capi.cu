@@ -57,6 +57,7 @@ struct smalfit_ctx {
     // mutable target buffers (Workspace holds const views)
     uint8_t* sil = nullptr; float* kp_target = nullptr; uint8_t* vis = nullptr;
     float* region_tsum = nullptr; float* inv_window = nullptr; float* gmask = nullptr; float* rmask = nullptr;
+    float* limit_buf = nullptr;      // [2][102] joint-rotation limits (min, max)
     bool targets_set = false;
     DevPool pool;
     std::string error;
@@ -244,7 +245,9 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
     w.dvs = P.alloc<float>(N * V * 3, true);
     w.gJ = P.alloc<float>(N * NJ * 3, true);
     w.gls = P.alloc<float>(N * NLS, true);
-    w.frame_loss = P.alloc<float>(N * 4, true);
+    w.frame_loss = P.alloc<float>(N * 8, true);
+    h->limit_buf = P.alloc<float>(2 * (NJ - 1) * 3, true);
+    w.gfocal_frame = P.alloc<float>(N * 2, true);
     w.beta_partial = P.alloc<float>(N * n_blocks * NBETA, true);
     h->sil = P.alloc<uint8_t>(N * SS, true);
     h->kp_target = P.alloc<float>(N * NKP * 2, true);
@@ -326,6 +329,29 @@ int smalfit_set_masks(smalfit_t h, const float* global_mask, const float* rotati
     cudaError_t e = cudaMemcpy(h->gmask, global_mask, 3 * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->rmask, rotation_mask, (NJ - 1) * 3 * sizeof(float), cudaMemcpyHostToDevice);
     return check_cuda(h, e, "smalfit_set_masks");
+}
+
+int smalfit_set_focal(smalfit_t h, const float* focal, float* grad_focal) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!focal && grad_focal) return fail(h, SMALFIT_EINVAL, "smalfit_set_focal: a gradient needs the parameter");
+    h->w.focal = focal;
+    h->w.gfocal = grad_focal;
+    return SMALFIT_OK;
+}
+
+int smalfit_set_joint_limits(smalfit_t h, const float* min_limits, const float* max_limits) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!min_limits != !max_limits) return fail(h, SMALFIT_EINVAL, "smalfit_set_joint_limits: give both limits or neither");
+    if (!min_limits) { h->w.limit_min = h->w.limit_max = nullptr; return SMALFIT_OK; }
+    const int n = (NJ - 1) * 3;
+    for (int i = 0; i < n; ++i)
+        if (!(min_limits[i] <= max_limits[i])) return fail(h, SMALFIT_EINVAL, "smalfit_set_joint_limits: min > max (or NaN) at %d", i);
+    cudaSetDevice(h->device);
+    cudaError_t e = cudaMemcpy(h->limit_buf, min_limits, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->limit_buf + n, max_limits, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return check_cuda(h, e, "smalfit_set_joint_limits");
+    h->w.limit_min = h->limit_buf; h->w.limit_max = h->limit_buf + n;
+    return SMALFIT_OK;
 }
 
 int smalfit_set_windows(smalfit_t h, const int32_t* fpw, int n) {

@@ -150,6 +150,7 @@ frame_forward_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, 
     const float* vs = w.v_shaped + (size_t)slot * m.V * 3;
 
     frame_pose_forward(S, m, w, p, fr, slot);
+    const float focal = w.focal ? *w.focal : CAM_F;
 
     // sparse linear-blend skinning + camera
     float4* ndc = w.ndc + (size_t)fr * m.Vp;
@@ -171,7 +172,7 @@ frame_forward_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, 
         vw[v * 3 + 0] = ax; vw[v * 3 + 1] = ay; vw[v * 3 + 2] = az;
         const float X = ax + S.tr[0], Y = ay + S.tr[1], Z = az + S.tr[2];
         float xn, yn, zv;
-        camera_fwd(X, Y, Z, xn, yn, zv);
+        camera_fwd(X, Y, Z, xn, yn, zv, focal);
         ndc[v] = make_float4(xn, yn, zv, 0.f);
         if (verts_out) {
             float* o = verts_out + ((size_t)blockIdx.x * m.V + v) * 3;
@@ -195,11 +196,11 @@ frame_forward_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, 
     __syncthreads();
 
     // keypoint projection + masked MSE (smal_fitter.py:140-144) and its gradient
-    float lk = 0.f;
+    float lk = 0.f, gf = 0.f;
     if (tid < NKP) {
         const int j = c_sk.kp_joint[tid];
         float xn, yn, zv, row, col;
-        camera_fwd(S.mj[j * 3 + 0], S.mj[j * 3 + 1], S.mj[j * 3 + 2], xn, yn, zv);
+        camera_fwd(S.mj[j * 3 + 0], S.mj[j * 3 + 1], S.mj[j * 3 + 2], xn, yn, zv, focal);
         const float half = 0.5f * (float)(w.S - 1);
         screen_fwd(xn, yn, half, row, col);
         w.kp_proj[(size_t)fr * NKP * 2 + tid * 2 + 0] = row;
@@ -211,11 +212,13 @@ frame_forward_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, 
             const float scale = wt.j2d * w.inv_window[fr] * (1.f / (float)(NKP * 2));
             lk = scale * (dr * dr + dc * dc);
             const float gyn = -half * 2.f * scale * dr, gxn = -half * 2.f * scale * dc;
-            camera_bwd(xn, yn, zv, gxn, gyn, g0, g1, g2);
+            camera_bwd(xn, yn, zv, gxn, gyn, g0, g1, g2, focal);
+            gf = camera_bwd_focal(xn, yn, gxn, gyn, focal);
         }
         S.gkp[tid * 3 + 0] = g0; S.gkp[tid * 3 + 1] = g1; S.gkp[tid * 3 + 2] = g2;
     }
     const float lsum = block_sum(lk, S.red);
+    if (w.gfocal) { gf = block_sum(gf, S.red); if (tid == 0) w.gfocal_frame[fr * 2 + 0] = gf; }
     if (tid < NMJ) {
         float g0 = 0.f, g1 = 0.f, g2 = 0.f;
         for (int k = 0; k < NKP; ++k)
@@ -223,7 +226,7 @@ frame_forward_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, 
         float* gj = w.gjoint + (size_t)fr * NMJ * 3 + tid * 3;
         gj[0] = g0; gj[1] = g1; gj[2] = g2;
     }
-    if (tid == 0) w.frame_loss[fr * 4 + 0] = lsum;
+    if (tid == 0) w.frame_loss[fr * 8 + 0] = lsum;
 }
 
 void launch_frame_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n,
@@ -538,7 +541,8 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
     const float4* ndc = w.ndc + (size_t)fr * m.Vp;
     const float* fg = w.face_grad + (size_t)fr * m.Fp * 8;
     float* dvs = w.dvs + (size_t)fr * m.V * 3;
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, gf = 0.f;
+    const float focal = w.focal ? *w.focal : CAM_F;
     for (int v = tid; v < m.V; v += blockDim.x) {
         float g0 = 0.f, g1 = 0.f, g2 = 0.f;
         if (use_sil) {
@@ -549,7 +553,8 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
                 gx += q.x; gy += q.y;
             }
             const float4 nd = ndc[v];
-            camera_bwd(nd.x, nd.y, nd.z, gx, gy, g0, g1, g2);
+            camera_bwd(nd.x, nd.y, nd.z, gx, gy, g0, g1, g2, focal);
+            gf += camera_bwd_focal(nd.x, nd.y, gx, gy, focal);
         }
         t0 += g0; t1 += g1; t2 += g2;
         for (int e = m.mjT_ptr[v]; e < m.mjT_ptr[v + 1]; ++e) {
@@ -573,6 +578,7 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
     }
     // dL/dtrans = sum_v (raster part) + sum_j dL/djoint_j   (verts + trans, joints + trans)
     t0 = block_sum(t0, S.red); t1 = block_sum(t1, S.red); t2 = block_sum(t2, S.red);
+    if (w.gfocal) { gf = block_sum(gf, S.red); if (tid == 0) w.gfocal_frame[fr * 2 + 1] = gf; }
     if (tid == 0) {
         float a0 = t0, a1 = t1, a2 = t2;
         for (int j = 0; j < NMJ; ++j) { a0 += S.gj[j * 3]; a1 += S.gj[j * 3 + 1]; a2 += S.gj[j * 3 + 2]; }
@@ -666,15 +672,25 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
             S.thg[tid] += 2.f * wt.splay * q;
         }
     }
+    // joint-limit hinge (the term the reference keeps commented out at smal_fitter.py:146-151, limits of
+    // priors/joint_limits_prior.py): w_limit * mean over (B, 34, 3) of max(q - hi, 0) + max(lo - q, 0)
+    float llimit = 0.f;
+    if (wt.limit > 0.f && w.limit_min && tid >= 3 && tid < NJ * 3) {
+        const float q = S.theta[tid], lo = w.limit_min[tid - 3], hi = w.limit_max[tid - 3];
+        const float cl = wt.limit * invw * (1.f / (float)((NJ - 1) * 3));
+        llimit = cl * (fmaxf(q - hi, 0.f) + fmaxf(lo - q, 0.f));
+        S.thg[tid] += cl * ((q > hi ? 1.f : 0.f) - (q < lo ? 1.f : 0.f));
+    }
     lpose = block_sum(lpose, S.red);
     lsplay = block_sum(lsplay, S.red);
+    llimit = block_sum(llimit, S.red);
     float lsil = 0.f;
     if (use_sil) {
         const int R4 = w.tiles_x * w.tiles_y * REGIONS_PER_TILE * REGION_H;
         for (int r = tid; r < R4; r += blockDim.x) lsil += w.region_l1[(size_t)fr * R4 + r];
         lsil = block_sum(lsil, S.red) * wt.sil * invw / ((float)w.S * (float)w.S);
     }
-    if (tid == 0) { w.frame_loss[fr * 4 + 1] = lpose; w.frame_loss[fr * 4 + 2] = lsplay; w.frame_loss[fr * 4 + 3] = lsil; }
+    if (tid == 0) { w.frame_loss[fr * 8 + 1] = lpose; w.frame_loss[fr * 8 + 2] = lsplay; w.frame_loss[fr * 8 + 3] = lsil; w.frame_loss[fr * 8 + 4] = llimit; }
     if (tid < 3) { if (g.glob) g.glob[fr * 3 + tid] = S.thg[tid] * w.gmask[tid]; }
     else if (tid < NJ * 3) { if (g.joint) g.joint[(size_t)fr * (NJ - 1) * 3 + (tid - 3)] = S.thg[tid] * w.rmask[tid - 3]; }
 }
@@ -783,22 +799,33 @@ finalize_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, int n_fr
     if (!s_last) return;
     __threadfence();
     // loss terms: fixed-order sums over the frames of the range and over the slots
-    float lk = 0.f, lp = 0.f, lsp = 0.f, lsil = 0.f, lb = 0.f;
+    float lk = 0.f, lp = 0.f, lsp = 0.f, lsil = 0.f, lb = 0.f, ll = 0.f;
     for (int f = tid; f < n_frames; f += blockDim.x) {
         const int fr = frame0 + f;
-        lk += w.frame_loss[fr * 4 + 0];
-        lp += w.frame_loss[fr * 4 + 1];
-        lsp += w.frame_loss[fr * 4 + 2];
-        if (wt.sil > 0.f) lsil += w.frame_loss[fr * 4 + 3];
+        lk += w.frame_loss[fr * 8 + 0];
+        lp += w.frame_loss[fr * 8 + 1];
+        lsp += w.frame_loss[fr * 8 + 2];
+        if (wt.sil > 0.f) lsil += w.frame_loss[fr * 8 + 3];
+        ll += w.frame_loss[fr * 8 + 4];
     }
     for (int q = tid; q < w.n_shapes; q += blockDim.x) lb += ((volatile float*)w.slot_loss)[q];
     lk = block_sum(lk, red); lp = block_sum(lp, red); lsp = block_sum(lsp, red); lsil = block_sum(lsil, red);
     lb = block_sum(lb, red);
+    ll = block_sum(ll, red);
+    if (w.gfocal) {          // dL/dfocal: fixed-order sum of the per-frame partials
+        float a = 0.f;
+        for (int f = tid; f < n_frames; f += blockDim.x) {
+            const int fr = frame0 + f;
+            a += ((wt.j2d > 0.f) ? w.gfocal_frame[fr * 2 + 0] : 0.f) + ((wt.sil > 0.f) ? w.gfocal_frame[fr * 2 + 1] : 0.f);
+        }
+        a = block_sum(a, red);
+        if (tid == 0) *w.gfocal = a;
+    }
     if (tid == 0) {
         if (loss_terms) {
             loss_terms[0] = lk; loss_terms[1] = lsil; loss_terms[2] = lb; loss_terms[3] = lp;
-            loss_terms[4] = 0.f; loss_terms[5] = lsp; loss_terms[6] = 0.f;
-            loss_terms[7] = lk + lsil + lb + lp + lsp;
+            loss_terms[4] = ll; loss_terms[5] = lsp; loss_terms[6] = 0.f;
+            loss_terms[7] = lk + lsil + lb + lp + lsp + ll;
         }
         *w.finalize_ticket = 0u;
     }

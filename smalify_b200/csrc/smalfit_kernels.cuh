@@ -89,7 +89,7 @@ struct Workspace {
     float* dvs;                 // [N][V*3]  per-frame dL/dv_shaped
     float* gJ;                  // [N][105]  per-frame dL/dJ(rest joints)
     float* gls;                 // [N][6]    per-frame dL/dlogscale
-    float* frame_loss;          // [N][4]    kp, pose, splay, silhouette
+    float* frame_loss;          // [N][8]    kp, pose, splay, silhouette, joint limit, -, -, -
     float* beta_partial;        // [n_shapes][n_blocks][20]
     // targets
     const uint8_t* sil;         // [N][S*S]
@@ -97,6 +97,11 @@ struct Workspace {
     const uint8_t* vis;         // [N][25]
     const float* region_tsum;   // [N][tiles*32*4] per region and pixel row: sum of the target mask
     const float* inv_window;    // [N] 1 / frames_per_window
+    const float* focal;         // [1] focal factor of the camera (NULL: the reference's fixed 1/tan(30 deg))
+    float* gfocal;              // [1] dL/dfocal of the last loss_grad call (NULL: not wanted)
+    float* gfocal_frame;        // [N][2] per-frame partials: keypoint term, silhouette term
+    const float* limit_min;     // [102] joint-rotation limits (NULL: term disabled, as in the reference)
+    const float* limit_max;     // [102]
     const float* gmask;         // [3]
     const float* rmask;         // [102]
     float* slot_loss;           // [N] shape-prior loss per shape slot

@@ -230,19 +230,22 @@ SMF_HD void chain_bwd_push(const ChainFwd& c, const ChainBwd& b, int i, int p) {
 // ---------------------------------------------------------------------------
 // Camera
 // ---------------------------------------------------------------------------
-SMF_HD void camera_fwd(float X, float Y, float Z, float& xn, float& yn, float& zv) {
+// f: focal factor of the NDC projection (1/tan(fov/2); the reference's fixed 60 degree camera = CAM_F).
+SMF_HD void camera_fwd(float X, float Y, float Z, float& xn, float& yn, float& zv, float f = CAM_F) {
     zv = CAM_DIST - Z;
     const float iz = 1.f / zv;
-    xn = -CAM_F * X * iz;
-    yn = CAM_F * Y * iz;
+    xn = -f * X * iz;
+    yn = f * Y * iz;
 }
 // (gx, gy) = dL/d(x_ndc, y_ndc) -> dL/d(X,Y,Z); z_view carries no gradient.
-SMF_HD void camera_bwd(float xn, float yn, float zv, float gx, float gy, float& gX, float& gY, float& gZ) {
+SMF_HD void camera_bwd(float xn, float yn, float zv, float gx, float gy, float& gX, float& gY, float& gZ, float f = CAM_F) {
     const float iz = 1.f / zv;
-    gX = -CAM_F * iz * gx;
-    gY = CAM_F * iz * gy;
+    gX = -f * iz * gx;
+    gY = f * iz * gy;
     gZ = (xn * gx + yn * gy) * iz;
 }
+// dL/df of one projected point: x_ndc and y_ndc are linear in f
+SMF_HD float camera_bwd_focal(float xn, float yn, float gx, float gy, float f) { return (xn * gx + yn * gy) / f; }
 // keypoint pixel (row, col) from NDC, transform_points_screen with (S-1)/2
 SMF_HD void screen_fwd(float xn, float yn, float half, float& row, float& col) {
     col = half * (1.f - xn);

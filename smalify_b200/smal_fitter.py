@@ -61,7 +61,7 @@ class _LossGradFn(torch.autograd.Function):
     fitter's workspace); backward: scale the stashed gradients by grad_output."""
 
     @staticmethod
-    def forward(ctx, fitter, frame0, n, weights, betas, lbs, glob, joint, trans):
+    def forward(ctx, fitter, frame0, n, weights, betas, lbs, glob, joint, trans, focal=None):
         terms = torch.empty(8, device=glob.device, dtype=torch.float32)
         ws = fitter._grad_ws
         lbs_dev = lbs if fitter.use_unity_prior else fitter._zero_logscale
@@ -74,6 +74,7 @@ class _LossGradFn(torch.autograd.Function):
         # shared-shape gradients are overwritten by the next window: keep this window's copy
         ctx.g_betas = ws["betas"].clone()
         ctx.g_lbs = ws["log_beta_scales"].clone()
+        ctx.g_focal = fitter._focal_grad.clone() if focal is not None else None
         ctx.mark_non_differentiable(terms)
         loss = terms[_cabi.L_TOTAL].clone()
         ctx.terms = terms
@@ -106,6 +107,7 @@ class _LossGradFn(torch.autograd.Function):
                 out.append(g)
             else:
                 out.append(None)
+        out.append(grad_loss * ctx.g_focal if (len(need) > 9 and need[9] and ctx.g_focal is not None) else None)
         return tuple(out)
 
 
@@ -137,7 +139,7 @@ class SMALFitter(nn.Module):
 
     def __init__(self, device, data_batch, batch_size, shape_family, use_unity_prior,
                  constants: model_io.SmalConstants | None = None, data_root: str | None = None,
-                 resident_targets: bool = True, per_frame_shapes: bool = False):
+                 resident_targets: bool = True, per_frame_shapes: bool = False, joint_limits=None, focal=None):
         super().__init__()
         self.rgb_imgs, self.sil_imgs, self.target_joints, self.target_visibility = data_batch
         self.target_visibility = self.target_visibility.long()
@@ -196,6 +198,20 @@ class SMALFitter(nn.Module):
         self._handle = _cabi.Handle(constants, self.device.index, n, self.image_size, self.use_unity_prior)
         if self.per_frame_shapes:
             self._handle.check(self._handle.lib.smalfit_set_per_frame_shapes(self._handle.h, 1), "smalfit_set_per_frame_shapes")
+        # extension: the joint-limit term the reference keeps commented out (smal_fitter.py:77-79,
+        # 146-151).  None = off (reference behaviour: w_limit is ignored); True = the reference's own table
+        # (constants.joint_limits()); or a (min, max) pair of (34, 3) arrays.
+        self.joint_limits = None
+        self.set_joint_limits(joint_limits)
+        # extension: a focal parameter.  None = the reference's fixed 60-degree camera and no sixth
+        # parameter; a float registers `self.focal` (frozen until the caller sets focal.requires_grad = True, like
+        # the stage loop does for the other tensors) and dL/dfocal is produced with the other gradients.
+        self.focal = None
+        self._focal_grad = torch.zeros(1, device=dev)
+        if focal is not None:
+            self.focal = nn.Parameter(torch.tensor([float(focal)], device=dev), requires_grad=False)
+            self._handle.check(self._handle.lib.smalfit_set_focal(self._handle.h, _ptr(self.focal), _ptr(self._focal_grad)),
+                               "smalfit_set_focal")
         ns = n if self.per_frame_shapes else 1
         self._grad_ws = {
             "betas": torch.zeros(ns * 20, device=dev).view(self.betas.shape),
@@ -285,11 +301,13 @@ class SMALFitter(nn.Module):
         else:
             self._upload_targets(a, n)         # the per-call H2D copy of smal_fitter.py:118-120
         loss, terms = _LossGradFn.apply(self, a, n, [float(w) for w in weights], self.betas, self.log_beta_scales,
-                                        self.global_rotation, self.joint_rotations, self.trans)
-        w_j2d, w_reproj, w_betas, w_pose, _w_limit, w_splay = [float(w) for w in weights]
+                                        self.global_rotation, self.joint_rotations, self.trans, self.focal)
+        w_j2d, w_reproj, w_betas, w_pose, w_limit, w_splay = [float(w) for w in weights]
         objs = {}
         if w_j2d > 0:
             objs["joint"] = terms[_cabi.L_JOINT]
+        if w_limit > 0 and self.joint_limits is not None:
+            objs["limit"] = terms[_cabi.L_LIMIT]
         if w_pose > 0:
             objs["pose"] = terms[_cabi.L_POSE]
         if w_splay > 0:
@@ -299,6 +317,19 @@ class SMALFitter(nn.Module):
         if w_reproj > 0:
             objs["sil_reproj"] = terms[_cabi.L_SIL]
         return loss, objs
+
+    def set_joint_limits(self, limits):
+        h = self._handle
+        fp = ctypes.POINTER(ctypes.c_float)
+        if limits is None or limits is False:
+            h.check(h.lib.smalfit_set_joint_limits(h.h, None, None), "smalfit_set_joint_limits")
+            self.joint_limits = None
+            return
+        lo, hi = K.joint_limits() if limits is True else limits
+        lo = np.ascontiguousarray(np.asarray(lo, np.float32).reshape(K.N_POSE, 3))
+        hi = np.ascontiguousarray(np.asarray(hi, np.float32).reshape(K.N_POSE, 3))
+        h.check(h.lib.smalfit_set_joint_limits(h.h, lo.ctypes.data_as(fp), hi.ctypes.data_as(fp)), "smalfit_set_joint_limits")
+        self.joint_limits = (lo, hi)
 
     def get_temporal(self, w_temp):
         """smal_fitter.py:177-190: returns (joint_loss, global_loss, trans_loss)."""
@@ -472,6 +503,8 @@ class FusedFit:
 
     def step(self, weights, w_temp, lr, train=(1, 1, 1, 1, 1), use_graph: bool = False):
         """Returns nothing; self.terms / self.temporal_terms hold the loss terms on the device."""
+        if self.f.focal is not None and self.f.focal.requires_grad:
+            raise NotImplementedError("FusedFit keeps the focal parameter fixed; train it through SMALFitter.forward/backward")
         self.step_count += 1
         f = self.f
         f._sync_masks()

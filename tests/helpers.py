@@ -36,12 +36,16 @@ def perturbed_params(m: O.OracleModel, gt: dict, seed: int, scale: float = 1.0) 
         trans=(gt["trans"] + 0.03 * scale * torch.randn(n, 3, generator=g)).to(dt))
 
 
-def oracle_loss_and_grads(m, p: O.FitParams, data, batch_range, weights, S, w_temp=None):
+def oracle_loss_and_grads(m, p: O.FitParams, data, batch_range, weights, S, w_temp=None, joint_limits=None, focal=None):
+    """focal: optional 0-d tensor; its gradient is returned under the key 'focal'."""
     rgb, sil, joints, vis = data
     for t in p.tensors():
         t.requires_grad_(True)
         t.grad = None
-    loss, objs = O.fitter_forward(m, p, sil, joints, vis, batch_range, weights, S)
+    if focal is not None:
+        focal.requires_grad_(True)
+        focal.grad = None
+    loss, objs = O.fitter_forward(m, p, sil, joints, vis, batch_range, weights, S, joint_limits=joint_limits, focal=focal)
     if w_temp is not None:
         jl, gl, tl = O.temporal_terms(p, w_temp)
         loss = loss + jl + gl + tl
@@ -50,6 +54,9 @@ def oracle_loss_and_grads(m, p: O.FitParams, data, batch_range, weights, S, w_te
              for k in ("betas", "log_beta_scales", "global_rotation", "joint_rotations", "trans")}
     for t in p.tensors():
         t.requires_grad_(False)
+    if focal is not None:
+        grads["focal"] = focal.grad.clone()
+        focal.requires_grad_(False)
     return float(loss), {k: float(v) for k, v in objs.items()}, grads
 
 

@@ -126,6 +126,72 @@ def test_tile_rasteriser_paths_agree(constants, fitter, oracle64, seq, knobs, mo
             assert H.rel_err(gb[k], ga[k].double().cpu()) < 2e-5, (name, k)
 
 
+def test_joint_limit_term(constants, oracle64, seq):
+    """Row 8f-4: the optional joint-limit hinge (reference: commented out at smal_fitter.py:146-151, limits of
+    priors/joint_limits_prior.py) against the oracle, value and gradient, with many joints past their limits;
+    off by default: w_limit is then ignored exactly as the reference ignores it."""
+    from smalify_b200.smal_fitter import SMALFitter
+    data, gt = seq
+    f = SMALFitter("cuda", data, N_SMALL, 1, True, constants=constants, joint_limits=True)
+    limits = K.joint_limits()
+    p = H.perturbed_params(oracle64, gt, seed=9)
+    gen = torch.Generator().manual_seed(4)
+    p.joint_rotations = p.joint_rotations + 0.8 * torch.randn(p.joint_rotations.shape, generator=gen, dtype=p.joint_rotations.dtype)
+    for weights in (STAGE1, (0.0, 0.0, 0.0, 0.0, 100.0, 0.0)):
+        lo, objs_o, go = H.oracle_loss_and_grads(oracle64, p, data, range(N_SMALL), weights, S_SMALL, joint_limits=limits)
+        assert objs_o["limit"] > 0
+        H.load_params_into(f, p)
+        for t in f.parameters():
+            t.grad = None
+            t.requires_grad_(True)
+        loss, objs = f(list(range(N_SMALL)), weights, 1)
+        loss.backward()
+        assert abs(float(objs["limit"]) - objs_o["limit"]) <= 2e-6 * objs_o["limit"]
+        assert abs(float(loss) - lo) <= 2e-5 * abs(lo)
+        assert H.rel_err(f.joint_rotations.grad, go["joint_rotations"]) < 1e-4
+    # default fitter: same weights, no limit term
+    f.set_joint_limits(None)
+    loss2, objs2 = f(list(range(N_SMALL)), STAGE1, 1)
+    lo2, objs_o2, _ = H.oracle_loss_and_grads(oracle64, p, data, range(N_SMALL), STAGE1, S_SMALL)
+    assert "limit" not in objs2 and abs(float(loss2) - lo2) <= 2e-5 * abs(lo2)
+
+
+def test_focal_parameter(constants, oracle64, seq):
+    """Row 8f-4: a focal parameter (the reference camera is fixed at fov 60 degrees, p3d_renderer.py:22-23).
+    Silhouettes, keypoints, loss and every gradient including dL/dfocal against the oracle at a non-default
+    focal; dL/dfocal also against a central finite difference of the GPU loss."""
+    from smalify_b200.smal_fitter import SMALFitter
+    data, gt = seq
+    f0 = 1.55
+    f = SMALFitter("cuda", data, N_SMALL, 1, True, constants=constants, focal=f0)
+    assert len(list(f.parameters())) == 6 and not f.focal.requires_grad
+    f.focal.requires_grad_(True)
+    p = H.perturbed_params(oracle64, gt, seed=5)
+    for weights in (STAGE1, STAGE0):
+        foc = torch.tensor(f0, dtype=torch.float64)
+        lo, objs_o, go = H.oracle_loss_and_grads(oracle64, p, data, range(N_SMALL), weights, S_SMALL, focal=foc)
+        H.load_params_into(f, p)
+        for t in f.parameters():
+            t.grad = None
+        loss, objs = f(list(range(N_SMALL)), weights, 1)
+        loss.backward()
+        assert abs(float(loss) - lo) <= 2e-5 * abs(lo), (float(loss), lo)
+        for k in ("global_rotation", "trans", "joint_rotations"):
+            assert H.rel_err(getattr(f, k).grad, go[k]) < 1e-4, k
+        gf = float(f.focal.grad)
+        assert abs(gf - float(go["focal"])) <= 1e-4 * abs(float(go["focal"])) + 1e-5, (gf, float(go["focal"]))
+    # the silhouette the backward differentiates really is rendered with this focal
+    alpha, kp = f.render()
+    theta = torch.cat([p.global_rotation[:, None], p.joint_rotations], 1)
+    vo, jo, _ = O.smal_forward(oracle64, p.betas.expand(N_SMALL, 20), theta, p.log_beta_scales.expand(N_SMALL, 6))
+    ao = O.render_silhouettes(oracle64, vo + p.trans[:, None], S_SMALL, focal=f0)
+    assert float((alpha.cpu().double() - ao).abs().mean()) < 1e-5
+    kpo = O.project_points_screen((jo + p.trans[:, None])[:, list(O.CANONICAL)], S_SMALL, focal=f0)
+    assert (kp.cpu().double() - kpo).abs().max() < 2e-4
+    # default construction: five parameters, reference camera
+    assert len(list(SMALFitter("cuda", data, N_SMALL, 1, True, constants=constants).parameters())) == 5
+
+
 def test_windows_and_temporal(fitter, oracle64, seq):
     data, gt = seq
     p = H.perturbed_params(oracle64, gt, seed=9)

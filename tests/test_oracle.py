@@ -160,3 +160,38 @@ def test_temporal_and_losses_shapes(constants, oracle64):
     jl, gl, tl = O.temporal_terms(p, 100.0)
     assert float(jl) == 0.0 and float(gl) == 0.0
     assert abs(float(tl) - 100.0 * (0.01 / 3 + 0.04 / 3)) < 1e-12
+
+
+def test_joint_limit_term_matches_reference_golden(constants):
+    """Row 8f-4: the limits table and the hinge of priors/joint_limits_prior.py (golden made by
+    tests/golden/make_limits_golden.py from the unmodified reference) against constants.joint_limits() and
+    the oracle's restatement of the commented-out term (smal_fitter.py:146-151)."""
+    import numpy as np
+    import torch
+    from oracle import smal_oracle as O
+    from smalify_b200 import constants as K
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "joint_limits_golden.npz"))
+    lo, hi = K.joint_limits()
+    assert lo.shape == hi.shape == (K.N_POSE, 3)
+    assert np.array_equal(lo[:32].reshape(-1), g["min_values"].astype(np.float32))
+    assert np.array_equal(hi[:32].reshape(-1), g["max_values"].astype(np.float32))
+    assert np.all(np.isinf(lo[32:])) and np.all(np.isinf(hi[32:]))           # ears: unbounded
+    # oracle term on the golden batch (ears at zero: no contribution)
+    m = O.OracleModel.from_constants(constants, torch.float64)
+    B = g["x"].shape[0]
+    p = O.FitParams.initial(m, B, K.GLOBAL_ROT_INIT)
+    q = torch.zeros(B, K.N_POSE, 3, dtype=torch.float64)
+    q[:, :32] = torch.from_numpy(g["x"]).reshape(B, 32, 3)
+    p.joint_rotations = q
+    w = (0.0, 0.0, 0.0, 0.0, 7.0, 0.0)
+    sil = torch.zeros(B, 1, 16, 16)
+    total, objs = O.fitter_forward(m, p, sil, torch.zeros(B, 25, 2), torch.zeros(B, 25), range(B), w, 16,
+                                   joint_limits=(lo.astype(np.float64), hi.astype(np.float64)))
+    want = 7.0 * g["hinge"].sum() / (B * K.N_POSE * 3)       # torch.mean over (B, 34, 3)
+    lo32, hi32 = g["min_values"], g["max_values"]
+    # (float32 table vs the reference's float64 literals: 1e-7 relative)
+    assert abs(float(objs["limit"]) - want) < 1e-6 * abs(want)
+    assert set(objs) == {"limit"}
+    # without limits the weight is ignored, as in the reference
+    total0, objs0 = O.fitter_forward(m, p, sil, torch.zeros(B, 25, 2), torch.zeros(B, 25), range(B), w, 16)
+    assert objs0 == {} and float(total0) == 0.0
