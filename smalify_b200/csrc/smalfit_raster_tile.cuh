@@ -43,6 +43,7 @@ struct RtSmem {
     unsigned plane[RT_WARPS][RT_PLANE];
     float4 stage[RT_WARPS][2][RT_BLK * 4];
     float l1[RT_PIX];
+    float pl[RT_PIX];                    // product of (1 - p) per pixel, direct (plane product) or listed (selection)
     unsigned list_off[RT_PIX];           // listed pixels: list offset, then (after P2) the depth threshold
     unsigned short list_cnt[RT_PIX];     // listed pixels: slots, then (after P2) the tie face id
     unsigned short active[RT_PIX];
@@ -74,6 +75,11 @@ __device__ __forceinline__ void l2_discard_line(const void* p) {
     asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
 }
 constexpr int RT_LIST_ALIGN = 16;               // entries per 128-byte line
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Face id of the slot-th (0-based) entry of the tile list whose rectangle covers pixel (lx, ly): list
 // slots of a pixel are in tile-list order, so this recovers the face behind a slot (ties only).
@@ -101,8 +107,9 @@ __device__ unsigned rt_slot_to_fid(const uint4* __restrict__ pool, int len, int 
 // rejected pairs carry key 0xffffffff and m = 1.  Slots are in face order, so "lower face id first" among
 // equal depths is "lower slot first".  Returns the threshold: selected <=> key < tkey || (key == tkey &&
 // slot <= tslot); tkey = 0xffffffff when every valid fragment is selected, tslot = -1 when no tie is cut.
-__device__ float rt_select(const uint2* __restrict__ L, int c, int lane, unsigned* scratch /* >= RT_SELCAP words */,
-                           unsigned& tkey, int& tslot, bool& capped) {
+__device__ __forceinline__ float rt_select(const uint2* __restrict__ L, const uint2* Ls /* shared-memory copy when c <= RT_SELCAP */,
+                                           int c, int lane, unsigned* scratch /* >= RT_SELCAP words */,
+                                           unsigned& tkey, int& tslot, bool& capped) {
     constexpr int NR = RT_SELCAP / 32;
     const unsigned ltmask = lanemask_lt();
     unsigned kr[NR];
@@ -118,7 +125,7 @@ __device__ float rt_select(const uint2* __restrict__ L, int c, int lane, unsigne
             for (int r = 0; r < NR; ++r) {
                 const int i = r * 32 + lane;
                 kr[r] = 0xffffffffu; mr[r] = 1.f;
-                if (i < c) { const uint2 e = L[i]; kr[r] = e.x; mr[r] = __uint_as_float(e.y); }
+                if (i < c) { const uint2 e = Ls[i]; kr[r] = e.x; mr[r] = __uint_as_float(e.y); }
                 pr *= mr[r];
                 if (kr[r] != 0xffffffffu) { lo = min(lo, kr[r]); hi = max(hi, kr[r]); ++nv; }
             }
@@ -183,7 +190,8 @@ __device__ float rt_select(const uint2* __restrict__ L, int c, int lane, unsigne
     if (!exact) {
         t = lo;
         int clt = 0, cle = 0;
-        for (int i = lane; i < c; i += 32) { const unsigned k = L[i].x; clt += (k < t); cle += (k <= t); }
+        const uint2* Lr = small ? Ls : L;
+        for (int i = lane; i < c; i += 32) { const unsigned k = Lr[i].x; clt += (k < t); cle += (k <= t); }
         clt = __reduce_add_sync(0xffffffffu, clt);
         cle = __reduce_add_sync(0xffffffffu, cle);
         if (cle > RAST_K) {
@@ -191,7 +199,7 @@ __device__ float rt_select(const uint2* __restrict__ L, int c, int lane, unsigne
             int need = RAST_K - clt;
             for (int base = 0; base < c; base += 32) {
                 const int i = base + lane;
-                const unsigned bal = __ballot_sync(0xffffffffu, i < c && L[i].x == t);
+                const unsigned bal = __ballot_sync(0xffffffffu, i < c && Lr[i].x == t);
                 const int n = __popc(bal);
                 if (need <= n) { ts = base + (int)__fns(bal, 0u, need); break; }
                 need -= n;
@@ -466,30 +474,62 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
             }
             __syncthreads();
 
-            // ---- P2: listed pixels of this pass, one warp each
+            // ---- P2a: the direct pixels' products leave the planes (fixed warp order) ...
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int row = wid + RT_WARPS * k;
+                const int idx = row * RT_PITCH + lane;
+                if (sm.cls[row * TILE_W + lane] != RT_CLS_DIRECT) continue;
+                float P = __uint_as_float(sm.plane[0][idx]);
+#pragma unroll
+                for (int q = 1; q < RT_WARPS; ++q) P *= __uint_as_float(sm.plane[q][idx]);
+                sm.pl[row * TILE_W + lane] = P;
+            }
+            __syncthreads();
+
+            // ---- P2: ... and every warp's plane becomes its two staging buffers for the listed pixels of this pass:
+            //      one warp per pixel, the next pixel's list streaming in (cp.async) while this one is selected
             {
                 const unsigned na = sm.n_active;
                 const uint2* list = ts.list + (size_t)blockIdx.x * ts.list_stride;
-                unsigned* scratch = reinterpret_cast<unsigned*>(sm.stage[wid][0]);     // the stage is idle here
+                unsigned* scratch = reinterpret_cast<unsigned*>(sm.stage[wid][0]);     // the TMA stage is idle here
+                uint2* stg = reinterpret_cast<uint2*>(plane);                          // 2 x RT_SELCAP entries
+                auto stage_px = [&](unsigned a, int buf) {
+                    const int px = (int)sm.active[a];
+                    const int c = (int)sm.list_cnt[px];
+                    if (c <= RT_SELCAP) {
+                        const uint2* src = list + sm.list_off[px];
+                        for (int ch = lane; ch * 2 < c; ch += 32) cp_async16(stg + buf * RT_SELCAP + ch * 2, src + ch * 2);
+                    }
+                };
+                int buf = 0;
+                if ((unsigned)wid < na) stage_px((unsigned)wid, 0);
+                cp_async_commit();
                 for (unsigned a = (unsigned)wid; a < na; a += RT_WARPS) {
+                    if (a + RT_WARPS < na) stage_px(a + RT_WARPS, buf ^ 1);
+                    cp_async_commit();
+                    cp_async_wait<1>();              // everything but the group just committed has landed
+                    __syncwarp();
                     const int px = (int)sm.active[a];
                     const int c = (int)sm.list_cnt[px];
                     unsigned tk, tf = 0xffffu;
                     int tslot;
                     bool capped;
-                    const float P = rt_select(list + sm.list_off[px], c, lane, scratch, tk, tslot, capped);
+                    const float P = rt_select(list + sm.list_off[px], stg + buf * RT_SELCAP, c, lane, scratch, tk, tslot, capped);
                     for (int ln = lane * RT_LIST_ALIGN; ln < c; ln += 32 * RT_LIST_ALIGN) l2_discard_line(list + sm.list_off[px] + ln);   // dead from here on
                     if (tslot >= 0)
                         tf = rt_slot_to_fid(w.tile_pool + (size_t)(frame0 + sm.t_f) * w.pool_cap + sm.t_off, sm.t_len, px % TILE_W, px / TILE_W, tslot, lane);
-                    __syncwarp();
+                    __syncwarp();                    // every lane is done with this buffer (it is refilled two pixels on)
                     if (lane == 0) {
-                        sm.plane[0][(px / TILE_W) * RT_PITCH + (px % TILE_W)] = __float_as_uint(P);
+                        sm.pl[px] = P;
                         sm.list_off[px] = tk;
                         sm.list_cnt[px] = (unsigned short)tf;
                         if (capped) atomicAdd(&sm.n_capped, 1u);
                         if (c > RT_SELCAP) atomicAdd(&sm.n_big, 1u);
                     }
+                    buf ^= 1;
                 }
+                cp_async_wait<0>();
             }
             __syncthreads();
 
@@ -501,18 +541,12 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int row = wid + RT_WARPS * k;
-                    const int idx = row * RT_PITCH + lane, px = row * TILE_W + lane;
+                    const int px = row * TILE_W + lane;
                     const unsigned cls = sm.cls[px];
                     if (cls == RT_CLS_IDLE || row < b0 || row >= b1) continue;
-                    float P;
+                    const float P = sm.pl[px];
                     unsigned tk = 0xffffffffu, tf = 0xffffu;
-                    if (cls == RT_CLS_LISTED) {
-                        P = __uint_as_float(sm.plane[0][idx]); tk = sm.list_off[px]; tf = sm.list_cnt[px];
-                    } else {
-                        P = __uint_as_float(sm.plane[0][idx]);
-#pragma unroll
-                        for (int q = 1; q < RT_WARPS; ++q) P *= __uint_as_float(sm.plane[q][idx]);
-                    }
+                    if (cls == RT_CLS_LISTED) { tk = sm.list_off[px]; tf = sm.list_cnt[px]; }
                     const int y = (tile2 / w.tiles_x) * TILE_H + row;
                     float l1 = 0.f;
                     if (x < S && y < S) {
