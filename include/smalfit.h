@@ -211,6 +211,17 @@ SMALFIT_API int smalfit_vertices(smalfit_t h, const smalfit_tensors_t* params, i
 SMALFIT_API int smalfit_set_profiling(smalfit_t h, int enable);
 SMALFIT_API int smalfit_get_profile(smalfit_t h, float ms[8]);
 
+/* Visualisation pass (row 8f-3): the reference's colour renderer (smal_fitter/p3d_renderer.py:41-59,70-72:
+ * hard rasterisation, faces_per_pixel = 1, HardPhongShader, one point light at (0, 0, 3), constant vertex
+ * colour, white background) of ARBITRARY world-space vertices -- generate_visualization renders the fitted
+ * mesh and a copy turned by 180 degrees (smal_fitter.py:209-272).
+ *   verts      DEVICE [n][V][3] float32 (e.g. from smalfit_vertices, transformed by the caller)
+ *   color_rgb  HOST 3 floats in [0,1]
+ *   rgb        DEVICE out [n][3][S][S] float32
+ * n <= max_frames.  Uses the handle's workspace as scratch: do not overlap with a loss_grad call on another
+ * stream; the backward of a preceding smalfit_loss_grad must have run before (its per-pixel buffer is reused). */
+SMALFIT_API int smalfit_render_color(smalfit_t h, const float* verts, int n, const float color_rgb[3], float* rgb, void* stream);
+
 /* counters[0] = pixels whose fragment count exceeded the K=100 cap (last call)
  * counters[1] = of those, pixels whose fragments spilled from shared memory to the global buffer (exact, slower)
  * counters[2] = (face, tile) entries dropped because a frame's tile pool overflowed (results INEXACT if > 0)

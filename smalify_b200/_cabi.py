@@ -89,6 +89,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "smalfit_vertices": ([vp, TP, C.c_int, C.c_int, vp, vp], C.c_int),
         "smalfit_set_profiling": ([vp, C.c_int], C.c_int),
         "smalfit_get_profile": ([vp, _f32p], C.c_int),
+        "smalfit_render_color": ([vp, vp, C.c_int, _f32p, vp, vp], C.c_int),
         "smalfit_counters": ([vp, C.POINTER(C.c_int64), vp], C.c_int),
         "smalfit_work_counts": ([vp, C.c_int, C.c_int, C.POINTER(C.c_int64), vp], C.c_int),
     }
@@ -104,7 +105,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "smalfit_abi_version", "smalfit_create", "smalfit_destroy", "smalfit_last_error", "smalfit_set_targets",
     "smalfit_set_visibility", "smalfit_set_masks", "smalfit_set_windows", "smalfit_set_joint_limits", "smalfit_set_focal", "smalfit_set_per_frame_shapes",
-    "smalfit_loss_grad", "smalfit_temporal", "smalfit_adam_step", "smalfit_adam_reset", "smalfit_render", "smalfit_vertices",
+    "smalfit_loss_grad", "smalfit_temporal", "smalfit_adam_step", "smalfit_adam_reset", "smalfit_render", "smalfit_vertices", "smalfit_render_color",
     "smalfit_counters", "smalfit_work_counts", "smalfit_set_profiling", "smalfit_get_profile",
 )
 

@@ -475,6 +475,22 @@ int smalfit_vertices(smalfit_t h, const smalfit_tensors_t* params, int frame0, i
     return run_forward(h, to_params(params), frame0, n, wt, false, nullptr, verts, (cudaStream_t)stream);
 }
 
+int smalfit_render_color(smalfit_t h, const float* verts, int n, const float color_rgb[3], float* rgb, void* stream) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!verts || !rgb || !color_rgb || n <= 0 || n > h->N) return fail(h, SMALFIT_EINVAL, "smalfit_render_color: bad arguments");
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    float focal = CAM_F;
+    if (h->w.focal) {
+        cudaError_t e = cudaMemcpyAsync(&focal, h->w.focal, sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return check_cuda(h, e, "smalfit_render_color focal");
+    }
+    launch_vis_color(h->m, h->w, verts, n, color_rgb, focal, rgb, st);
+    h->n_launches += 3;
+    return check_launch(h, "visualisation kernels");
+}
+
 int smalfit_set_profiling(smalfit_t h, int enable) {
     if (!h) return SMALFIT_EINVAL;
     cudaSetDevice(h->device);

@@ -442,6 +442,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #include "smalfit_raster_tile.cuh"
 namespace smf {
 
+}  // namespace smf
+#include "smalfit_vis.cuh"
+namespace smf {
+
 // ---------------------------------------------------------------------------
 // raster_backward: one warp per (frame, face); lanes sweep the face's pixel rectangle
 // ---------------------------------------------------------------------------

@@ -137,6 +137,9 @@ void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, 
 size_t raster_tile_smem_bytes();
 void launch_raster_tile_forward(const ModelDev& m, const Workspace& w, const TileScratch& ts, int frame0, int n, Weights wt,
                                 float* alpha_out, int n_ctas, cudaStream_t st);
+struct VisArgs;
+void launch_vis_color(const ModelDev& m, const Workspace& w, const float* verts, int n, const float color[3], float focal,
+                      float* rgb, cudaStream_t st);
 void launch_raster_backward(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st);
 void launch_frame_backward(const ModelDev& m, const Workspace& w, const Params& p, const Grads& g,
                            int frame0, int n, Weights wt, cudaStream_t st);

@@ -175,6 +175,16 @@ class ResultExporter:
         self.stage_id = 0
         self.epoch_name = "0"
 
+    def export(self, collage_np, batch_id, global_id, img_parameters, vertices, faces):
+        """ImageExporter.export (optimize_to_joints.py:43-53): collage png + parameter pkl + mesh ply of one frame."""
+        import cv2
+        stem = os.path.join(self.output_dirs[global_id], "st{0}_ep{1}".format(self.stage_id, self.epoch_name))
+        cv2.imwrite(stem + ".png", np.ascontiguousarray(collage_np[:, :, ::-1]))        # RGB -> BGR for cv2
+        with open(stem + ".pkl", "wb") as f:
+            pkl.dump(img_parameters, f)
+        v = vertices[batch_id]
+        write_ply(stem + ".ply", v.cpu().numpy() if hasattr(v, "cpu") else np.asarray(v), np.asarray(faces))
+
     def export_fitter(self, fitter, write_mesh: bool = True):
         """The pkl (5 keys) and ply of every frame at the fitter's current parameters."""
         verts = fitter.vertices().cpu().numpy() if write_mesh else None

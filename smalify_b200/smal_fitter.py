@@ -362,6 +362,53 @@ class SMALFitter(nn.Module):
         h.check(h.lib.smalfit_vertices(h.h, ctypes.byref(params), a, n, _ptr(v), _stream(self.device)), "smalfit_vertices")
         return v
 
+    # ---- visualisation (row 8f-3; host-side glue around smalfit_render_color) ----------------------
+    @torch.no_grad()
+    def render_color(self, verts: torch.Tensor, color=None) -> torch.Tensor:
+        """Hard Phong rendering (B,3,S,S) of world-space vertices (B,V,3): the reference's colour renderer
+        (p3d_renderer.py:41-59,70-72).  B <= num_images."""
+        from .visualization import MESH_COLOR
+        v = verts.detach().to(self.device, torch.float32).contiguous()
+        n, S = int(v.shape[0]), self.image_size
+        out = torch.empty(n, 3, S, S, device=self.device)
+        col = (ctypes.c_float * 3)(*(color if color is not None else MESH_COLOR))
+        h = self._handle
+        h.check(h.lib.smalfit_render_color(h.h, _ptr(v), n, col, _ptr(out), _stream(self.device)), "smalfit_render_color")
+        return out
+
+    @torch.no_grad()
+    def model_joints(self, batch_range=None) -> torch.Tensor:
+        """The 41 model joints (B,41,3) of the current parameters, trans included (smal_torch.py:171-184)."""
+        if not hasattr(self, "_mj_dense"):
+            t = self.constants.tables
+            V = self.constants.v_template.shape[0]
+            M = np.zeros((K.N_MODEL_JOINTS, V), np.float32)
+            for j in range(K.N_MODEL_JOINTS):
+                sl = slice(int(t["mj_ptr"][j]), int(t["mj_ptr"][j + 1]))
+                M[j, t["mj_vert"][sl]] = t["mj_weight"][sl]
+            self._mj_dense = torch.from_numpy(M).to(self.device)
+        return torch.einsum("jv,bvk->bjk", self._mj_dense, self.vertices(batch_range))     # rows sum to 1: trans carries over
+
+    @torch.no_grad()
+    def project_points(self, points: torch.Tensor) -> torch.Tensor:
+        """(B,J,3) world points -> (B,J,2) (row, col) pixels: transform_points_screen as used at p3d_renderer.py:67-68."""
+        f = float(self.focal) if self.focal is not None else K.CAMERA_FOCAL
+        zv = K.CAMERA_DISTANCE - points[..., 2]
+        xn, yn = -f * points[..., 0] / zv, f * points[..., 1] / zv
+        half = (self.image_size - 1) / 2.0
+        return torch.stack([half * (1.0 - yn), half * (1.0 - xn)], dim=-1)
+
+    def generate_visualization(self, image_exporter):
+        """smal_fitter.py:209-272: one collage + parameter pickle + mesh per frame through the exporter."""
+        from .visualization import collage
+        for j in range(0, self.num_images, self.batch_size):
+            br = list(range(j, min(self.num_images, j + self.batch_size)))
+            rows = collage(self, br)
+            verts = self.vertices(br).cpu()
+            for b, gid in enumerate(br):
+                img = (np.transpose(rows[b].numpy(), (1, 2, 0)) * 255.0).astype(np.uint8)
+                image_exporter.export(img, b, gid, self.export_parameters(gid), verts, np.asarray(self.constants.faces))
+
     def set_profiling(self, enable: bool):
         h = self._handle
         h.check(h.lib.smalfit_set_profiling(h.h, int(bool(enable))), "smalfit_set_profiling")
