@@ -81,6 +81,7 @@ SYMMETRY_AXIS_RUNS = (
 # Camera (p3d_renderer.py:22-23: look_at_view_transform(2.7, 0, 0) and the
 # default 60 degree OpenGL perspective camera of PyTorch3D 0.2.5).
 CAMERA_DISTANCE = 2.7
+VIS_FREQUENCY = 100                     # config.py: collage / checkpoint export every this many epochs
 CAMERA_FOCAL = 1.7320508075688772       # 1 / tan(fov / 2), OpenGLPerspectiveCameras default fov = 60 degrees
 NDC_FOCAL = 1.0 / math.tan(math.radians(60.0) / 2.0)   # sqrt(3)
 

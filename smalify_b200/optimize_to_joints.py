@@ -3,7 +3,9 @@
 ``fit_sequence(model, ...)`` reproduces the reference's loop (new Adam per stage,
 stage-0 freezing and torso-only visibility, windowed accumulation, temporal term)
 on a ``SMALFitter``; ``fused=True`` runs every epoch as one ``FusedFit.step``.
-Data loading, tqdm and image export of the reference script are out of scope.
+``image_exporter`` (data_io.ResultExporter) turns on the reference's visualisation hook: a collage, the
+parameter pickle and the mesh of every frame each ``vis_frequency`` epochs and once more at the end, under
+the names the reference uses (optimize_to_joints.py:113-115,139-144).
 """
 from __future__ import annotations
 
@@ -25,8 +27,15 @@ def stage_visibility(visibility: torch.Tensor, stage_id: int) -> torch.Tensor:
 
 def fit_sequence(model: SMALFitter, schedule=K.STAGE_SCHEDULE, window_size: int = K.WINDOW_SIZE,
                  allow_limb_scaling: bool = True, fused: bool = False, use_graph: bool = False,
-                 iters_override=None, callback=None, process_group=None, frame_shard=None):
+                 iters_override=None, callback=None, process_group=None, frame_shard=None,
+                 image_exporter=None, vis_frequency: int = K.VIS_FREQUENCY):
     """Runs the stage loop in place on ``model``.  Returns the list of per-stage final losses."""
+
+    def visualise(stage_id, epoch_id):
+        if image_exporter is not None and epoch_id % vis_frequency == 0:
+            image_exporter.stage_id, image_exporter.epoch_name = stage_id, str(epoch_id)
+            model.generate_visualization(image_exporter)
+
     data_visibility = model.target_visibility.clone()
     n = model.num_images
     fused_loop = FusedFit(model, window_size, frame_shard=frame_shard, process_group=process_group) if fused else None
@@ -56,6 +65,7 @@ def fit_sequence(model: SMALFitter, schedule=K.STAGE_SCHEDULE, window_size: int 
                 fused_loop.step(opt_weight, w_temp, lr, train, use_graph=use_graph)
                 if callback is not None:
                     callback(stage_id, epoch_id, fused_loop.total_loss())
+                visualise(stage_id, epoch_id)
             last = fused_loop.total_loss() if epochs else None
         else:
             optimizer = torch.optim.Adam(model.parameters(), lr=lr, betas=K.ADAM_BETAS)
@@ -73,5 +83,9 @@ def fit_sequence(model: SMALFitter, schedule=K.STAGE_SCHEDULE, window_size: int 
                 last = acc_loss.detach()
                 if callback is not None:
                     callback(stage_id, epoch_id, last)
+                visualise(stage_id, epoch_id)
         finals.append(None if last is None else float(last))
+    if image_exporter is not None:                   # "Final stage" export (optimize_to_joints.py:142-144)
+        image_exporter.stage_id, image_exporter.epoch_name = 10, "0"
+        model.generate_visualization(image_exporter)
     return finals
