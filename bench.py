@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=8)
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: libsmalfit's one-shot all-reduce over NVLink peer memory, or NCCL")
     return ap.parse_args()
 
 
@@ -188,7 +190,7 @@ def run_ours(args):
     per = N // world
     lo, hi = rank * per, (rank + 1) * per
     fitter = SMALFitter(dev, data, N, 1, True, constants=c)
-    loop = FusedFit(fitter, N, frame_shard=(lo, hi), process_group=group)
+    loop = FusedFit(fitter, N, frame_shard=(lo, hi), process_group=group, collective=args.collective if world > 1 else "nccl")
     row = K.STAGE_SCHEDULE[STAGE]
     weights, w_temp, lr = row[:6], row[6], row[8]
 
@@ -327,6 +329,7 @@ def run_ours(args):
         "config": {"workload": f"synthetic rs_dog-like sequence, WINDOW_SIZE={N}, {S}x{S} sil, stage-1 weights "
                                f"(kp+sil+pose+shape+splay+temporal), Adam step, frames sharded over {world} GPU(s)",
                    "frames": N, "image_size": S, "frames_per_gpu": frames_rank, "parallelism": f"frame-shard x{world}",
+                   "collective": (loop.collective + (" TIMED OUT" if loop.collective == "peer" and loop.peer_timed_out() else "")) if world > 1 else None,
                    "l2": "256 MiB write between timed steps (L2 flush); per-step CUDA events",
                    "cuda_graph": True},
         "e2e": {"value": e2e_ips, "unit": "iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},

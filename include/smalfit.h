@@ -203,6 +203,24 @@ SMALFIT_API int smalfit_render(smalfit_t h, const smalfit_tensors_t* params, int
 SMALFIT_API int smalfit_vertices(smalfit_t h, const smalfit_tensors_t* params, int frame0, int n_frames,
                      float* verts, void* stream);
 
+/* ---- multi-GPU: one-shot all-reduce over NVLink peer memory (row 8e) ----------------------------
+ * Frames are sharded over ranks (one process per GPU); per optimiser step the flat gradient (26 + 108 N floats
+ * + the 8 loss terms) is summed over ranks.  These calls replace the NCCL all_reduce with one kernel per rank
+ * that stores the vector into every peer's receive buffer, signals, waits for all peers and sums the slots in
+ * rank order (bit-identical replicas).  Set-up, once per handle:
+ *   smalfit_peer_init     allocates this rank's receive buffer for vectors of up to n_floats and returns its
+ *                         64-byte CUDA IPC handle; the caller exchanges the handles (e.g. torch.distributed
+ *                         all_gather) and passes all `world` of them, in rank order, to
+ *   smalfit_peer_connect  which maps the peers' buffers (needs P2P access between the GPUs); synchronise the
+ *                         ranks (a barrier) before the first all-reduce.
+ * smalfit_peer_allreduce enqueues the kernel on `stream` (CUDA-graph capturable); every rank must call it the
+ * same number of times.  A peer that does not arrive within a few seconds makes the kernel give up (the data
+ * is then not reduced) and raises the flag smalfit_peer_status reads. */
+SMALFIT_API int smalfit_peer_init(smalfit_t h, int rank, int world, int n_floats, unsigned char handle_out[64]);
+SMALFIT_API int smalfit_peer_connect(smalfit_t h, const unsigned char* handles /* [world][64] */);
+SMALFIT_API int smalfit_peer_allreduce(smalfit_t h, float* data, int n, void* stream);
+SMALFIT_API int smalfit_peer_status(smalfit_t h, int* timed_out, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------- */
 /* Per-phase device times of the most recent smalfit_loss_grad (CUDA events on the caller's
  * stream; do not enable while capturing a CUDA graph).  ms[0] shape+frame forward,

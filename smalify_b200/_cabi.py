@@ -90,6 +90,10 @@ def load_library(path: str | None = None) -> C.CDLL:
         "smalfit_set_profiling": ([vp, C.c_int], C.c_int),
         "smalfit_get_profile": ([vp, _f32p], C.c_int),
         "smalfit_render_color": ([vp, vp, C.c_int, _f32p, vp, vp], C.c_int),
+        "smalfit_peer_init": ([vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ubyte)], C.c_int),
+        "smalfit_peer_connect": ([vp, C.POINTER(C.c_ubyte)], C.c_int),
+        "smalfit_peer_allreduce": ([vp, vp, C.c_int, vp], C.c_int),
+        "smalfit_peer_status": ([vp, C.POINTER(C.c_int), vp], C.c_int),
         "smalfit_counters": ([vp, C.POINTER(C.c_int64), vp], C.c_int),
         "smalfit_work_counts": ([vp, C.c_int, C.c_int, C.POINTER(C.c_int64), vp], C.c_int),
     }
@@ -106,6 +110,7 @@ EXPORTED_SYMBOLS = (
     "smalfit_abi_version", "smalfit_create", "smalfit_destroy", "smalfit_last_error", "smalfit_set_targets",
     "smalfit_set_visibility", "smalfit_set_masks", "smalfit_set_windows", "smalfit_set_joint_limits", "smalfit_set_focal", "smalfit_set_per_frame_shapes",
     "smalfit_loss_grad", "smalfit_temporal", "smalfit_adam_step", "smalfit_adam_reset", "smalfit_render", "smalfit_vertices", "smalfit_render_color",
+    "smalfit_peer_init", "smalfit_peer_connect", "smalfit_peer_allreduce", "smalfit_peer_status",
     "smalfit_counters", "smalfit_work_counts", "smalfit_set_profiling", "smalfit_get_profile",
 )
 

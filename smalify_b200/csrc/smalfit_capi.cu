@@ -53,6 +53,10 @@ struct smalfit_ctx {
     Workspace w{};
     TileScratch ts{};
     int tile_ctas = 0;
+    PeerDev peer{};             // one-shot all-reduce over peer memory (smalfit_peer_*); world == 0: not set up
+    void* peer_local = nullptr; // this rank's allocation (receive buffer + flags + counters)
+    void* peer_mapped[PEER_MAX] = {};
+    size_t peer_floats = 0;
     AdamState* adam_state = nullptr;
     // mutable target buffers (Workspace holds const views)
     uint8_t* sil = nullptr; float* kp_target = nullptr; uint8_t* vis = nullptr;
@@ -285,6 +289,8 @@ void smalfit_destroy(smalfit_t h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    for (int r = 0; r < PEER_MAX; ++r) if (h->peer_mapped[r]) cudaIpcCloseMemHandle(h->peer_mapped[r]);
+    if (h->peer_local) cudaFree(h->peer_local);
     h->pool.release();
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
@@ -518,6 +524,74 @@ int smalfit_get_profile(smalfit_t h, float ms[8]) {
     e = cudaEventElapsedTime(&ms[6], h->ev[0], h->ev[6]);
     ms[7] = 0.f;
     return check_cuda(h, e, "cudaEventElapsedTime");
+}
+
+// ---- one-shot all-reduce over peer memory (row 8e) ----------------------------------------------
+// layout of a rank's allocation: [2][world][stride] floats | [2][world] flags | epoch | ticket | error | pushed
+static size_t peer_bytes(int world, int stride) { return ((size_t)2 * world * stride) * sizeof(float) + ((size_t)2 * world + 4) * sizeof(unsigned); }
+
+int smalfit_peer_init(smalfit_t h, int rank, int world, int n_floats, unsigned char handle_out[64]) {
+    if (!h || !handle_out) return SMALFIT_EINVAL;
+    if (world < 2 || world > PEER_MAX || rank < 0 || rank >= world || n_floats <= 0)
+        return fail(h, SMALFIT_EINVAL, "smalfit_peer_init: need 2..%d ranks and a positive length", PEER_MAX);
+    if (h->peer_local) return fail(h, SMALFIT_ESTATE, "smalfit_peer_init: already initialised");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaSetDevice(h->device);
+    const int stride = (n_floats + 31) / 32 * 32;
+    cudaError_t e = cudaMalloc(&h->peer_local, peer_bytes(world, stride));
+    if (e == cudaSuccess) e = cudaMemset(h->peer_local, 0, peer_bytes(world, stride));
+    cudaIpcMemHandle_t ih;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&ih, h->peer_local);
+    if (e != cudaSuccess) { if (h->peer_local) cudaFree(h->peer_local); h->peer_local = nullptr; return check_cuda(h, e, "smalfit_peer_init"); }
+    memcpy(handle_out, &ih, 64);
+    h->peer.rank = rank; h->peer.world = world; h->peer.stride = stride;
+    h->peer_floats = (size_t)n_floats;
+    return SMALFIT_OK;
+}
+
+int smalfit_peer_connect(smalfit_t h, const unsigned char* handles) {
+    if (!h || !handles) return SMALFIT_EINVAL;
+    if (!h->peer_local) return fail(h, SMALFIT_ESTATE, "smalfit_peer_connect: call smalfit_peer_init first");
+    cudaSetDevice(h->device);
+    const int W = h->peer.world, stride = h->peer.stride;
+    for (int r = 0; r < W; ++r) {
+        void* base = h->peer_local;
+        if (r != h->peer.rank) {
+            cudaIpcMemHandle_t ih;
+            memcpy(&ih, handles + (size_t)r * 64, 64);
+            cudaError_t e = cudaIpcOpenMemHandle(&base, ih, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return check_cuda(h, e, "smalfit_peer_connect: cudaIpcOpenMemHandle (NVLink / P2P access between the ranks' GPUs is required)");
+            h->peer_mapped[r] = base;
+        }
+        h->peer.buf[r] = static_cast<float*>(base);
+        h->peer.flags[r] = reinterpret_cast<unsigned*>(static_cast<float*>(base) + (size_t)2 * W * stride);
+    }
+    unsigned* tail = h->peer.flags[h->peer.rank] + 2 * W;
+    h->peer.epoch = tail; h->peer.ticket = tail + 1; h->peer.error = tail + 2; h->peer.pushed = tail + 3;
+    return SMALFIT_OK;
+}
+
+int smalfit_peer_allreduce(smalfit_t h, float* data, int n, void* stream) {
+    if (!h || !data) return SMALFIT_EINVAL;
+    if (!h->peer_local || !h->peer.epoch) return fail(h, SMALFIT_ESTATE, "smalfit_peer_allreduce: peers are not connected");
+    if (n <= 0 || (size_t)n > h->peer_floats) return fail(h, SMALFIT_EINVAL, "smalfit_peer_allreduce: length exceeds the buffer");
+    cudaSetDevice(h->device);
+    launch_peer_allreduce(h->peer, data, n, (cudaStream_t)stream);
+    h->n_launches += 1;
+    return check_launch(h, "peer_allreduce");
+}
+
+int smalfit_peer_status(smalfit_t h, int* timed_out, void* stream) {
+    if (!h || !timed_out) return SMALFIT_EINVAL;
+    *timed_out = 0;
+    if (!h->peer.epoch) return SMALFIT_OK;
+    cudaSetDevice(h->device);
+    unsigned v = 0;
+    cudaError_t e = cudaMemcpyAsync(&v, h->peer.error, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return check_cuda(h, e, "smalfit_peer_status");
+    *timed_out = (int)v;
+    return SMALFIT_OK;
 }
 
 int smalfit_work_counts(smalfit_t h, int frame0, int n, int64_t counts[2], void* stream) {

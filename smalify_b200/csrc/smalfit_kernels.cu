@@ -982,6 +982,79 @@ void launch_region_tsum(const Workspace& w, int frame0, int n, float* region_tsu
     region_tsum_kernel<<<grid, 256, 0, st>>>(w, frame0, region_tsum);
 }
 
+// ---------------------------------------------------------------------------
+// One-shot all-reduce of the flat gradient (26 + 108 N floats + 8 loss terms, 55 KB at N = 128) over
+// NVLink peer memory (row 8e).  Every rank holds a receive buffer with one slot per source rank, mapped into
+// all peers (CUDA IPC).  One launch per rank, one CTA per peer:
+//   push    CTA p stores this rank's vector into slot [rank] of peer p's buffer (coalesced remote stores),
+//           then releases flag [rank] of peer p with the epoch (st.release.sys after a system fence);
+//   wait    every CTA acquires all `world` flags of its own rank (ld.acquire.sys, bounded spin);
+//   reduce  CTA c sums slice c of the `world` slots in rank order -- the same order on every rank, so the
+//           replicas stay bit-identical -- and writes it back into the vector.
+// Slots and flags are double-buffered by epoch parity: a rank can only be one all-reduce ahead of the slowest
+// peer, because finishing one needs everybody's flag.  Latency-class payload: one NVLink round, no ring.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(1024) peer_allreduce_kernel(PeerDev pd, float* data, int n) {
+    __shared__ int s_ok;
+    const int tid = threadIdx.x, p = blockIdx.x;
+    const unsigned e = *(volatile unsigned*)pd.epoch + 1u;
+    const unsigned par = e & 1u;
+    if (tid == 0) s_ok = 1;
+    // push
+    float* dst = pd.buf[p] + ((size_t)par * pd.world + pd.rank) * pd.stride;
+    for (int i = tid; i < n; i += blockDim.x) dst[i] = data[i];
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        st_release_sys(pd.flags[p] + par * pd.world + pd.rank, e);
+        atomicAdd(pd.pushed, 1u);                 // the reduce below overwrites `data`: every local CTA must have read it first
+    }
+    // wait for every rank's vector in this rank's buffer (and for this rank's own pushes)
+    if (tid < pd.world) {
+        const unsigned* fl = pd.flags[pd.rank] + par * pd.world + tid;
+        bool ok = false;
+        for (int it = 0; it < (1 << 21); ++it) {                  // ~ seconds: a lost peer must not hang the GPU
+            if (ld_acquire_sys(fl) == e) { ok = true; break; }
+            __nanosleep(20);
+        }
+        if (ok && tid == 0) {
+            ok = false;
+            for (int it = 0; it < (1 << 21); ++it) {
+                if (*(volatile unsigned*)pd.pushed >= e * (unsigned)pd.world) { ok = true; break; }
+                __nanosleep(20);
+            }
+        }
+        if (!ok) { s_ok = 0; *pd.error = 1u; }
+    }
+    __syncthreads();
+    // reduce this CTA's slice, fixed rank order
+    if (s_ok) {
+        const float* src = pd.buf[pd.rank] + (size_t)par * pd.world * pd.stride;
+        const int lo = (int)(((long long)n * p) / pd.world), hi = (int)(((long long)n * (p + 1)) / pd.world);
+        for (int i = lo + tid; i < hi; i += blockDim.x) {
+            float a = 0.f;
+            for (int r = 0; r < pd.world; ++r) a += __ldcg(src + (size_t)r * pd.stride + i);      // written by remote GPUs: not through L1
+            data[i] = a;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(pd.ticket, 1u) == gridDim.x - 1) { *pd.ticket = 0u; *(volatile unsigned*)pd.epoch = e; }
+    }
+}
+
+void launch_peer_allreduce(const PeerDev& pd, float* data, int n, cudaStream_t st) {
+    peer_allreduce_kernel<<<pd.world, 1024, 0, st>>>(pd, data, n);
+}
+
 cudaError_t configure_kernels(const ModelDev& m) {
     const int frame_smem = (int)(sizeof(FrameSmem) + (size_t)m.V * 3 * sizeof(float));
     cudaError_t e = cudaFuncSetAttribute(frame_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);

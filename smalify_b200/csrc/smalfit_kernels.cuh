@@ -137,6 +137,17 @@ void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, 
 size_t raster_tile_smem_bytes();
 void launch_raster_tile_forward(const ModelDev& m, const Workspace& w, const TileScratch& ts, int frame0, int n, Weights wt,
                                 float* alpha_out, int n_ctas, cudaStream_t st);
+constexpr int PEER_MAX = 8;                 // ranks of one NVSwitch domain
+struct PeerDev {                            // one-shot all-reduce over peer-mapped memory (smalfit_peer_*)
+    float* buf[PEER_MAX];                   // rank r's receive buffer: [2 parities][world][stride] floats, mapped here
+    unsigned* flags[PEER_MAX];              // rank r's arrival flags: [2][world]
+    unsigned* epoch;                        // [1] completed all-reduces (local)
+    unsigned* ticket;                       // [1]
+    unsigned* pushed;                       // [1] local CTAs that finished pushing, all epochs
+    unsigned* error;                        // [1] set when a peer did not arrive within the spin limit
+    int rank, world, stride;
+};
+void launch_peer_allreduce(const PeerDev& pd, float* data, int n, cudaStream_t st);
 struct VisArgs;
 void launch_vis_color(const ModelDev& m, const Workspace& w, const float* verts, int n, const float color[3], float focal,
                       float* rgb, cudaStream_t st);

@@ -472,7 +472,12 @@ class FusedFit:
 
     SIZES = lambda n: (20, 6, n * 3, n * K.N_POSE * 3, n * 3)  # noqa: E731
 
-    def __init__(self, fitter: SMALFitter, window_size: int | None = None, frame_shard=None, process_group=None):
+    def __init__(self, fitter: SMALFitter, window_size: int | None = None, frame_shard=None, process_group=None,
+                 collective: str = "nccl"):
+        """collective (frames sharded over `process_group` only): "nccl" = one torch.distributed.all_reduce of the
+        flat gradient per step; "peer" = libsmalfit's one-shot all-reduce over NVLink peer memory
+        (smalfit_peer_allreduce: one kernel per rank, rank-ordered sum), set up here with an all_gather of the
+        CUDA IPC handles."""
         self.f = fitter
         n = fitter.num_images
         dev = fitter.device
@@ -511,6 +516,33 @@ class FusedFit:
         self._graph = None
         self._graph_key = None
         self._warmed = False
+        self.collective = "nccl"
+        if process_group is not None and collective == "peer":
+            self._connect_peers(total + 8)
+        elif collective not in ("nccl", "peer"):
+            raise ValueError("collective must be 'nccl' or 'peer'")
+
+    def _connect_peers(self, n_floats: int):
+        import torch.distributed as dist
+        h, dev, group = self.f._handle, self.f.device, self.group
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        mine_c = (ctypes.c_ubyte * 64)()
+        h.check(h.lib.smalfit_peer_init(h.h, rank, world, int(n_floats), mine_c), "smalfit_peer_init")
+        on_gpu = dist.get_backend(group) == "nccl"
+        mine = torch.tensor(list(mine_c), dtype=torch.uint8, device=dev if on_gpu else "cpu")
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=group)
+        blob = torch.cat(gathered).cpu().numpy().tobytes()
+        h.check(h.lib.smalfit_peer_connect(h.h, (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)), "smalfit_peer_connect")
+        dist.barrier(group=group)                 # every rank has mapped every buffer before the first store
+        self.collective = "peer"
+
+    def peer_timed_out(self) -> bool:
+        """True when a peer failed to arrive in some all-reduce (the step's gradient was then not reduced)."""
+        v = ctypes.c_int(0)
+        h = self.f._handle
+        h.check(h.lib.smalfit_peer_status(h.h, ctypes.byref(v), _stream(self.f.device)), "smalfit_peer_status")
+        return bool(v.value)
 
     def _t(self, idx):
         names = ("betas", "log_beta_scales", "global_rotation", "joint_rotations", "trans")
@@ -538,7 +570,9 @@ class FusedFit:
         h.check(h.lib.smalfit_loss_grad(h.h, ctypes.byref(params), a, b - a, _weights6(weights),
                                         self.n_windows if rank0 else 0, ctypes.byref(grads), _ptr(self.terms), st),
                 "smalfit_loss_grad")
-        if sharded:
+        if sharded and self.collective == "peer":
+            h.check(h.lib.smalfit_peer_allreduce(h.h, _ptr(self.flat_g), int(self.flat_g.numel()), st), "smalfit_peer_allreduce")
+        elif sharded:
             torch.distributed.all_reduce(self.flat_g, group=self.group)      # gradients + loss terms
         h.check(h.lib.smalfit_temporal(h.h, ctypes.byref(params), f.num_images, float(w_temp), ctypes.byref(grads),
                                        _ptr(self.temporal_terms), st), "smalfit_temporal")
