@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SMALFIT_ABI_VERSION 1
+#define SMALFIT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SMALFIT_API __attribute__((visibility("default")))
@@ -224,7 +224,7 @@ SMALFIT_API int smalfit_peer_status(smalfit_t h, int* timed_out, void* stream);
 /* ---- diagnostics ------------------------------------------------------- */
 /* Per-phase device times of the most recent smalfit_loss_grad (CUDA events on the caller's
  * stream; do not enable while capturing a CUDA graph).  ms[0] shape+frame forward,
- * [1] face rectangles + vertex staging copy, [2] raster forward, [3] raster backward,
+ * [1] face preparation + binning, [2] raster forward (hand-out list + tile kernel), [3] raster backward,
  * [4] frame backward, [5] shape backward + finalize, [6] whole call. */
 SMALFIT_API int smalfit_set_profiling(smalfit_t h, int enable);
 SMALFIT_API int smalfit_get_profile(smalfit_t h, float ms[8]);
@@ -241,7 +241,7 @@ SMALFIT_API int smalfit_get_profile(smalfit_t h, float ms[8]);
 SMALFIT_API int smalfit_render_color(smalfit_t h, const float* verts, int n, const float color_rgb[3], float* rgb, void* stream);
 
 /* counters[0] = pixels whose fragment count exceeded the K=100 cap (last call)
- * counters[1] = of those, pixels whose fragments spilled from shared memory to the global buffer (exact, slower)
+ * counters[1] = pixels whose candidate list was longer than the 256 keys a warp selects from registers (exact, slower)
  * counters[2] = (face, tile) entries dropped because a frame's tile pool overflowed (results INEXACT if > 0)
  * counters[3] = kernel launches since create.  counters[0..2] are reset by the call. */
 SMALFIT_API int smalfit_counters(smalfit_t h, int64_t counters[4], void* stream);

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # a missing file raises below)
 LIB_PATH = os.environ.get("SMALFIT_LIB") or os.path.join(_HERE, "libsmalfit.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 L_JOINT, L_SIL, L_BETAS, L_POSE, L_LIMIT, L_SPLAY, L_TEMPORAL, L_TOTAL = range(8)
 
 _f32p = C.POINTER(C.c_float)

@@ -2,28 +2,33 @@
 //
 // Semantics: PyTorch3D 0.2.5 rasterize_meshes (faces_per_pixel = 100, blur 9.21e-4, no culling) +
 // sigmoid_alpha_blend as configured at smal_fitter/p3d_renderer.py:26-39,66, fused with the L1
-// silhouette term of smal_fitter/smal_fitter.py:172-173.  Same outputs as raster_forward_kernel:
-// per pixel (coef, depth threshold, tie face id) for raster_backward, per region row sum|alpha - T|.
+// silhouette term of smal_fitter/smal_fitter.py:172-173.  Outputs: per pixel (coef, depth threshold, tie
+// face id) for raster_backward, per region row sum|alpha - T|, optionally alpha itself.
 //
-// Work item = one 32x32-pixel tile of one frame (bin_faces lists, heaviest tiles of every frame
-// first), pulled by persistent CTAs of 8 warps, 3 CTAs per SM.  The tile's face list is split into
-// 8 contiguous ranges, one per warp, and every warp is *face-parallel*: it streams its prepared
-// faces (64-byte records written by bin_faces) through a double-buffered shared-memory stage with
-// 1-D TMA bulk copies, and for each face its 32 lanes sweep the face's pixel rectangle.  No pair is
-// evaluated twice and nothing is gathered: the per-pair cost is the fragment arithmetic itself.
+// Work item (build_items_kernel) = one 32x32-pixel tile of one frame, or one band of rows of a tile that
+// holds more than 1/RT_FAIR of a CTA's fair share of the launch's (pixel, face) pairs; items are handed out
+// largest first to persistent CTAs of 8 warps, 3 CTAs per SM.  The tile's face list (bin_faces, ascending
+// face id) is split into 8 contiguous ranges of equal cost, one per warp, and every warp is *face-parallel*:
+// it streams its prepared faces (64-byte records written by bin_faces) through a double-buffered
+// shared-memory stage with 1-D TMA bulk copies, and for each face its 32 lanes sweep the face's pixel
+// rectangle.  No pair is evaluated twice and nothing is gathered: the per-pair cost is the fragment
+// arithmetic itself (frag_setup_forward, operation for operation the backward's face_eval_core).
 //
 //   P0  box counts: each warp adds its faces' rectangles into its own 33x33 corner grid (native
 //       32-bit shared-memory atomics) and integrates it -> candidates per (warp, pixel).
-//   P0b per pixel: c = sum over warps.  c <= K: every fragment is selected, the pixel only needs the
-//       product of (1 - p): the planes are set to 1.0f.  c > K ("listed"): the pixel gets c slots in
-//       the CTA's fragment list (global scratch, L2 resident); each warp's plane holds its write
-//       cursor = list offset + candidates of the warps before it, so slots are in face order and
-//       the list is identical from run to run.  Tiles whose lists exceed the scratch are done in
-//       several passes over disjoint pixel sets.
+//   P0b per pixel: c = sum over warps.  c <= K ("direct"): every fragment is selected, the pixel only needs
+//       the product of (1 - p): the planes are set to 1.0f.  c > K ("listed"): the pixel gets c slots
+//       (128-byte aligned) in the CTA's fragment list (global scratch); each warp's plane holds its write
+//       cursor = list offset + candidates of the warps before it, so slots are in face order and the list is
+//       identical from run to run.  Tiles whose lists exceed the scratch are done in several passes over
+//       disjoint pixel sets (RT_SKIP).
 //   P1  sweep: direct pixels multiply into the warp's plane (plain LDS/FMUL/STS: lanes of one face
-//       touch distinct pixels), listed pixels store (depth key, 1 - p, face id) at their cursor.
-//   P2  per listed pixel, one warp: keys in registers (8 per lane), exact K-th order statistic of
-//       (depth, face id) by bisection on the key bits, product over the selected set.
+//       touch distinct pixels), listed pixels store (depth key, 1 - p) at their cursor (evict_last).
+//   P2a the direct pixels' products leave the planes (multiplied in warp order).
+//   P2  per listed pixel, one warp: the list is staged into the warp's (now free) plane with cp.async while
+//       the previous pixel is selected; keys in registers (8 per lane; longer lists first bisect in memory),
+//       exact K-th order statistic of (depth, slot) by bisection on the key bits, product over the selected
+//       set; the list's lines are then dropped from L2 without write-back.
 //   P3  per pixel: alpha, |alpha - T|, coef = dL/dalpha * P / sigma; region row sums in fixed order.
 // Every reduction has a fixed order: results are run-to-run deterministic.
 #pragma once
