@@ -329,7 +329,8 @@ def run_ours(args):
         "config": {"workload": f"synthetic rs_dog-like sequence, WINDOW_SIZE={N}, {S}x{S} sil, stage-1 weights "
                                f"(kp+sil+pose+shape+splay+temporal), Adam step, frames sharded over {world} GPU(s)",
                    "frames": N, "image_size": S, "frames_per_gpu": frames_rank, "parallelism": f"frame-shard x{world}",
-                   "collective": (loop.collective + (" TIMED OUT" if loop.collective == "peer" and loop.peer_timed_out() else "")) if world > 1 else None,
+                   "collective": (loop.collective + (" TIMED OUT" if loop.collective == "peer" and loop.peer_timed_out() else "")
+                                  + (f" (peer unavailable: {loop.peer_error})" if getattr(loop, "peer_error", None) else "")) if world > 1 else None,
                    "l2": "256 MiB write between timed steps (L2 flush); per-step CUDA events",
                    "cuda_graph": True},
         "e2e": {"value": e2e_ips, "unit": "iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},

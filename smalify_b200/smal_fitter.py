@@ -523,18 +523,33 @@ class FusedFit:
             raise ValueError("collective must be 'nccl' or 'peer'")
 
     def _connect_peers(self, n_floats: int):
+        """Sets up the peer-memory all-reduce on every rank, or on none: the ranks agree (MIN over a success
+        flag) after each step, so that a GPU without P2P / IPC access leaves all of them on NCCL."""
         import torch.distributed as dist
         h, dev, group = self.f._handle, self.f.device, self.group
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-        mine_c = (ctypes.c_ubyte * 64)()
-        h.check(h.lib.smalfit_peer_init(h.h, rank, world, int(n_floats), mine_c), "smalfit_peer_init")
         on_gpu = dist.get_backend(group) == "nccl"
-        mine = torch.tensor(list(mine_c), dtype=torch.uint8, device=dev if on_gpu else "cpu")
+        cdev = dev if on_gpu else "cpu"
+
+        def all_ok(ok: bool) -> bool:
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=cdev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return bool(t.item())
+
+        mine_c = (ctypes.c_ubyte * 64)()
+        self.peer_error = None
+        rc = h.lib.smalfit_peer_init(h.h, rank, world, int(n_floats), mine_c) if world <= 8 else -1
+        if not all_ok(rc == 0):
+            self.peer_error = "smalfit_peer_init failed on some rank"
+            return
+        mine = torch.tensor(list(mine_c), dtype=torch.uint8, device=cdev)
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine, group=group)
         blob = torch.cat(gathered).cpu().numpy().tobytes()
-        h.check(h.lib.smalfit_peer_connect(h.h, (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)), "smalfit_peer_connect")
-        dist.barrier(group=group)                 # every rank has mapped every buffer before the first store
+        rc = h.lib.smalfit_peer_connect(h.h, (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob))
+        if not all_ok(rc == 0):                   # (also the barrier: every rank has mapped every buffer before the first store)
+            self.peer_error = "smalfit_peer_connect failed on some rank: " + h.lib.smalfit_last_error(h.h).decode()
+            return
         self.collective = "peer"
 
     def peer_timed_out(self) -> bool:
