@@ -3,6 +3,7 @@ loss only) through ingest -> SMALFitter -> stage-0 fit, and the checkpoint wire 
 import json
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -64,3 +65,28 @@ def test_checkpoint_wire_format_round_trip(constants, stanford, tmp_path):
     a0, _ = f.render()
     a1, _ = g.render()
     assert torch.equal(a0, a1)
+
+
+def test_script_main_and_generate_video(constants, stanford, tmp_path):
+    """optimize_to_joints.main / generate_video.main equivalents on the config-1 image: a short schedule, the
+    collage + pkl + ply exports under the reference's names, then the reload -> per-frame collage path."""
+    import cv2
+    from smalify_b200.optimize_to_joints import RunConfig, generate_video, main
+    data, _ = stanford
+    names = ["0000.jpg"]                         # load_checkpoint addresses frames as <dir>/<%04d>/<epoch>.pkl
+    cfg = RunConfig(OUTPUT_DIR=str(tmp_path / "checkpoints" / "run"), SEQUENCE_OR_IMAGE_NAME="stanfordextra:x", WINDOW_SIZE=1,
+                    VIS_FREQUENCY=4, CHECKPOINT_NAME="run")
+    model, finals = main(cfg, constants=constants, data=(data, names), iters_override=(6, 5, 0, 0))
+    d = os.path.join(cfg.OUTPUT_DIR, "0000")
+    for stem in ("st0_ep0", "st0_ep4", "st1_ep4", "st10_ep0"):
+        assert os.path.exists(os.path.join(d, stem + ".png")) and os.path.exists(os.path.join(d, stem + ".pkl")), stem
+    S = K.CROP_SIZE
+    assert cv2.imread(os.path.join(d, "st10_ep0.png")).shape == (S, 5 * S, 3)
+    assert finals[1] is not None and finals[1] == finals[1]
+    out = generate_video(cfg, constants=constants, data=(data, names), checkpoints_root=str(tmp_path / "checkpoints"),
+                         export_root=str(tmp_path / "exported"))
+    img = cv2.imread(os.path.join(out, "0000.png"))
+    assert img is not None and img.shape == (S, 5 * S, 3)
+    # the reloaded parameters are the exported ones: same collage up to the png quantisation
+    ref = cv2.imread(os.path.join(d, "st10_ep0.png"))
+    assert float(np.mean(np.abs(img.astype(np.int32) - ref.astype(np.int32)) > 2)) < 0.01
