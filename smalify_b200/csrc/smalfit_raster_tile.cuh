@@ -58,7 +58,7 @@ struct RtSmem {
     unsigned char cls[RT_PIX];           // pixel class in the current pass
     unsigned cost_total;
     int item;
-    unsigned n_active, total;
+    unsigned n_active, total, p2_next;
     int t_f, t_tile, t_len;              // current item (kept here across the sweep, which needs the registers)
     unsigned t_off;
     unsigned n_capped, n_big;
@@ -323,7 +323,8 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                 if (e < len) {
                     const unsigned rect = pool[e].z;
                     const int rows = min((int)(rect >> 24), b1 - 1) - max((int)((rect >> 16) & 0xffu), b0) + 1;
-                    cost = (((rect >> 8) & 0xffu) - (rect & 0xffu) + 1u) * (unsigned)max(rows, 0) + RT_FACE_COST;
+                    const unsigned npx = (((rect >> 8) & 0xffu) - (rect & 0xffu) + 1u) * (unsigned)max(rows, 0);
+                    cost = npx ? ((npx + 31u) & ~31u) + RT_FACE_COST : 2u;        // the sweep takes whole 32-lane steps
                 }
 #pragma unroll
                 for (int o = RT_BLK / 2; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
@@ -404,7 +405,7 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
                 if (lane == 31) sm.warp_tot[wid] = incl;
-                if (threadIdx.x == 0) sm.n_active = 0u;
+                if (threadIdx.x == 0) { sm.n_active = 0u; sm.p2_next = 0u; }
                 __syncthreads();
                 unsigned base = 0u, total = 0u;
 #pragma unroll
@@ -507,11 +508,16 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                         for (int ch = lane; ch * 2 < c; ch += 32) cp_async16(stg + buf * RT_SELCAP + ch * 2, src + ch * 2);
                     }
                 };
+                // pixels are drawn from a shared counter (lists differ a lot in length; the results do not depend on
+                // which warp takes which pixel), one ahead so that the next list can stream in
+                auto draw = [&]() { unsigned a = 0u; if (lane == 0) a = atomicAdd(&sm.p2_next, 1u); return __shfl_sync(0xffffffffu, a, 0); };
                 int buf = 0;
-                if ((unsigned)wid < na) stage_px((unsigned)wid, 0);
+                unsigned a = draw();
+                if (a < na) stage_px(a, 0);
                 cp_async_commit();
-                for (unsigned a = (unsigned)wid; a < na; a += RT_WARPS) {
-                    if (a + RT_WARPS < na) stage_px(a + RT_WARPS, buf ^ 1);
+                while (a < na) {
+                    const unsigned a_next = draw();
+                    if (a_next < na) stage_px(a_next, buf ^ 1);
                     cp_async_commit();
                     cp_async_wait<1>();              // everything but the group just committed has landed
                     __syncwarp();
@@ -533,6 +539,7 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                         if (c > RT_SELCAP) atomicAdd(&sm.n_big, 1u);
                     }
                     buf ^= 1;
+                    a = a_next;
                 }
                 cp_async_wait<0>();
             }
