@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SMALFIT_ABI_VERSION 2
+#define SMALFIT_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SMALFIT_API __attribute__((visibility("default")))
@@ -38,7 +38,12 @@ extern "C" {
 #define SMALFIT_EINVAL (-1)   /* bad argument */
 #define SMALFIT_ECUDA (-2)    /* CUDA runtime error */
 #define SMALFIT_ENOMEM (-3)
-#define SMALFIT_ESTATE (-4)   /* call order (e.g. targets not set) */
+#define SMALFIT_ESTATE (-4)   /* call order (e.g. targets not set), or a sticky device-side fault (smalfit_status) */
+
+/* bits of smalfit_status(): device-side faults, sticky until smalfit_destroy */
+#define SMALFIT_STATUS_POOL_OVERFLOW 1   /* a frame needed more (face, tile) entries than the pool holds: that step's
+                                            silhouette loss / gradient were INEXACT (entries were dropped) */
+#define SMALFIT_STATUS_PEER_TIMEOUT 2    /* a peer rank did not arrive in an all-reduce: the kernel trapped */
 
 #define SMALFIT_N_JOINTS 35
 #define SMALFIT_N_POSE 34
@@ -122,7 +127,28 @@ SMALFIT_API int smalfit_abi_version(void);
  * smal_fitter.py:101-102).  max_frames = N frames of the sequence, image_size = S. */
 SMALFIT_API int smalfit_create(const smalfit_model_t* model, int device, int max_frames, int image_size,
                    smalfit_t* out);
+/* The same with options (NULL = defaults = smalfit_create).  Zero-initialise, set struct_size = sizeof, fill in
+ * what differs:
+ *   frame_base, frame_capacity   this handle only ever runs the per-frame kernels on frames
+ *                                [frame_base, frame_base + frame_capacity) of the max_frames-frame sequence (one rank of a
+ *                                frame-sharded fit): targets and workspace are allocated for those frames only, O(N / ranks)
+ *                                instead of O(N).  Parameter / gradient tensors keep their full [N] layout.
+ *                                frame_capacity = 0: all frames.
+ *   pool_entries_per_frame       capacity of the per-frame (face, 32x32 tile) pool; 0 = a heuristic for animals that
+ *                                fill the crop like crop_to_silhouette's output (smal_fitter/utils.py:5-36).  A frame that
+ *                                needs more raises SMALFIT_STATUS_POOL_OVERFLOW. */
+typedef struct {
+    int32_t struct_size;
+    int32_t frame_base, frame_capacity;
+    int32_t pool_entries_per_frame;
+} smalfit_options_t;
+SMALFIT_API int smalfit_create_ex(const smalfit_model_t* model, int device, int max_frames, int image_size,
+                      const smalfit_options_t* options, smalfit_t* out);
 SMALFIT_API void smalfit_destroy(smalfit_t h);
+/* Sticky device-side faults (SMALFIT_STATUS_* bits), read without synchronising from a host-mapped word the kernels
+ * write: a fault raised by step k is visible at the latest after the caller's next synchronisation.
+ * smalfit_loss_grad / smalfit_fused_step also check it on entry and fail with SMALFIT_ESTATE once it is set. */
+SMALFIT_API int smalfit_status(smalfit_t h, int* flags);
 SMALFIT_API const char* smalfit_last_error(smalfit_t h);   /* h may be NULL: last create error */
 
 /* ---- targets (self.sil_imgs / target_joints / target_visibility,
@@ -176,6 +202,24 @@ SMALFIT_API int smalfit_loss_grad(smalfit_t h, const smalfit_tensors_t* params, 
                       const float weights[6], int prior_windows, const smalfit_tensors_t* grads,
                       float* loss_terms, void* stream);
 
+/* One whole epoch of the reference's loop (optimize_to_joints.py:117-137) for frames [frame0, frame0 + n_frames) of
+ * an n_total-frame sequence, as one kernel sequence without host involvement (CUDA-graph capturable):
+ *   - loss terms + analytic gradients of every window (what smalfit_loss_grad does; window sizes from
+ *     smalfit_set_windows),
+ *   - get_temporal(w_temp) (smal_fitter.py:177-190) folded into the same kernels: frame i owns the pair (i, i+1) and
+ *     receives the gradient of both pairs it is part of,
+ *   - when peers are connected (smalfit_peer_*) and shapes are shared: every rank stores the gradient of ITS frames
+ *     and its share of the shared-shape gradient / loss terms into all peers, waits for theirs, and sums in rank order
+ *     -- inside the same kernel that then applies
+ *   - Adam (optimize_to_joints.py:96,137; device-side step counter, reset by smalfit_adam_reset) to all frames
+ *     (replicas stay bit-identical), or to the frames of the range only when nothing is exchanged.
+ * grads / exp_avg / exp_avg_sq: caller-owned, full [N] layout.  loss_terms: dev float[12]: SMALFIT_L_* with
+ * L_TEMPORAL filled and included in L_TOTAL, then [8..10] = the (joint, global, trans) values get_temporal returns. */
+SMALFIT_API int smalfit_fused_step(smalfit_t h, const smalfit_tensors_t* params, const smalfit_tensors_t* grads,
+                       const smalfit_tensors_t* exp_avg, const smalfit_tensors_t* exp_avg_sq, int frame0, int n_frames,
+                       int n_total, const float weights[6], float w_temp, int prior_windows, const int32_t train[5],
+                       float lr, float beta1, float beta2, float eps, float* loss_terms, void* stream);
+
 /* SMALFitter.get_temporal(w_temp) (smal_fitter.py:177-190) over frames [0,N) and its
  * gradient ADDED into grads.{global_rotation,joint_rotations,trans}; terms = dev
  * float[3] (joint, global, trans) as the reference returns them. */
@@ -214,8 +258,9 @@ SMALFIT_API int smalfit_vertices(smalfit_t h, const smalfit_tensors_t* params, i
  *   smalfit_peer_connect  which maps the peers' buffers (needs P2P access between the GPUs); synchronise the
  *                         ranks (a barrier) before the first all-reduce.
  * smalfit_peer_allreduce enqueues the kernel on `stream` (CUDA-graph capturable); every rank must call it the
- * same number of times.  A peer that does not arrive within a few seconds makes the kernel give up (the data
- * is then not reduced) and raises the flag smalfit_peer_status reads. */
+ * same number of times.  A peer that does not arrive within 60 s is fatal: the kernel raises
+ * SMALFIT_STATUS_PEER_TIMEOUT (smalfit_status, smalfit_peer_status) and traps, so that no rank can continue with an
+ * un-reduced gradient (every later CUDA call of that process fails). */
 SMALFIT_API int smalfit_peer_init(smalfit_t h, int rank, int world, int n_floats, unsigned char handle_out[64]);
 SMALFIT_API int smalfit_peer_connect(smalfit_t h, const unsigned char* handles /* [world][64] */);
 SMALFIT_API int smalfit_peer_allreduce(smalfit_t h, float* data, int n, void* stream);
@@ -240,17 +285,25 @@ SMALFIT_API int smalfit_get_profile(smalfit_t h, float ms[8]);
  * stream; the backward of a preceding smalfit_loss_grad must have run before (its per-pixel buffer is reused). */
 SMALFIT_API int smalfit_render_color(smalfit_t h, const float* verts, int n, const float color_rgb[3], float* rgb, void* stream);
 
-/* counters[0] = pixels whose fragment count exceeded the K=100 cap (last call)
- * counters[1] = pixels whose candidate list was longer than the 256 keys a warp selects from registers (exact, slower)
- * counters[2] = (face, tile) entries dropped because a frame's tile pool overflowed (results INEXACT if > 0)
+/* counters[0] = pixels whose fragment count exceeded the K=100 cap, summed over the calls since the last read
+ * counters[1] = pixels whose candidate list was longer than the 256 keys a warp selects from registers (exact, slower), same
+ * counters[2] = (face, tile) entries dropped because a frame's tile pool overflowed (results INEXACT if > 0;
+ *               also raises SMALFIT_STATUS_POOL_OVERFLOW), same
  * counters[3] = kernel launches since create.  counters[0..2] are reset by the call. */
 SMALFIT_API int smalfit_counters(smalfit_t h, int64_t counters[4], void* stream);
 
 /* Diagnostics (synchronises): work of the last rasterised pass over frames [frame0, frame0 + n).
  * counts[0] = (pixel, face) pairs that passed the bounding-box test (what PyTorch3D's fine rasteriser
  *             evaluates after its coarse pass; each is evaluated once in the forward and once in the backward)
- * counts[1] = (face, 32x32 tile) entries binned. */
-SMALFIT_API int smalfit_work_counts(smalfit_t h, int frame0, int n, int64_t counts[2], void* stream);
+ * counts[1] = (face, 32x32 tile) entries binned
+ * counts[2] = of counts[0], the pairs whose pixel carries a silhouette gradient (the backward evaluates only those)
+ * counts[3] = of counts[2], the pairs that are fragments selected by the K-nearest rule (contribute to the gradient).
+ * counts[2..3] are accumulated by the backward while profiling is on (smalfit_set_profiling) since the last call. */
+SMALFIT_API int smalfit_work_counts(smalfit_t h, int frame0, int n, int64_t counts[4], void* stream);
+
+/* Measured FP32 ceiling of this GPU for the roofline: TFLOP/s of a register-resident FMA chain on every SM,
+ * scalar FFMA (tflops[0]) and packed FFMA2 (tflops[1], fma.rn.f32x2).  Synchronises. */
+SMALFIT_API int smalfit_fp32_peak(smalfit_t h, float tflops[2], void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,19 @@
 #include <omp.h>
 #endif
 
+/* -DRASTER_DOUBLE builds the same restatement in double precision (libraster_ref64.so, entry points suffixed
+ * _f64): the float64 arm of whole-fit comparisons, where the float64 torch oracle would take hours. */
+#ifdef RASTER_DOUBLE
+#define float double
+#define fminf fmin
+#define fmaxf fmax
+#define sqrtf sqrt
+#define expf exp
+#define raster_soft_silhouette raster_soft_silhouette_f64
+#define raster_set_threads raster_set_threads_f64
+#define raster_num_threads raster_num_threads_f64
+#endif
+
 #define K_EPS 1e-8f
 
 typedef struct { float pz, sd; int f; } frag_t;

@@ -17,8 +17,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # a missing file raises below)
 LIB_PATH = os.environ.get("SMALFIT_LIB") or os.path.join(_HERE, "libsmalfit.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 L_JOINT, L_SIL, L_BETAS, L_POSE, L_LIMIT, L_SPLAY, L_TEMPORAL, L_TOTAL = range(8)
+N_TERMS_FUSED = 12          # smalfit_fused_step: + (joint, global, trans) temporal values at [8..10]
+STATUS_POOL_OVERFLOW, STATUS_PEER_TIMEOUT = 1, 2
 
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
@@ -39,6 +41,11 @@ class ModelDesc(C.Structure):
         ("pose_mean", _f32p), ("pose_prec", _f32p), ("pose_use", _f32p),
         ("shape_dim", C.c_int32), ("shape_mean", _f32p), ("shape_prec", _f32p),
     ]
+
+
+class Options(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("frame_base", C.c_int32), ("frame_capacity", C.c_int32),
+                ("pool_entries_per_frame", C.c_int32)]
 
 
 class Tensors(C.Structure):
@@ -71,7 +78,12 @@ def load_library(path: str | None = None) -> C.CDLL:
     TP = C.POINTER(Tensors)
     protos = {
         "smalfit_create": ([C.POINTER(ModelDesc), C.c_int, C.c_int, C.c_int, C.POINTER(vp)], C.c_int),
+        "smalfit_create_ex": ([C.POINTER(ModelDesc), C.c_int, C.c_int, C.c_int, C.POINTER(Options), C.POINTER(vp)], C.c_int),
         "smalfit_destroy": ([vp], None),
+        "smalfit_status": ([vp, C.POINTER(C.c_int)], C.c_int),
+        "smalfit_fused_step": ([vp, TP, TP, TP, TP, C.c_int, C.c_int, C.c_int, _f32p, C.c_float, C.c_int, _i32p,
+                                C.c_float, C.c_float, C.c_float, C.c_float, vp, vp], C.c_int),
+        "smalfit_fp32_peak": ([vp, _f32p, vp], C.c_int),
         "smalfit_last_error": ([vp], C.c_char_p),
         "smalfit_set_targets": ([vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp], C.c_int),
         "smalfit_set_visibility": ([vp, C.c_int, C.c_int, vp, C.c_int, vp], C.c_int),
@@ -107,7 +119,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 
 
 EXPORTED_SYMBOLS = (
-    "smalfit_abi_version", "smalfit_create", "smalfit_destroy", "smalfit_last_error", "smalfit_set_targets",
+    "smalfit_abi_version", "smalfit_create", "smalfit_create_ex", "smalfit_status", "smalfit_fused_step", "smalfit_fp32_peak", "smalfit_destroy", "smalfit_last_error", "smalfit_set_targets",
     "smalfit_set_visibility", "smalfit_set_masks", "smalfit_set_windows", "smalfit_set_joint_limits", "smalfit_set_focal", "smalfit_set_per_frame_shapes",
     "smalfit_loss_grad", "smalfit_temporal", "smalfit_adam_step", "smalfit_adam_reset", "smalfit_render", "smalfit_vertices", "smalfit_render_color",
     "smalfit_peer_init", "smalfit_peer_connect", "smalfit_peer_allreduce", "smalfit_peer_status",
@@ -175,11 +187,19 @@ def make_model_desc(c, use_unity_prior: bool = True):
 class Handle:
     """RAII wrapper of smalfit_t."""
 
-    def __init__(self, constants, device_index: int, max_frames: int, image_size: int, use_unity_prior: bool = True):
+    def __init__(self, constants, device_index: int, max_frames: int, image_size: int, use_unity_prior: bool = True,
+                 frame_shard=None, pool_entries_per_frame: int = 0):
+        """frame_shard = (lo, hi): this handle only runs the per-frame kernels on frames [lo, hi) (one rank of a
+        frame-sharded fit); its workspace and resident targets are sized for those frames only."""
         self.lib = load_library()
         desc, keep = make_model_desc(constants, use_unity_prior)
         h = C.c_void_p()
-        rc = self.lib.smalfit_create(C.byref(desc), int(device_index), int(max_frames), int(image_size), C.byref(h))
+        opt = Options()
+        opt.struct_size = C.sizeof(Options)
+        if frame_shard is not None:
+            opt.frame_base, opt.frame_capacity = int(frame_shard[0]), int(frame_shard[1]) - int(frame_shard[0])
+        opt.pool_entries_per_frame = int(pool_entries_per_frame)
+        rc = self.lib.smalfit_create_ex(C.byref(desc), int(device_index), int(max_frames), int(image_size), C.byref(opt), C.byref(h))
         del keep
         if rc != 0:
             raise SmalfitError(f"smalfit_create failed ({rc}): {self.lib.smalfit_last_error(None).decode()}")
@@ -190,6 +210,20 @@ class Handle:
     def check(self, rc: int, what: str):
         if rc != 0:
             raise SmalfitError(f"{what} failed ({rc}): {self.lib.smalfit_last_error(self.h).decode()}")
+
+    def status(self) -> int:
+        """Sticky device-side fault bits (STATUS_*), read from host-mapped memory without synchronising."""
+        v = C.c_int(0)
+        self.lib.smalfit_status(self.h, C.byref(v))
+        return int(v.value)
+
+    def raise_on_fault(self):
+        st = self.status()
+        if st & STATUS_PEER_TIMEOUT:
+            raise SmalfitError("a peer rank did not arrive in an all-reduce (fatal: the kernel trapped)")
+        if st & STATUS_POOL_OVERFLOW:
+            raise SmalfitError("a step needed more (face, tile) entries than the bin pool holds: its silhouette loss and gradient "
+                               "were inexact.  Recreate the fitter with a larger pool_entries_per_frame.")
 
     def close(self):
         if getattr(self, "h", None):

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsmalfit.so")
 SOURCES = ["smalfit_kernels.cu", "smalfit_capi.cu"]
-HEADERS = ["smalfit_math.cuh", "smalfit_kernels.cuh", os.path.join("..", "..", "include", "smalfit.h")]
+PUBLIC_HEADER = os.path.join(HERE, "..", "include", "smalfit.h")
 
 
 def _nvcc() -> str:
@@ -30,7 +30,8 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    # every file of csrc/ (sources and the headers they include) + the public header
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + [PUBLIC_HEADER, os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 

@@ -53,6 +53,10 @@ struct smalfit_ctx {
     Workspace w{};
     TileScratch ts{};
     int tile_ctas = 0;
+    int frame_base = 0, frame_cap = 0;   // frames this handle runs the per-frame kernels on (smalfit_options_t)
+    unsigned* status_host = nullptr;     // host-mapped sticky fault word (SMALFIT_STATUS_*)
+    unsigned* tail_ticket = nullptr;
+    float* peak_scratch = nullptr;
     PeerDev peer{};             // one-shot all-reduce over peer memory (smalfit_peer_*); world == 0: not set up
     void* peer_local = nullptr; // this rank's allocation (receive buffer + flags + counters)
     void* peer_mapped[PEER_MAX] = {};
@@ -103,7 +107,18 @@ Grads to_grads(const smalfit_tensors_t* t) {
     return g;
 }
 
-bool range_ok(smalfit_t h, int frame0, int n) { return frame0 >= 0 && n > 0 && frame0 + n <= h->N; }
+// per-frame kernels only run on the frames the workspace was allocated for
+bool range_ok(smalfit_t h, int frame0, int n) { return n > 0 && frame0 >= h->frame_base && frame0 + n <= h->frame_base + h->frame_cap; }
+
+int check_status(smalfit_t h, const char* who) {
+    const unsigned st = h->status_host ? *(volatile unsigned*)h->status_host : 0u;
+    if (st & SMALFIT_STATUS_PEER_TIMEOUT) return fail(h, SMALFIT_ESTATE, "%s: a peer rank did not arrive in an earlier all-reduce (fatal)", who);
+    if (st & SMALFIT_STATUS_POOL_OVERFLOW)
+        return fail(h, SMALFIT_ESTATE, "%s: an earlier step needed more (face, tile) entries than the pool holds (%d per frame) and its "
+                    "silhouette loss / gradient were inexact; recreate the handle with a larger smalfit_options_t.pool_entries_per_frame",
+                    who, h->w.pool_cap);
+    return SMALFIT_OK;
+}
 
 }  // namespace
 
@@ -114,8 +129,22 @@ int smalfit_abi_version(void) { return SMALFIT_ABI_VERSION; }
 const char* smalfit_last_error(smalfit_t h) { return h ? h->error.c_str() : g_create_error.c_str(); }
 
 int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int image_size, smalfit_t* out) {
+    return smalfit_create_ex(md, device, max_frames, image_size, nullptr, out);
+}
+
+int smalfit_create_ex(const smalfit_model_t* md, int device, int max_frames, int image_size, const smalfit_options_t* opt,
+                      smalfit_t* out) {
     if (!md || !out || max_frames <= 0 || image_size <= 0 || image_size > 1024)
         return fail(nullptr, SMALFIT_EINVAL, "smalfit_create: bad arguments");
+    smalfit_options_t o{};
+    if (opt) {
+        if (opt->struct_size < (int)sizeof(int32_t) || opt->struct_size > (int)sizeof(smalfit_options_t))
+            return fail(nullptr, SMALFIT_EINVAL, "smalfit_create_ex: options.struct_size");
+        memcpy(&o, opt, (size_t)opt->struct_size);
+    }
+    if (o.frame_capacity == 0) { o.frame_base = 0; o.frame_capacity = max_frames; }
+    if (o.frame_base < 0 || o.frame_capacity < 0 || o.frame_base + o.frame_capacity > max_frames || o.pool_entries_per_frame < 0)
+        return fail(nullptr, SMALFIT_EINVAL, "smalfit_create_ex: frame range / pool size out of range");
     if (md->n_verts <= 0 || md->n_verts > 65535 || md->n_faces <= 0 || md->n_faces > 65504)
         return fail(nullptr, SMALFIT_EINVAL, "smalfit_create: mesh size out of range (V=%d F=%d)", md->n_verts, md->n_faces);
     if (md->shape_dim != 26 && md->shape_dim != 20)
@@ -130,6 +159,7 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
 
     smalfit_ctx* h = new smalfit_ctx();
     h->device = device; h->N = max_frames; h->S = image_size; h->n_sm = prop.multiProcessorCount;
+    h->frame_base = o.frame_base; h->frame_cap = o.frame_capacity;
     const int V = md->n_verts, F = md->n_faces;
     ModelDev& m = h->m;
     m.V = V; m.F = F; m.Fp = (F + 31) / 32 * 32; m.Vp = (V + 3) / 4 * 4;
@@ -201,27 +231,34 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
 
     // ---- workspace ----
     Workspace& w = h->w;
-    const size_t N = max_frames, SS = (size_t)image_size * image_size;
+    // Per-frame buffers hold the handle's own frames only (C of them, frames [B, B + C)) but are addressed by
+    // absolute frame id everywhere: their base pointers are shifted back by B frames (never dereferenced below B).
+    const size_t NT = max_frames;                     // frames of the sequence: parameter-sized buffers
+    const size_t N = o.frame_capacity, B = o.frame_base, SS = (size_t)image_size * image_size;
+#define SHIFT(ptr, per_frame) ((ptr) ? (ptr) - B * (size_t)(per_frame) : (ptr))
     w.N = max_frames; w.S = image_size;
     w.tiles_x = (image_size + TILE_W - 1) / TILE_W; w.tiles_y = (image_size + TILE_H - 1) / TILE_H;
     const size_t tiles = (size_t)w.tiles_x * w.tiles_y;
     w.n_shapes = 1;
+    w.slot0 = o.frame_base;
     const int n_blocks = (V * 3 + 255) / 256;
-    w.v_shaped = P.alloc<float>(N * V * 3);          // sized for per-frame shapes too
-    w.ndc = P.alloc<float4>(N * m.Vp);
-    w.gjoint = P.alloc<float>(N * NMJ * 3, true);
-    w.kp_proj = P.alloc<float>(N * NKP * 2, true);
-    w.face_rect = P.alloc<uint2>(N * m.Fp);
-    w.face_rec = P.alloc<float4>(N * m.Fp * 4);
-    {   // (face, tile) entries per frame grow with the face size in pixels: ~Fp * ((bbox_px + 32) / 32)^2
+    w.v_shaped = SHIFT(P.alloc<float>(N * V * 3), V * 3);          // sized for per-frame shapes too (slot 0 = the shared shape)
+    w.ndc = SHIFT(P.alloc<float4>(N * m.Vp), m.Vp);
+    w.gjoint = SHIFT(P.alloc<float>(N * NMJ * 3, true), NMJ * 3);
+    w.kp_proj = SHIFT(P.alloc<float>(N * NKP * 2, true), NKP * 2);
+    w.face_rect = SHIFT(P.alloc<uint2>(N * m.Fp), m.Fp);
+    w.face_rec = SHIFT(P.alloc<float4>(N * m.Fp * 4), m.Fp * 4);
+    if (o.pool_entries_per_frame > 0) {
+        w.pool_cap = (o.pool_entries_per_frame + 31) / 32 * 32;
+    } else {   // (face, tile) entries per frame grow with the face size in pixels: ~Fp * ((bbox_px + 32) / 32)^2
         const float bbox_px = 18.f * (float)image_size / 256.f;
         const float per_face = ((bbox_px + 32.f) / 32.f) * ((bbox_px + 32.f) / 32.f);
         int mult = (int)(2.5f * per_face + 1.f);
         mult = mult < 8 ? 8 : (mult > 64 ? 64 : mult);
         w.pool_cap = mult * m.Fp;
     }
-    w.tile_pool = P.alloc<uint4>(N * (size_t)w.pool_cap);
-    w.tile_rec = P.alloc<float4>(N * (size_t)w.pool_cap * 4);
+    w.tile_pool = SHIFT(P.alloc<uint4>(N * (size_t)w.pool_cap), w.pool_cap);
+    w.tile_rec = SHIFT(P.alloc<float4>(N * (size_t)w.pool_cap * 4), (size_t)w.pool_cap * 4);
     {
         h->tile_ctas = h->n_sm * RT_CTAS_PER_SM;
         h->ts.list_cap = 192 * 1024;        // 1.5 MB per CTA: a 32x32 tile with ~190 candidates on every pixel in one pass
@@ -231,48 +268,59 @@ int smalfit_create(const smalfit_model_t* md, int device, int max_frames, int im
         h->ts.list = P.alloc<uint2>((size_t)h->tile_ctas * h->ts.list_stride);
         h->ts.item_next = P.alloc<unsigned>(2, true);
         h->ts.n_items = h->ts.item_next + 1;
-        h->ts.items = P.alloc<unsigned>(N * tiles * 8);
+        h->ts.items = P.alloc<unsigned>(N * tiles * 8 + 8);
         const char* e_nsub = getenv("SMALFIT_RT_NSUB");         // tuning knobs for measurements
         const char* e_split = getenv("SMALFIT_RT_SPLITLEN");
         h->ts.nsub = e_nsub ? atoi(e_nsub) : 0;
         { const char* e_fair = getenv("SMALFIT_RT_FAIR"); h->ts.fair = e_fair ? atoi(e_fair) : 0; }
         h->ts.split_len = e_split ? atoi(e_split) : 0;
     }
-    w.tile_off = P.alloc<unsigned>(N * (tiles + 1), true);
-    w.tile_cost = P.alloc<unsigned>(N * tiles, true);
-    w.bin_cnt = P.alloc<unsigned>(N * BIN_WARPS * tiles, true);
-    w.bin_cost = P.alloc<unsigned>(N * BIN_PARTS * tiles, true);
-    w.pix = P.alloc<uint2>(N * SS, true);
-    w.pix_tfid = P.alloc<uint16_t>(N * SS, true);
-    w.region_l1 = P.alloc<float>(N * tiles * REGIONS_PER_TILE * REGION_H, true);
-    w.face_grad = P.alloc<float>(N * m.Fp * 8, true);
-    w.dvs = P.alloc<float>(N * V * 3, true);
-    w.gJ = P.alloc<float>(N * NJ * 3, true);
-    w.gls = P.alloc<float>(N * NLS, true);
-    w.frame_loss = P.alloc<float>(N * 8, true);
+    w.tile_off = SHIFT(P.alloc<unsigned>(N * (tiles + 1), true), tiles + 1);
+    w.tile_cost = SHIFT(P.alloc<unsigned>(N * tiles, true), tiles);
+    w.bin_cnt = SHIFT(P.alloc<unsigned>(N * BIN_WARPS * tiles, true), BIN_WARPS * tiles);
+    w.bin_cost = SHIFT(P.alloc<unsigned>(N * BIN_PARTS * tiles, true), BIN_PARTS * tiles);
+    w.pix = SHIFT(P.alloc<uint2>(N * SS, true), SS);
+    w.pix_tfid = SHIFT(P.alloc<uint16_t>(N * SS, true), SS);
+    w.region_l1 = SHIFT(P.alloc<float>(N * tiles * REGIONS_PER_TILE * REGION_H, true), tiles * REGIONS_PER_TILE * REGION_H);
+    w.face_grad = SHIFT(P.alloc<float>(N * m.Fp * 8, true), m.Fp * 8);
+    w.dvs = SHIFT(P.alloc<float>(N * V * 3, true), V * 3);
+    w.gJ = SHIFT(P.alloc<float>(N * NJ * 3, true), NJ * 3);
+    w.gls = SHIFT(P.alloc<float>(N * NLS, true), NLS);
+    w.frame_loss = SHIFT(P.alloc<float>(N * 8, true), 8);
     h->limit_buf = P.alloc<float>(2 * (NJ - 1) * 3, true);
-    w.gfocal_frame = P.alloc<float>(N * 2, true);
-    w.beta_partial = P.alloc<float>(N * n_blocks * NBETA, true);
-    h->sil = P.alloc<uint8_t>(N * SS, true);
-    h->kp_target = P.alloc<float>(N * NKP * 2, true);
-    h->vis = P.alloc<uint8_t>(N * NKP, true);
-    h->region_tsum = P.alloc<float>(N * tiles * REGIONS_PER_TILE * REGION_H, true);
-    std::vector<float> ones(N > 102 ? N : 102, 1.0f);
-    std::vector<float> invw(N, 1.0f / (float)N);
-    h->inv_window = P.upload(invw.data(), N);
+    w.gfocal_frame = SHIFT(P.alloc<float>(N * 2, true), 2);
+    w.beta_partial = SHIFT(P.alloc<float>(N * n_blocks * NBETA, true), n_blocks * NBETA);
+    h->sil = SHIFT(P.alloc<uint8_t>(N * SS, true), SS);
+    h->kp_target = SHIFT(P.alloc<float>(N * NKP * 2, true), NKP * 2);
+    h->vis = SHIFT(P.alloc<uint8_t>(N * NKP, true), NKP);
+    h->region_tsum = SHIFT(P.alloc<float>(N * tiles * REGIONS_PER_TILE * REGION_H, true), tiles * REGIONS_PER_TILE * REGION_H);
+    std::vector<float> ones(NT > 102 ? NT : 102, 1.0f);
+    std::vector<float> invw(NT, 1.0f / (float)NT);
+    h->inv_window = P.upload(invw.data(), NT);
     h->gmask = P.upload(ones.data(), 3);
     h->rmask = P.upload(ones.data(), (NJ - 1) * 3);
     w.sil = h->sil; w.kp_target = h->kp_target; w.vis = h->vis; w.region_tsum = h->region_tsum;
     w.inv_window = h->inv_window; w.gmask = h->gmask; w.rmask = h->rmask;
     h->adam_state = P.alloc<AdamState>(1, true);
-    w.temporal_partial = P.alloc<float>(((size_t)N * 108 + 255) / 256 * 3 + 3, true);
+    w.temporal_partial = P.alloc<float>(((size_t)NT * 108 + 255) / 256 * 3 + 3, true);
     w.temporal_ticket = P.alloc<unsigned>(1, true);
-    w.slot_loss = P.alloc<float>(N, true);
+    w.slot_loss = SHIFT(P.alloc<float>(N, true), 1);
     w.finalize_ticket = P.alloc<unsigned>(1, true);
-    w.counters = P.alloc<unsigned long long>(4, true);
+    w.counters = P.alloc<unsigned long long>(8, true);
+    h->tail_ticket = P.alloc<unsigned>(1, true);
+    h->peak_scratch = P.alloc<float>(4, true);
+#undef SHIFT
+    if (P.err == cudaSuccess) {
+        P.err = cudaHostAlloc(reinterpret_cast<void**>(&h->status_host), sizeof(unsigned), cudaHostAllocMapped);
+        if (P.err == cudaSuccess) {
+            *h->status_host = 0u;
+            P.err = cudaHostGetDevicePointer(reinterpret_cast<void**>(&w.status), h->status_host, 0);
+        }
+    }
     if (P.err != cudaSuccess) {
         const cudaError_t pe = P.err;
         P.release();
+        if (h->status_host) cudaFreeHost(h->status_host);
         delete h;
         return fail(nullptr, pe == cudaErrorMemoryAllocation ? SMALFIT_ENOMEM : SMALFIT_ECUDA,
                     "smalfit_create: device allocation/upload failed: %s", cudaGetErrorString(pe));
@@ -292,13 +340,14 @@ void smalfit_destroy(smalfit_t h) {
     for (int r = 0; r < PEER_MAX; ++r) if (h->peer_mapped[r]) cudaIpcCloseMemHandle(h->peer_mapped[r]);
     if (h->peer_local) cudaFree(h->peer_local);
     h->pool.release();
+    if (h->status_host) cudaFreeHost(h->status_host);
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
 }
 
 int smalfit_set_per_frame_shapes(smalfit_t h, int enable) {
     if (!h) return SMALFIT_EINVAL;
-    h->w.n_shapes = enable ? h->N : 1;
+    h->w.n_shapes = enable ? h->N : 1;       // slots are addressed by absolute frame id
     return SMALFIT_OK;
 }
 
@@ -374,7 +423,7 @@ int smalfit_set_windows(smalfit_t h, const int32_t* fpw, int n) {
 static int run_forward(smalfit_t h, const Params& p, int frame0, int n, Weights wt, bool raster, float* alpha_out,
                        float* verts_out, cudaStream_t st) {
     h->mark(0, st);
-    launch_shape_forward(h->m, h->w, p, st);
+    launch_shape_forward(h->m, h->w, p, frame0, n, st);
     launch_frame_forward(h->m, h->w, p, frame0, n, wt, verts_out, st);
     h->n_launches += 2;
     h->mark(1, st);
@@ -390,18 +439,8 @@ static int run_forward(smalfit_t h, const Params& p, int frame0, int n, Weights 
     return check_launch(h, "forward kernels");
 }
 
-int smalfit_loss_grad(smalfit_t h, const smalfit_tensors_t* params, int frame0, int n, const float weights[6],
-                      int prior_windows, const smalfit_tensors_t* grads, float* loss_terms, void* stream) {
-    if (!h) return SMALFIT_EINVAL;
-    if (!params || !weights || !range_ok(h, frame0, n)) return fail(h, SMALFIT_EINVAL, "smalfit_loss_grad: bad arguments");
-    if (!params->betas || !params->log_beta_scales || !params->global_rotation || !params->joint_rotations || !params->trans)
-        return fail(h, SMALFIT_EINVAL, "smalfit_loss_grad: NULL parameter tensor");
-    if (!h->targets_set) return fail(h, SMALFIT_ESTATE, "smalfit_loss_grad: call smalfit_set_targets first");
-    cudaSetDevice(h->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    const Weights wt{weights[0], weights[1], weights[2], weights[3], weights[4], weights[5]};
-    const Params p = to_params(params);
-    const Grads g = to_grads(grads);
+static int run_loss_grad(smalfit_t h, const Params& p, const Grads& g, int frame0, int n, const Weights& wt, int prior_windows,
+                         float* loss_terms, cudaStream_t st) {
     const bool raster = wt.sil > 0.f;
     int rc = run_forward(h, p, frame0, n, wt, raster, nullptr, nullptr, st);
     if (rc) return rc;
@@ -414,6 +453,98 @@ int smalfit_loss_grad(smalfit_t h, const smalfit_tensors_t* params, int frame0, 
     h->mark(6, st);
     if (h->profiling) h->ev_valid = true;
     return check_launch(h, "backward kernels");
+}
+
+int smalfit_loss_grad(smalfit_t h, const smalfit_tensors_t* params, int frame0, int n, const float weights[6],
+                      int prior_windows, const smalfit_tensors_t* grads, float* loss_terms, void* stream) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!params || !weights || !range_ok(h, frame0, n)) return fail(h, SMALFIT_EINVAL, "smalfit_loss_grad: bad arguments");
+    if (!params->betas || !params->log_beta_scales || !params->global_rotation || !params->joint_rotations || !params->trans)
+        return fail(h, SMALFIT_EINVAL, "smalfit_loss_grad: NULL parameter tensor");
+    if (!h->targets_set) return fail(h, SMALFIT_ESTATE, "smalfit_loss_grad: call smalfit_set_targets first");
+    if (int rc = check_status(h, "smalfit_loss_grad")) return rc;
+    cudaSetDevice(h->device);
+    Weights wt{weights[0], weights[1], weights[2], weights[3], weights[4], weights[5], 0.f, h->N, 8};
+    return run_loss_grad(h, to_params(params), to_grads(grads), frame0, n, wt, prior_windows, loss_terms, (cudaStream_t)stream);
+}
+
+int smalfit_fused_step(smalfit_t h, const smalfit_tensors_t* params, const smalfit_tensors_t* grads, const smalfit_tensors_t* exp_avg,
+                       const smalfit_tensors_t* exp_avg_sq, int frame0, int n, int n_total, const float weights[6], float w_temp,
+                       int prior_windows, const int32_t train[5], float lr, float beta1, float beta2, float eps, float* loss_terms,
+                       void* stream) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !weights || !train || !loss_terms || !range_ok(h, frame0, n) ||
+        n_total < frame0 + n || n_total > h->N || w_temp < 0.f)
+        return fail(h, SMALFIT_EINVAL, "smalfit_fused_step: bad arguments");
+    const smalfit_tensors_t* all4[4] = {params, grads, exp_avg, exp_avg_sq};
+    for (const smalfit_tensors_t* t : all4)
+        if (!t->betas || !t->log_beta_scales || !t->global_rotation || !t->joint_rotations || !t->trans)
+            return fail(h, SMALFIT_EINVAL, "smalfit_fused_step: NULL tensor");
+    if (!h->targets_set) return fail(h, SMALFIT_ESTATE, "smalfit_fused_step: call smalfit_set_targets first");
+    if (int rc = check_status(h, "smalfit_fused_step")) return rc;
+    const bool exchange = h->peer.epoch != nullptr && h->w.n_shapes == 1;
+    if (exchange) {
+        if (frame0 != h->peer.rank * n || n_total != h->peer.world * n)
+            return fail(h, SMALFIT_EINVAL, "smalfit_fused_step: with peers connected rank r must own frames [r n, (r + 1) n) of world * n");
+        if ((size_t)(40 + 108 * n) > h->peer_floats)
+            return fail(h, SMALFIT_EINVAL, "smalfit_fused_step: peer buffers are too small for %d frames per rank", n);
+    }
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    // the temporal term is folded into frame_backward / finalize
+    Weights wt{weights[0], weights[1], weights[2], weights[3], weights[4], weights[5], w_temp, n_total, 12};
+    int rc = run_loss_grad(h, to_params(params), to_grads(grads), frame0, n, wt, prior_windows, loss_terms, st);
+    if (rc) return rc;
+    TailArgs a{};
+    const smalfit_tensors_t* src[4] = {params, grads, exp_avg, exp_avg_sq};
+    float** dst[4] = {a.p, a.g, a.m, a.v};
+    for (int q = 0; q < 4; ++q) {
+        dst[q][0] = src[q]->betas; dst[q][1] = src[q]->log_beta_scales; dst[q][2] = src[q]->global_rotation;
+        dst[q][3] = src[q]->joint_rotations; dst[q][4] = src[q]->trans;
+    }
+    for (int q = 0; q < 5; ++q) a.train[q] = train[q] ? 1 : 0;
+    a.n_shapes = h->w.n_shapes; a.n_total = n_total; a.frame0 = frame0; a.n_frames = n; a.exchange = exchange ? 1 : 0;
+    a.terms = loss_terms; a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps;
+    a.state = h->adam_state; a.ticket = h->tail_ticket;
+    launch_step_tail(h->peer, a, st);
+    h->n_launches += 1;
+    return check_launch(h, "step_tail kernel");
+}
+
+int smalfit_status(smalfit_t h, int* flags) {
+    if (!h || !flags) return SMALFIT_EINVAL;
+    *flags = h->status_host ? (int)*(volatile unsigned*)h->status_host : 0;
+    return SMALFIT_OK;
+}
+
+int smalfit_fp32_peak(smalfit_t h, float tflops[2], void* stream) {
+    if (!h || !tflops) return SMALFIT_EINVAL;
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    cudaError_t e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e != cudaSuccess) return check_cuda(h, e, "smalfit_fp32_peak");
+    const int iters = 1 << 15;
+    for (int packed = 0; packed < 2 && e == cudaSuccess; ++packed) {
+        launch_fp32_peak(h->peak_scratch, h->n_sm, packed, 256, st);            // warm-up
+        float best = 1e30f;
+        for (int rep = 0; rep < 3 && e == cudaSuccess; ++rep) {
+            cudaEventRecord(e0, st);
+            launch_fp32_peak(h->peak_scratch, h->n_sm, packed, iters, st);
+            cudaEventRecord(e1, st);
+            e = cudaEventSynchronize(e1);
+            float ms = 0.f;
+            if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+            if (ms < best) best = ms;
+        }
+        // threads x iterations x 8 chains (4 packed pairs x 2 rounds) x 2 flop
+        const double flop = (double)h->n_sm * 8 * 256 * (double)iters * 8.0 * 2.0 * (packed ? 2.0 : 1.0);
+        tflops[packed] = (float)(flop / ((double)best * 1e-3) / 1e12);
+    }
+    h->n_launches += 8;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return check_cuda(h, e, "smalfit_fp32_peak");
 }
 
 int smalfit_temporal(smalfit_t h, const smalfit_tensors_t* params, int n_frames, float w_temp,
@@ -464,7 +595,7 @@ int smalfit_render(smalfit_t h, const smalfit_tensors_t* params, int frame0, int
     if (!params || !range_ok(h, frame0, n)) return fail(h, SMALFIT_EINVAL, "smalfit_render: bad arguments");
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    const Weights wt{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const Weights wt{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, h->N, 8};
     int rc = run_forward(h, to_params(params), frame0, n, wt, silhouettes != nullptr, silhouettes, nullptr, st);
     if (rc) return rc;
     if (keypoints)
@@ -477,7 +608,7 @@ int smalfit_vertices(smalfit_t h, const smalfit_tensors_t* params, int frame0, i
     if (!h) return SMALFIT_EINVAL;
     if (!params || !verts || !range_ok(h, frame0, n)) return fail(h, SMALFIT_EINVAL, "smalfit_vertices: bad arguments");
     cudaSetDevice(h->device);
-    const Weights wt{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const Weights wt{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, h->N, 8};
     return run_forward(h, to_params(params), frame0, n, wt, false, nullptr, verts, (cudaStream_t)stream);
 }
 
@@ -507,6 +638,7 @@ int smalfit_set_profiling(smalfit_t h, int enable) {
         }
     }
     h->profiling = enable != 0;
+    h->w.count_pairs = h->profiling ? 1 : 0;
     h->ev_valid = false;
     return SMALFIT_OK;
 }
@@ -568,6 +700,7 @@ int smalfit_peer_connect(smalfit_t h, const unsigned char* handles) {
     }
     unsigned* tail = h->peer.flags[h->peer.rank] + 2 * W;
     h->peer.epoch = tail; h->peer.ticket = tail + 1; h->peer.error = tail + 2; h->peer.pushed = tail + 3;
+    h->peer.status = h->w.status;
     return SMALFIT_OK;
 }
 
@@ -582,19 +715,13 @@ int smalfit_peer_allreduce(smalfit_t h, float* data, int n, void* stream) {
 }
 
 int smalfit_peer_status(smalfit_t h, int* timed_out, void* stream) {
+    (void)stream;
     if (!h || !timed_out) return SMALFIT_EINVAL;
-    *timed_out = 0;
-    if (!h->peer.epoch) return SMALFIT_OK;
-    cudaSetDevice(h->device);
-    unsigned v = 0;
-    cudaError_t e = cudaMemcpyAsync(&v, h->peer.error, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
-    if (e != cudaSuccess) return check_cuda(h, e, "smalfit_peer_status");
-    *timed_out = (int)v;
+    *timed_out = (h->status_host && (*(volatile unsigned*)h->status_host & SMALFIT_STATUS_PEER_TIMEOUT)) ? 1 : 0;
     return SMALFIT_OK;
 }
 
-int smalfit_work_counts(smalfit_t h, int frame0, int n, int64_t counts[2], void* stream) {
+int smalfit_work_counts(smalfit_t h, int frame0, int n, int64_t counts[4], void* stream) {
     if (!h || !counts) return SMALFIT_EINVAL;
     if (!range_ok(h, frame0, n)) return fail(h, SMALFIT_EINVAL, "smalfit_work_counts: bad frame range");
     cudaSetDevice(h->device);
@@ -608,6 +735,12 @@ int smalfit_work_counts(smalfit_t h, int frame0, int n, int64_t counts[2], void*
     counts[0] = counts[1] = 0;
     for (unsigned c : cost) counts[0] += c;
     for (int f = 0; f < n; ++f) counts[1] += off[(size_t)f * (tiles + 1) + tiles];
+    unsigned long long bw[2] = {0, 0};
+    e = cudaMemcpyAsync(bw, h->w.counters + 4, sizeof(bw), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->w.counters + 4, 0, 2 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return check_cuda(h, e, "smalfit_work_counts");
+    counts[2] = (int64_t)bw[0]; counts[3] = (int64_t)bw[1];
     return SMALFIT_OK;
 }
 

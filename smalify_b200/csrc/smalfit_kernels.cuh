@@ -65,6 +65,7 @@ struct Grads {
 struct Workspace {
     int N, S, tiles_x, tiles_y;
     int n_shapes;
+    int slot0;                  // workspace slot of the shared shape (= the handle's first frame)
     // per shape slot
     float* v_shaped;            // [n_shapes][V*3]
     // per frame (indexed by absolute frame id)
@@ -89,7 +90,7 @@ struct Workspace {
     float* dvs;                 // [N][V*3]  per-frame dL/dv_shaped
     float* gJ;                  // [N][105]  per-frame dL/dJ(rest joints)
     float* gls;                 // [N][6]    per-frame dL/dlogscale
-    float* frame_loss;          // [N][8]    kp, pose, splay, silhouette, joint limit, -, -, -
+    float* frame_loss;          // [N][8]    kp, pose, splay, silhouette, joint limit, temporal (joint, global, trans)
     float* beta_partial;        // [n_shapes][n_blocks][20]
     // targets
     const uint8_t* sil;         // [N][S*S]
@@ -108,10 +109,18 @@ struct Workspace {
     unsigned* finalize_ticket;  // [1]
     float* temporal_partial;    // [blocks][3] per-block temporal loss partials
     unsigned* temporal_ticket;  // [1]
-    unsigned long long* counters;   // [4]
+    unsigned long long* counters;   // [8] capped pixels, long lists, dropped bin entries, -, backward pairs in live pixels, backward fragments used
+    unsigned* status;           // [1] host-mapped sticky fault bits (SMALFIT_STATUS_*)
+    int count_pairs;            // the backward accumulates counters[4..5] (profiling)
 };
+constexpr unsigned STATUS_POOL_OVERFLOW = 1u, STATUS_PEER_TIMEOUT = 2u;
 
-struct Weights { float j2d, sil, betas, pose, limit, splay; };
+struct Weights {
+    float j2d, sil, betas, pose, limit, splay;
+    float temp;                 // w_temp of get_temporal folded into frame_backward (0: not folded, smalfit_temporal adds it)
+    int n_total;                // frames of the whole sequence (temporal pairs end at n_total - 1)
+    int n_terms;                // 8: loss_terms as smalfit_loss_grad documents; 12: + the three temporal values (smalfit_fused_step)
+};
 struct AdamState { int step; float bc1; float bc2_sqrt; int pad; };
 struct AdamSegments { float* p[5]; const float* g[5]; float* m[5]; float* v[5]; int len[5]; int train[5]; };
 
@@ -130,7 +139,7 @@ struct TileScratch {        // tile rasteriser: per resident CTA
 // ---- launch wrappers (defined in smalfit_kernels.cu) ----------------------
 void upload_skeleton(const SkeletonConst& sk);
 cudaError_t configure_kernels(const ModelDev& m);
-void launch_shape_forward(const ModelDev& m, const Workspace& w, const Params& p, cudaStream_t st);
+void launch_shape_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n, cudaStream_t st);
 void launch_frame_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n,
                           Weights wt, float* verts_out, cudaStream_t st);
 void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st);
@@ -144,9 +153,24 @@ struct PeerDev {                            // one-shot all-reduce over peer-map
     unsigned* epoch;                        // [1] completed all-reduces (local)
     unsigned* ticket;                       // [1]
     unsigned* pushed;                       // [1] local CTAs that finished pushing, all epochs
-    unsigned* error;                        // [1] set when a peer did not arrive within the spin limit
+    unsigned* error;                        // [1] set when a peer did not arrive within the time limit
+    unsigned* status;                       // host-mapped sticky fault bits of the handle
     int rank, world, stride;
 };
+// The step tail (smalfit_fused_step): [exchange over peer memory] + Adam in one kernel.
+struct TailArgs {
+    float* p[5]; float* g[5]; float* m[5]; float* v[5];     // betas, log_beta_scales, global_rotation, joint_rotations, trans
+    int train[5];
+    int n_shapes, n_total;      // shapes (1: shared) and frames of the sequence
+    int frame0, n_frames;       // this rank's frames
+    int exchange;               // sum / gather over the connected peers (shared shapes only)
+    float* terms;               // [12] loss terms of this rank (in) -> summed over ranks (out)
+    float lr, b1, b2, eps;
+    AdamState* state;
+    unsigned* ticket;           // [1]
+};
+void launch_step_tail(const PeerDev& pd, const TailArgs& a, cudaStream_t st);
+void launch_fp32_peak(float* out, int n_sm, int packed, int iters, cudaStream_t st);
 void launch_peer_allreduce(const PeerDev& pd, float* data, int n, cudaStream_t st);
 struct VisArgs;
 void launch_vis_color(const ModelDev& m, const Workspace& w, const float* verts, int n, const float color[3], float focal,

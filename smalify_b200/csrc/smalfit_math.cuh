@@ -360,97 +360,6 @@ SMF_HD bool face_eval_core(const FaceSetup& f, float px, float py, Fragment& fr)
     return true;
 }
 
-// Forward-only fragment test straight from the nine vertex floats: the signed squared distance
-// (and, when want_pz, the depth -- bit-identical to face_eval's) without building a FaceSetup.
-// Segment distances use |a|^2, |b|^2 and cross^2/|e|^2 (equal to the clamped-t form in exact
-// arithmetic); the blur-expanded bbox test is implied by the distance test and omitted.
-SMF_HD bool frag_forward(float x0, float y0, float z0, float x1, float y1, float z1, float x2, float y2, float z2,
-                         float px, float py, bool want_pz, float& sd, float& pz) {
-    const float e01x = fsub(x1, x0), e01y = fsub(y1, y0);
-    const float e02x = fsub(x2, x0), e02y = fsub(y2, y0);
-    const float e12x = fsub(x2, x1), e12y = fsub(y2, y1);
-    const float area = cross2(e02x, e02y, e01x, e01y);
-    if ((area <= RAST_EPS && area >= -RAST_EPS) || fmaxf(z0, fmaxf(z1, z2)) < 0.f) return false;
-    const float den = fadd(area, RAST_EPS);
-    const float ax = fsub(px, x0), ay = fsub(py, y0);
-    const float bx = fsub(px, x1), by = fsub(py, y1);
-    const float cx = fsub(px, x2), cy = fsub(py, y2);
-    const float n0 = cross2(bx, by, e12x, e12y);
-    const float n1 = cross2(e02x, e02y, cx, cy);
-    const float n2 = cross2(ax, ay, e01x, e01y);
-    pz = 0.f;
-    if (want_pz) {
-        const float rden = 1.f / den;
-        const float w0 = fmul(n0, rden), w1 = fmul(n1, rden), w2 = fmul(n2, rden);
-        pz = ffma(w2, z2, ffma(w1, z1, fmul(w0, z0)));
-        if (pz < 0.f) return false;
-    } else {
-        const float sn = ffma(n2, z2, ffma(n1, z1, fmul(n0, z0)));
-        if ((sn < 0.f && den > 0.f) || (sn > 0.f && den < 0.f)) return false;
-    }
-    const bool inside = (den > 0.f) ? (n0 > 0.f && n1 > 0.f && n2 > 0.f) : (n0 < 0.f && n1 < 0.f && n2 < 0.f);
-    const float da = dot2(ax, ay, ax, ay), db = dot2(bx, by, bx, by), dc = dot2(cx, cy, cx, cy);
-    const float l01 = dot2(e01x, e01y, e01x, e01y), l02 = dot2(e02x, e02y, e02x, e02y), l12 = dot2(e12x, e12y, e12x, e12y);
-    const float p01 = dot2(e01x, e01y, ax, ay), p02 = dot2(e02x, e02y, ax, ay), p12 = dot2(e12x, e12y, bx, by);
-#if defined(__CUDA_ARCH__)
-    float r01, r02, r12;      // MUFU.RCP (1 ulp): the squared distances feed a sigmoid, 1e-7 relative is ample
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r01) : "f"(l01));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r02) : "f"(l02));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r12) : "f"(l12));
-    const float i01 = fmul(fmul(n2, n2), r01), i02 = fmul(fmul(n1, n1), r02), i12 = fmul(fmul(n0, n0), r12);
-#else
-    const float i01 = n2 * n2 / l01, i02 = n1 * n1 / l02, i12 = n0 * n0 / l12;
-#endif
-    const float d01 = (l01 <= RAST_EPS || p01 >= l01) ? db : (p01 <= 0.f ? da : i01);
-    const float d02 = (l02 <= RAST_EPS || p02 >= l02) ? dc : (p02 <= 0.f ? da : i02);
-    const float d12 = (l12 <= RAST_EPS || p12 >= l12) ? dc : (p12 <= 0.f ? db : i12);
-    const float d = fminf(d01, fminf(d02, d12));
-    if (!inside && d >= RAST_BLUR) return false;
-    sd = inside ? -d : d;
-    return true;
-}
-
-// Backward-side fragment test: the same acceptance arithmetic as frag_forward (edge functions, depth,
-// |a|^2 / cross^2/|e|^2 distances -- here with the set-up's exact 1/|e|^2), plus, for the closest edge only
-// (ties 01 -> 02 -> 12, PointTriangleDistanceBackward), the clamped parameter and (p_proj - p).
-SMF_HD bool frag_backward(const FaceSetup& f, float px, float py, bool want_pz, Fragment& fr) {
-    if (f.valid == 0.f) return false;
-    const float ax = fsub(px, f.x0), ay = fsub(py, f.y0);
-    const float bx = fsub(px, f.x1), by = fsub(py, f.y1);
-    const float cx = fsub(px, f.x2), cy = fsub(py, f.y2);
-    const float n0 = cross2(bx, by, f.e12x, f.e12y);
-    const float n1 = cross2(f.e02x, f.e02y, cx, cy);
-    const float n2 = cross2(ax, ay, f.e01x, f.e01y);
-    fr.pz = 0.f;
-    if (want_pz) {
-        const float w0 = fmul(n0, f.rden), w1 = fmul(n1, f.rden), w2 = fmul(n2, f.rden);
-        fr.pz = ffma(w2, f.z2, ffma(w1, f.z1, fmul(w0, f.z0)));
-        if (fr.pz < 0.f) return false;
-    } else {
-        const float sn = ffma(n2, f.z2, ffma(n1, f.z1, fmul(n0, f.z0)));
-        if ((sn < 0.f && f.rden > 0.f) || (sn > 0.f && f.rden < 0.f)) return false;
-    }
-    const bool inside = (f.rden > 0.f) ? (n0 > 0.f && n1 > 0.f && n2 > 0.f) : (n0 < 0.f && n1 < 0.f && n2 < 0.f);
-    const float da = dot2(ax, ay, ax, ay), db = dot2(bx, by, bx, by), dc = dot2(cx, cy, cx, cy);
-    const float p01 = dot2(f.e01x, f.e01y, ax, ay), p02 = dot2(f.e02x, f.e02y, ax, ay), p12 = dot2(f.e12x, f.e12y, bx, by);
-    // rl == 0 marks a degenerate edge (distance to its end point); p * rl >= 1 <=> projection beyond the end
-    const float t01 = fmul(p01, f.rl01), t02 = fmul(p02, f.rl02), t12 = fmul(p12, f.rl12);
-    const float d01 = (f.rl01 == 0.f || t01 >= 1.f) ? db : (p01 <= 0.f ? da : fmul(fmul(n2, n2), f.rl01));
-    const float d02 = (f.rl02 == 0.f || t02 >= 1.f) ? dc : (p02 <= 0.f ? da : fmul(fmul(n1, n1), f.rl02));
-    const float d12 = (f.rl12 == 0.f || t12 >= 1.f) ? dc : (p12 <= 0.f ? db : fmul(fmul(n0, n0), f.rl12));
-    float d, t, ex, ey, sx, sy;
-    if (d01 <= d02 && d01 <= d12) { fr.edge = 0; d = d01; t = t01; ex = f.e01x; ey = f.e01y; sx = ax; sy = ay; if (f.rl01 == 0.f) t = 1.f; }
-    else if (d02 <= d01 && d02 <= d12) { fr.edge = 1; d = d02; t = t02; ex = f.e02x; ey = f.e02y; sx = ax; sy = ay; if (f.rl02 == 0.f) t = 1.f; }
-    else { fr.edge = 2; d = d12; t = t12; ex = f.e12x; ey = f.e12y; sx = bx; sy = by; if (f.rl12 == 0.f) t = 1.f; }
-    if (!inside && d >= RAST_BLUR) return false;
-    t = fsat(t);
-    fr.t = t;
-    fr.qx = ffma(t, ex, -sx);
-    fr.qy = ffma(t, ey, -sy);
-    fr.sd = inside ? -d : d;
-    return true;
-}
-
 // Forward-side fragment test against a prepared face (edges, 1/(area+eps) and 1/|e|^2 from
 // face_setup): face_eval without the bounding-box test (implied by the distance test) and without
 // the closest-edge bookkeeping.  Depth and signed distance are formed with exactly face_eval's
@@ -480,25 +389,6 @@ SMF_HD bool frag_setup_forward(const FaceSetup& f, float px, float py, float& sd
     if (!inside && d >= RAST_BLUR) return false;
     sd = inside ? -d : d;
     return true;
-}
-
-// Closest edge of an accepted fragment with its clamped parameter and (p_proj - p), the
-// quantities PointTriangleDistanceBackward differentiates (ties 01 -> 02 -> 12).
-SMF_HD void closest_edge(const FaceSetup& f, float px, float py, Fragment& fr) {
-    const float ax = fsub(px, f.x0), ay = fsub(py, f.y0);
-    const float bx = fsub(px, f.x1), by = fsub(py, f.y1);
-    const float t01 = (f.rl01 == 0.f) ? 1.f : fsat(fmul(dot2(f.e01x, f.e01y, ax, ay), f.rl01));
-    const float q01x = ffma(t01, f.e01x, -ax), q01y = ffma(t01, f.e01y, -ay);
-    const float d01 = dot2(q01x, q01y, q01x, q01y);
-    const float t02 = (f.rl02 == 0.f) ? 1.f : fsat(fmul(dot2(f.e02x, f.e02y, ax, ay), f.rl02));
-    const float q02x = ffma(t02, f.e02x, -ax), q02y = ffma(t02, f.e02y, -ay);
-    const float d02 = dot2(q02x, q02y, q02x, q02y);
-    const float t12 = (f.rl12 == 0.f) ? 1.f : fsat(fmul(dot2(f.e12x, f.e12y, bx, by), f.rl12));
-    const float q12x = ffma(t12, f.e12x, -bx), q12y = ffma(t12, f.e12y, -by);
-    const float d12 = dot2(q12x, q12y, q12x, q12y);
-    if (d01 <= d02 && d01 <= d12) { fr.edge = 0; fr.t = t01; fr.qx = q01x; fr.qy = q01y; }
-    else if (d02 <= d01 && d02 <= d12) { fr.edge = 1; fr.t = t02; fr.qx = q02x; fr.qy = q02y; }
-    else { fr.edge = 2; fr.t = t12; fr.qx = q12x; fr.qy = q12y; }
 }
 
 // 1 - sigmoid(-sd/sigma) the way the reference forms it in fp32: p = sigmoid(x), m = 1 - p.

@@ -60,7 +60,7 @@ def fit_sequence(model: SMALFitter, schedule=K.STAGE_SCHEDULE, window_size: int 
         last = None
         if fused:
             fused_loop.reset_optimizer()
-            model._sync_visibility(0, n)
+            model._sync_visibility(model.frame_shard[0], model.frame_shard[1] - model.frame_shard[0])
             train = (int(model.betas.requires_grad), int(model.log_beta_scales.requires_grad), 1,
                      int(model.joint_rotations.requires_grad), 1)
             for epoch_id in range(epochs):

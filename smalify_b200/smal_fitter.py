@@ -100,10 +100,14 @@ class _LossGradFn(torch.autograd.Function):
                 out.append(grad_loss * ctx.g_lbs if f.use_unity_prior else torch.zeros_like(f.log_beta_scales))
             else:
                 out.append(None)
+        whole = (a == 0 and n == ws["trans"].shape[0])
         for idx, key in ((6, "global_rotation"), (7, "joint_rotations"), (8, "trans")):
             if need[idx]:
-                g = torch.zeros_like(ws[key])
-                g[a:a + n] = grad_loss * ws[key][a:a + n]
+                if whole:                         # one window covers the sequence: no zero fill / slice copy
+                    g = grad_loss * ws[key]
+                else:
+                    g = torch.zeros_like(ws[key])
+                    g[a:a + n] = grad_loss * ws[key][a:a + n]
                 out.append(g)
             else:
                 out.append(None)
@@ -139,7 +143,16 @@ class SMALFitter(nn.Module):
 
     def __init__(self, device, data_batch, batch_size, shape_family, use_unity_prior,
                  constants: model_io.SmalConstants | None = None, data_root: str | None = None,
-                 resident_targets: bool = True, per_frame_shapes: bool = False, joint_limits=None, focal=None):
+                 resident_targets: bool = True, per_frame_shapes: bool = False, joint_limits=None, focal=None,
+                 frame_shard=None, pool_entries_per_frame: int = 0, binarize_masks: bool = False):
+        """Beyond the reference's arguments (smal_fitter.py:26-30):
+        frame_shard=(lo, hi): this process fits frames [lo, hi) of the sequence (one rank of a frame-sharded run): the
+            library's workspace and resident targets are sized for those frames only; parameters keep their full
+            (N, ...) layout.  forward() then takes batch ranges inside [lo, hi).
+        pool_entries_per_frame: capacity of the rasteriser's (face, tile) pool (0 = heuristic); an overflow raises.
+        binarize_masks: the silhouette targets are stored as uint8 {0, 1}.  The reference takes the L1 distance to
+            the float mask (smal_fitter.py:172-173), which is the same thing for the binary masks its loaders
+            produce; a mask with other values is rejected unless this flag asks for thresholding at 0.5."""
         super().__init__()
         self.rgb_imgs, self.sil_imgs, self.target_joints, self.target_visibility = data_batch
         self.target_visibility = self.target_visibility.long()
@@ -195,7 +208,11 @@ class SMALFitter(nn.Module):
         self.rotation_mask = torch.ones(K.N_POSE, 3, device=dev)
 
         self.faces = torch.from_numpy(np.asarray(constants.faces).astype(np.int64)).to(dev)
-        self._handle = _cabi.Handle(constants, self.device.index, n, self.image_size, self.use_unity_prior)
+        self.frame_shard = (0, n) if frame_shard is None else (int(frame_shard[0]), int(frame_shard[1]))
+        if not (0 <= self.frame_shard[0] < self.frame_shard[1] <= n):
+            raise ValueError(f"frame_shard {frame_shard} outside the {n}-frame sequence")
+        self._handle = _cabi.Handle(constants, self.device.index, n, self.image_size, self.use_unity_prior,
+                                    frame_shard=self.frame_shard, pool_entries_per_frame=pool_entries_per_frame)
         if self.per_frame_shapes:
             self._handle.check(self._handle.lib.smalfit_set_per_frame_shapes(self._handle.h, 1), "smalfit_set_per_frame_shapes")
         # extension: the joint-limit term the reference keeps commented out (smal_fitter.py:77-79,
@@ -222,14 +239,25 @@ class SMALFitter(nn.Module):
         self._masks_sent = None
         self._vis_sent = None
         # host copies in the layout the library takes (uint8 masks, float32 joints)
-        self._sil_u8 = (self.sil_imgs.reshape(n, self.image_size, self.image_size) > 0.5).to(torch.uint8).contiguous()
+        sil_f = self.sil_imgs.reshape(n, self.image_size, self.image_size)
+        if not binarize_masks and not bool(((sil_f == 0) | (sil_f == 1)).all()):
+            raise ValueError("silhouette targets must be binary {0, 1} masks (the library keeps them as uint8); "
+                             "pass binarize_masks=True to threshold soft masks at 0.5")
+        self._sil_u8 = (sil_f > 0.5).to(torch.uint8).contiguous()
         self._joints_f32 = self.target_joints.reshape(n, K.N_KEYPOINTS, 2).float().contiguous()
         if self.device.type == "cuda":
             self._sil_u8 = self._sil_u8.pin_memory() if not self._sil_u8.is_cuda else self._sil_u8
             self._joints_f32 = self._joints_f32.pin_memory() if not self._joints_f32.is_cuda else self._joints_f32
-        self._upload_targets(0, n)
+        self._upload_targets(self.frame_shard[0], self.frame_shard[1] - self.frame_shard[0])
+        self._n_forward = 0
 
     # ------------------------------------------------------------------
+    def check_faults(self):
+        """Raises if a kernel reported a sticky fault (bin-pool overflow: inexact silhouette terms; peer timeout).
+        Reads a host-mapped word: no synchronisation, so a fault of the step just enqueued may only show on the
+        next call."""
+        self._handle.raise_on_fault()
+
     def _lbs_dev(self):
         return self.log_beta_scales if self.use_unity_prior else self._zero_logscale
 
@@ -252,10 +280,20 @@ class SMALFitter(nn.Module):
             torch.cuda.current_stream(self.device).synchronize()     # vis is a temporary host tensor
 
     def _sync_visibility(self, a, n):
+        """The stage loop rewrites target_visibility in place or rebinds it (optimize_to_joints.py:98-110): the rows
+        are sent again only when the tensor or its version counter changed since they were last sent."""
+        tv = self.target_visibility
+        # (host tensor, as the loaders produce: its content is the key -- a rebound tensor can reuse a freed address)
+        key = hash(tv.numpy().tobytes()) if tv.device.type == "cpu" else (tv.data_ptr(), tv._version)
+        if self._vis_sent is None or self._vis_sent[0] != key:
+            self._vis_sent = (key, set())
+        if (a, n) in self._vis_sent[1]:
+            return
         vis = self._vis_u8(a, n).to(self.device, non_blocking=False)
         h = self._handle
         h.check(h.lib.smalfit_set_visibility(h.h, a, n, _ptr(vis), 0, _stream(self.device)), "smalfit_set_visibility")
         self._vis_keepalive = vis
+        self._vis_sent[1].add((a, n))
 
     def _sync_masks(self):
         key = (self.global_mask._version, self.global_mask.data_ptr(), self.rotation_mask._version, self.rotation_mask.data_ptr())
@@ -294,6 +332,7 @@ class SMALFitter(nn.Module):
     def forward(self, batch_range, weights, stage_id):
         """SMALFitter.forward (smal_fitter.py:107-175): returns (loss, objs)."""
         a, n = _contiguous_range(batch_range)
+        self._n_forward += 1
         self._sync_masks()
         self._set_window_for(a, n)
         if self.resident_targets:
@@ -341,7 +380,7 @@ class SMALFitter(nn.Module):
     def render(self, batch_range=None):
         """Soft silhouettes (B,1,S,S) and projected keypoints (B,25,2) of the current
         parameters (Renderer.forward's first two outputs, p3d_renderer.py:61-74)."""
-        a, n = _contiguous_range(batch_range if batch_range is not None else range(self.num_images))
+        a, n = _contiguous_range(batch_range if batch_range is not None else range(*self.frame_shard))
         self._sync_masks()
         S = self.image_size
         sil = torch.empty(n, 1, S, S, device=self.device)
@@ -354,7 +393,7 @@ class SMALFitter(nn.Module):
 
     @torch.no_grad()
     def vertices(self, batch_range=None):
-        a, n = _contiguous_range(batch_range if batch_range is not None else range(self.num_images))
+        a, n = _contiguous_range(batch_range if batch_range is not None else range(*self.frame_shard))
         self._sync_masks()
         v = torch.empty(n, self.constants.v_template.shape[0], 3, device=self.device)
         params = _tensors(self.betas, self._lbs_dev(), self.global_rotation, self.joint_rotations, self.trans)
@@ -427,28 +466,47 @@ class SMALFitter(nn.Module):
         h.check(h.lib.smalfit_counters(h.h, arr, _stream(self.device)), "smalfit_counters")
         return dict(capped_pixels=arr[0], spilled_pixels=arr[1], dropped_bin_entries=arr[2], launches=arr[3])
 
-    def work_counts(self, frame0=0, n=None):
-        """(pixel, face) pairs and (face, tile) entries of the last rasterised pass (diagnostic, synchronises)."""
-        arr = (ctypes.c_int64 * 2)()
+    def work_counts(self, frame0=None, n=None):
+        """(pixel, face) pairs and (face, tile) entries of the last rasterised pass, and -- accumulated by the
+        backward while profiling is on -- the pairs in pixels that carry a gradient / that contribute to it
+        (diagnostic, synchronises)."""
+        arr = (ctypes.c_int64 * 4)()
         h = self._handle
-        n = self.num_images - frame0 if n is None else n
+        frame0 = self.frame_shard[0] if frame0 is None else frame0
+        n = self.frame_shard[1] - frame0 if n is None else n
         h.check(h.lib.smalfit_work_counts(h.h, frame0, n, arr, _stream(self.device)), "smalfit_work_counts")
-        return dict(pairs=arr[0], tile_entries=arr[1])
+        return dict(pairs=arr[0], tile_entries=arr[1], live_pairs=arr[2], used_pairs=arr[3])
+
+    def fp32_peak(self):
+        """Measured FP32 FMA ceiling of this GPU in TFLOP/s: scalar FFMA and packed FFMA2 (roofline denominator)."""
+        arr = (ctypes.c_float * 2)()
+        h = self._handle
+        h.check(h.lib.smalfit_fp32_peak(h.h, arr, _stream(self.device)), "smalfit_fp32_peak")
+        return dict(ffma=float(arr[0]), ffma2=float(arr[1]))
 
     # ------------------------------------------------------------------
     def export_parameters(self, frame_id):
-        """The per-frame dict ImageExporter pickles (smal_fitter.py:213-219,268)."""
+        """The per-frame dict ImageExporter pickles (smal_fitter.py:213-219,268): this frame's rotations and
+        translation, and the shape the frame is rendered with (the shared one, or the frame's own when every frame
+        has its own shape): betas (20,), log_betascale (6,)."""
         with torch.no_grad():
+            betas = self.betas[frame_id] if self.per_frame_shapes else self.betas
+            if self.per_frame_shapes or not self.use_unity_prior:
+                scales = self.log_beta_scales[frame_id]
+            else:
+                scales = self.log_beta_scales
             return {
                 "global_rotation": (self.global_rotation[frame_id] * self.global_mask[0]).cpu().numpy(),
                 "joint_rotations": (self.joint_rotations[frame_id] * self.rotation_mask).cpu().numpy(),
-                "betas": self.betas.detach().cpu().numpy(),
-                "log_betascale": (self.log_beta_scales if self.use_unity_prior else self.log_beta_scales[frame_id]).detach().cpu().numpy(),
+                "betas": betas.detach().cpu().numpy(),
+                "log_betascale": scales.detach().cpu().numpy(),
                 "trans": self.trans[frame_id].detach().cpu().numpy(),
             }
 
     def load_checkpoint(self, checkpoint_path, epoch):
-        """smal_fitter.py:192-207: per-frame pickles; betas / scales are averaged over frames."""
+        """smal_fitter.py:192-207: per-frame pickles; the shared betas / scales become the mean over frames (with one
+        shape per frame every frame keeps its own).  Values are copied into the existing parameter storage, so the
+        library handle and any FusedFit views stay valid."""
         beta_list, scale_list = [], []
         with torch.no_grad():
             for frame_id in range(self.num_images):
@@ -458,44 +516,55 @@ class SMALFitter(nn.Module):
                 self.global_rotation[frame_id] = torch.from_numpy(p["global_rotation"]).float().to(self.device)
                 self.joint_rotations[frame_id] = torch.from_numpy(p["joint_rotations"]).float().to(self.device).view(K.N_POSE, 3)
                 self.trans[frame_id] = torch.from_numpy(p["trans"]).float().to(self.device)
-                beta_list.append(p["betas"][:self.n_betas])
-                scale_list.append(p["log_betascale"])
-        self.betas = nn.Parameter(torch.from_numpy(np.mean(beta_list, axis=0)).float().to(self.device))
-        self.log_beta_scales = nn.Parameter(torch.from_numpy(np.mean(scale_list, axis=0)).float().to(self.device))
+                beta_list.append(np.asarray(p["betas"]).reshape(-1)[:self.n_betas])
+                scale_list.append(np.asarray(p["log_betascale"]).reshape(-1)[:6])
+            betas = torch.from_numpy(np.stack(beta_list)).float().to(self.device)
+            scales = torch.from_numpy(np.stack(scale_list)).float().to(self.device)
+            if self.per_frame_shapes:
+                self.betas.copy_(betas)
+                self.log_beta_scales.copy_(scales)
+            else:
+                self.betas.copy_(betas.mean(0))
+                self.log_beta_scales.copy_(scales.mean(0) if self.use_unity_prior else scales)
 
 
 class FusedFit:
-    """One call = one epoch of optimize_to_joints.py:117-137 on flat device buffers:
-    loss + gradients of every window, temporal term, [all-reduce of the flat gradient when the
-    frames are sharded over ranks], Adam.  Parameters stay the fitter's nn.Parameters
-    (re-pointed at slices of one flat buffer)."""
+    """One call = one epoch of optimize_to_joints.py:117-137 on flat device buffers, as ONE library call
+    (smalfit_fused_step): loss + gradients of every window with the temporal term folded in, then a single tail
+    kernel that [exchanges the gradient with the peer ranks over NVLink and] applies Adam.  Parameters stay the
+    fitter's nn.Parameters (re-pointed at slices of one flat buffer).
 
-    SIZES = lambda n: (20, 6, n * 3, n * K.N_POSE * 3, n * 3)  # noqa: E731
+    collective (frames sharded over `process_group` only):
+      "peer"  the exchange lives inside the tail kernel (peer memory, rank-ordered sums, bit-identical replicas);
+              needs equal contiguous shards, rank r owning frames [r n, (r + 1) n)
+      "nccl"  the unfused sequence: loss_grad, one torch.distributed.all_reduce of the flat gradient, temporal, Adam
+    With one shape per frame (`per_frame_shapes`, BASELINE config 4) nothing is shared between frames: no
+    collective at all, every rank steps its own frames only."""
+
+    NAMES = ("betas", "log_beta_scales", "global_rotation", "joint_rotations", "trans")
 
     def __init__(self, fitter: SMALFitter, window_size: int | None = None, frame_shard=None, process_group=None,
-                 collective: str = "nccl"):
-        """collective (frames sharded over `process_group` only): "nccl" = one torch.distributed.all_reduce of the
-        flat gradient per step; "peer" = libsmalfit's one-shot all-reduce over NVLink peer memory
-        (smalfit_peer_allreduce: one kernel per rank, rank-ordered sum), set up here with an all_gather of the
-        CUDA IPC handles."""
+                 collective: str = "peer"):
         self.f = fitter
         n = fitter.num_images
         dev = fitter.device
         if not fitter.use_unity_prior:
             raise NotImplementedError("FusedFit supports the unity-prior (shared log_beta_scales) configuration")
+        if collective not in ("nccl", "peer"):
+            raise ValueError("collective must be 'nccl' or 'peer'")
         ns = n if fitter.per_frame_shapes else 1
         self.sizes = (ns * 20, ns * 6, n * 3, n * K.N_POSE * 3, n * 3)
         total = sum(self.sizes)
+        nt = _cabi.N_TERMS_FUSED
         self.flat_p = torch.empty(total, device=dev)
-        self.flat_g = torch.zeros(total + 8, device=dev)       # + the 8 loss terms: one all-reduce covers both
+        self.flat_g = torch.zeros(total + nt, device=dev)       # + the loss terms: one all-reduce covers both (nccl path)
         self.flat_m = torch.zeros(total, device=dev)
         self.flat_v = torch.zeros(total, device=dev)
-        names = ("betas", "log_beta_scales", "global_rotation", "joint_rotations", "trans")
         shapes = (tuple(fitter.betas.shape), tuple(fitter.log_beta_scales.shape), (n, 3), (n, K.N_POSE, 3), (n, 3))
         off = 0
         self.views = {}
         with torch.no_grad():
-            for name, size, shape in zip(names, self.sizes, shapes):
+            for name, size, shape in zip(self.NAMES, self.sizes, shapes):
                 par = getattr(fitter, name)
                 self.flat_p[off:off + size] = par.detach().reshape(-1)
                 par.data = self.flat_p[off:off + size].view(shape)
@@ -508,23 +577,31 @@ class FusedFit:
         fitter.set_windows(wins)
         fitter._windows_for = wins.copy()
         self.n_windows = (n + self.window - 1) // self.window
-        self.shard = frame_shard or (0, n)
+        self.shard = tuple(frame_shard) if frame_shard is not None else tuple(fitter.frame_shard)
+        if not (fitter.frame_shard[0] <= self.shard[0] and self.shard[1] <= fitter.frame_shard[1]):
+            raise ValueError(f"frame_shard {self.shard} is outside the frames the fitter holds {fitter.frame_shard}")
         self.group = process_group
-        self.terms = self.flat_g[total:total + 8]
-        self.temporal_terms = torch.zeros(3, device=dev)
+        self.sharded = process_group is not None and not fitter.per_frame_shapes
+        self.terms = self.flat_g[total:total + nt]
+        self.temporal_terms = self.terms[8:11]
         self.step_count = 0
         self._graph = None
         self._graph_key = None
         self._warmed = False
-        self.collective = "nccl"
-        if process_group is not None and collective == "peer":
-            self._connect_peers(total + 8)
-        elif collective not in ("nccl", "peer"):
-            raise ValueError("collective must be 'nccl' or 'peer'")
+        self.peer_error = None
+        self.collective = None
+        if self.sharded:
+            self.collective = "nccl"
+            if collective == "peer":
+                self._connect_peers(total + nt)
+        self.fused_tail = (not self.sharded) or self.collective == "peer"
+        if not self.fused_tail:
+            self.temporal_terms = torch.zeros(3, device=dev)
 
     def _connect_peers(self, n_floats: int):
-        """Sets up the peer-memory all-reduce on every rank, or on none: the ranks agree (MIN over a success
-        flag) after each step, so that a GPU without P2P / IPC access leaves all of them on NCCL."""
+        """Sets up the peer-memory exchange on every rank, or on none: the ranks agree (MIN over a success
+        flag) after each step, so that a GPU without P2P / IPC access -- or shards the tail kernel cannot address --
+        leaves all of them on NCCL."""
         import torch.distributed as dist
         h, dev, group = self.f._handle, self.f.device, self.group
         rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -536,9 +613,13 @@ class FusedFit:
             dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
             return bool(t.item())
 
+        n = self.f.num_images
+        per = self.shard[1] - self.shard[0]
+        if not all_ok(per * world == n and self.shard[0] == rank * per and world <= 8):
+            self.peer_error = "unequal / non-contiguous shards (or more than 8 ranks)"
+            return
         mine_c = (ctypes.c_ubyte * 64)()
-        self.peer_error = None
-        rc = h.lib.smalfit_peer_init(h.h, rank, world, int(n_floats), mine_c) if world <= 8 else -1
+        rc = h.lib.smalfit_peer_init(h.h, rank, world, int(n_floats), mine_c)
         if not all_ok(rc == 0):
             self.peer_error = "smalfit_peer_init failed on some rank"
             return
@@ -553,15 +634,11 @@ class FusedFit:
         self.collective = "peer"
 
     def peer_timed_out(self) -> bool:
-        """True when a peer failed to arrive in some all-reduce (the step's gradient was then not reduced)."""
-        v = ctypes.c_int(0)
-        h = self.f._handle
-        h.check(h.lib.smalfit_peer_status(h.h, ctypes.byref(v), _stream(self.f.device)), "smalfit_peer_status")
-        return bool(v.value)
+        """True when a peer failed to arrive in some exchange (fatal: the kernel trapped)."""
+        return bool(self.f._handle.status() & _cabi.STATUS_PEER_TIMEOUT)
 
     def _t(self, idx):
-        names = ("betas", "log_beta_scales", "global_rotation", "joint_rotations", "trans")
-        return _tensors(*(self.views[k][idx] for k in names))
+        return _tensors(*(self.views[k][idx] for k in self.NAMES))
 
     def reset_optimizer(self):
         """Fresh Adam state, as a new torch.optim.Adam per stage (optimize_to_joints.py:96)."""
@@ -577,22 +654,24 @@ class FusedFit:
         h = f._handle
         st = _stream(f.device)
         a, b = self.shard
-        sharded = self.group is not None
-        if sharded:
-            self.flat_g.zero_()
         params, grads = self._t(0), self._t(1)
-        rank0 = (not sharded) or torch.distributed.get_rank(self.group) == 0
+        rank0 = (not self.sharded) or torch.distributed.get_rank(self.group) == 0
+        tr = (ctypes.c_int32 * 5)(*[int(x) for x in train])
+        m, v = self._t(2), self._t(3)
+        if self.fused_tail:
+            h.check(h.lib.smalfit_fused_step(h.h, ctypes.byref(params), ctypes.byref(grads), ctypes.byref(m), ctypes.byref(v),
+                                             a, b - a, f.num_images, _weights6(weights), float(w_temp),
+                                             self.n_windows if rank0 else 0, tr, float(lr), K.ADAM_BETAS[0], K.ADAM_BETAS[1],
+                                             K.ADAM_EPS, _ptr(self.terms), st), "smalfit_fused_step")
+            return
+        # unfused sequence with NCCL: frames this rank does not own must contribute zeros to the sum
+        self.flat_g.zero_()
         h.check(h.lib.smalfit_loss_grad(h.h, ctypes.byref(params), a, b - a, _weights6(weights),
                                         self.n_windows if rank0 else 0, ctypes.byref(grads), _ptr(self.terms), st),
                 "smalfit_loss_grad")
-        if sharded and self.collective == "peer":
-            h.check(h.lib.smalfit_peer_allreduce(h.h, _ptr(self.flat_g), int(self.flat_g.numel()), st), "smalfit_peer_allreduce")
-        elif sharded:
-            torch.distributed.all_reduce(self.flat_g, group=self.group)      # gradients + loss terms
+        torch.distributed.all_reduce(self.flat_g, group=self.group)      # gradients + loss terms
         h.check(h.lib.smalfit_temporal(h.h, ctypes.byref(params), f.num_images, float(w_temp), ctypes.byref(grads),
                                        _ptr(self.temporal_terms), st), "smalfit_temporal")
-        tr = (ctypes.c_int32 * 5)(*[int(x) for x in train])
-        m, v = self._t(2), self._t(3)
         h.check(h.lib.smalfit_adam_step(h.h, ctypes.byref(params), ctypes.byref(grads), ctypes.byref(m), ctypes.byref(v),
                                         f.num_images, tr, float(lr), K.ADAM_BETAS[0], K.ADAM_BETAS[1], K.ADAM_EPS,
                                         0 if device_step else self.step_count, st), "smalfit_adam_step")
@@ -604,6 +683,7 @@ class FusedFit:
         self.step_count += 1
         f = self.f
         f._sync_masks()
+        f.check_faults()                  # host-mapped word: no synchronisation (also covers the graph replays below)
         if not use_graph or not self._warmed:
             # eager launch (also the first call: loads every kernel before a capture)
             self._enqueue(weights, w_temp, lr, train, device_step=True)
@@ -623,4 +703,6 @@ class FusedFit:
         self._graph.replay()
 
     def total_loss(self) -> torch.Tensor:
+        if self.fused_tail:
+            return self.terms[_cabi.L_TOTAL]              # includes the temporal term
         return self.terms[_cabi.L_TOTAL] + self.temporal_terms.sum()

@@ -51,23 +51,6 @@ int chk_face_eval(const float* tri /* x0,y0,z0,x1,y1,z1,x2,y2,z2 */, float px, f
     return 1;
 }
 
-// lean forward variant: out = (pz, sd)
-int chk_frag_forward(const float* tri, float px, float py, int want_pz, float* out) {
-    float sd = 0.f, pz = 0.f;
-    const bool ok = frag_forward(tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8], px, py, want_pz != 0, sd, pz);
-    out[0] = pz; out[1] = sd;
-    return ok ? 1 : 0;
-}
-
-// backward variant: out = (pz, sd, t, qx, qy), returns edge + 1 (0 = no fragment)
-int chk_frag_backward(const float* tri, float px, float py, int want_pz, float* out) {
-    const FaceSetup fs = face_setup(tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8]);
-    Fragment fr;
-    if (!frag_backward(fs, px, py, want_pz != 0, fr)) return 0;
-    out[0] = fr.pz; out[1] = fr.sd; out[2] = fr.t; out[3] = fr.qx; out[4] = fr.qy;
-    return fr.edge + 1;
-}
-
 // tile-rasteriser forward variant (prepared face): out = (pz, sd)
 int chk_frag_setup_forward(const float* tri, float px, float py, float* out) {
     const FaceSetup fs = face_setup(tri[0], tri[1], tri[2], tri[3], tri[4], tri[5], tri[6], tri[7], tri[8]);

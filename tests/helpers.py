@@ -71,3 +71,30 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     b = b.double().cpu()
     a = a.double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-12))
+
+
+def bench_subsequence(constants, m: O.OracleModel, idx, S: int, n_total: int = 128, seed: int = 0):
+    """Frames `idx` of the synthetic `n_total`-frame sequence bench.py fits (same ground truth, keypoint noise and
+    visibility rows), with targets rendered by the oracle.  Returns (data_batch, gt_params_of_the_subset)."""
+    return synthetic.make_subsequence(constants, n_total, idx, S, oracle_renderer(m, S), seed=seed)
+
+
+def record_result(name: str, payload: dict):
+    """Parity figures the GPU tests measure (pixel-flip counts, error maxima) are appended to
+    gpurun_out/parity_results.json so that they travel back from the GPU box."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        path = os.path.join(out, "parity_results.json")
+        cur = {}
+        if os.path.exists(path):
+            with open(path) as fh:
+                cur = json.load(fh)
+        cur[name] = payload
+        with open(path, "w") as fh:
+            json.dump(cur, fh, indent=1, sort_keys=True)
+    except OSError:
+        pass

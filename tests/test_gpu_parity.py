@@ -316,3 +316,82 @@ def test_missing_library_fails_loudly(tmp_path):
     from smalify_b200 import _cabi
     with pytest.raises(_cabi.SmalfitError):
         _cabi.load_library(str(tmp_path / "libsmalfit_missing.so"))
+
+
+def test_fused_step_equals_the_unfused_sequence(constants, seq):
+    """smalfit_fused_step (temporal term folded into the frame kernels, Adam in the step-tail kernel) against the
+    call sequence it replaces (smalfit_loss_grad, smalfit_temporal, smalfit_adam_step): the same operations in the
+    same order, so parameters, Adam state and gradients agree BIT FOR BIT after several steps; the loss terms to
+    rounding (their sums are grouped differently)."""
+    import ctypes
+    from smalify_b200 import _cabi
+    from smalify_b200.smal_fitter import FusedFit, SMALFitter, _ptr, _stream, _weights6
+    data, _ = seq
+    row = K.STAGE_SCHEDULE[1]
+    w, w_temp, lr = row[:6], row[6], row[8]
+    fa = SMALFitter("cuda", data, N_SMALL, 1, True, constants=constants)
+    fb = SMALFitter("cuda", data, N_SMALL, 1, True, constants=constants)
+    la, lb = FusedFit(fa, 2), FusedFit(fb, 2)           # windows of 2 + 1 frames
+    assert la.fused_tail
+    h = fb._handle
+    st = _stream(fb.device)
+    temporal = torch.zeros(3, device=fb.device)
+    for step in range(1, 6):
+        la.step(w, w_temp, lr, use_graph=(step > 2))
+        params, grads, m, v = lb._t(0), lb._t(1), lb._t(2), lb._t(3)
+        h.check(h.lib.smalfit_loss_grad(h.h, ctypes.byref(params), 0, N_SMALL, _weights6(w), lb.n_windows, ctypes.byref(grads),
+                                        _ptr(lb.terms), st), "loss_grad")
+        h.check(h.lib.smalfit_temporal(h.h, ctypes.byref(params), N_SMALL, float(w_temp), ctypes.byref(grads), _ptr(temporal), st), "temporal")
+        tr = (ctypes.c_int32 * 5)(1, 1, 1, 1, 1)
+        h.check(h.lib.smalfit_adam_step(h.h, ctypes.byref(params), ctypes.byref(grads), ctypes.byref(m), ctypes.byref(v), N_SMALL, tr,
+                                        float(lr), K.ADAM_BETAS[0], K.ADAM_BETAS[1], K.ADAM_EPS, step, st), "adam")
+        torch.cuda.synchronize()
+        total = sum(la.sizes)
+        assert torch.equal(la.flat_g[:total], lb.flat_g[:total]), step
+        assert torch.equal(la.flat_p, lb.flat_p) and torch.equal(la.flat_m, lb.flat_m) and torch.equal(la.flat_v, lb.flat_v), step
+        tb = float(lb.terms[_cabi.L_TOTAL] + temporal.sum())
+        assert abs(float(la.total_loss()) - tb) <= 1e-6 * abs(tb)
+        assert torch.allclose(la.temporal_terms, temporal, rtol=1e-6, atol=0)
+    assert fa._handle.status() == 0
+
+
+def test_pool_overflow_is_reported_not_silent(constants, seq):
+    """A (face, tile) pool that is too small must not pass silently (the dropped entries make the silhouette terms
+    inexact): the sticky fault shows in smalfit_status and the next hot-path call fails."""
+    from smalify_b200 import _cabi
+    from smalify_b200.smal_fitter import SMALFitter
+    data, _ = seq
+    f = SMALFitter("cuda", data, N_SMALL, 1, True, constants=constants, pool_entries_per_frame=1024)
+    loss, _ = f(list(range(N_SMALL)), STAGE1, 1)
+    torch.cuda.synchronize()
+    assert f._handle.status() & _cabi.STATUS_POOL_OVERFLOW
+    assert f.counters()["dropped_bin_entries"] > 0
+    with pytest.raises(_cabi.SmalfitError):
+        f(list(range(N_SMALL)), STAGE1, 1)
+    with pytest.raises(_cabi.SmalfitError):
+        f.check_faults()
+
+
+def test_frame_shard_handle_matches_full_handle(constants, seq):
+    """A handle created for a shard of the frames (workspace and targets sized for them only) gives, on its frames,
+    the gradients of the full handle; frames outside the shard are rejected."""
+    from smalify_b200 import _cabi
+    from smalify_b200.smal_fitter import SMALFitter
+    data, gt = seq
+    full = SMALFitter("cuda", data, N_SMALL, 1, True, constants=constants)
+    part = SMALFitter("cuda", data, N_SMALL, 1, True, constants=constants, frame_shard=(1, 3))
+    res = []
+    for f in (full, part):
+        for t in f.parameters():
+            t.grad = None
+            t.requires_grad_(True)
+        f.set_windows(np.full(N_SMALL, 2, np.int32))
+        f._windows_for = np.full(N_SMALL, 2, np.int32)
+        loss, _ = f([1, 2], STAGE1, 1)
+        loss.backward()
+        res.append((float(loss), {k: getattr(f, k).grad.clone() for k in ("global_rotation", "trans", "joint_rotations", "betas", "log_beta_scales")}))
+    assert res[0][0] == res[1][0]
+    for k in res[0][1]:
+        assert torch.equal(res[0][1][k], res[1][1][k]), k
+    with pytest.raises(_cabi.SmalfitError):
+        part([0, 1], STAGE1, 1)

@@ -33,7 +33,7 @@ def main():
         extra = sys.argv[sys.argv.index("--") + 1:] if "--" in sys.argv else []
         for lib in sorted(glob.glob(os.path.join(VDIR, "*.so"))):
             env = dict(os.environ, SMALFIT_LIB=lib)
-            res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu-baseline", "--steps", steps] + extra,
+            res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu-baseline", "--no-quality", "--no-dropin", "--steps", steps] + extra,
                                  env=env, capture_output=True, text=True)
             try:
                 d = json.loads(res.stdout.strip().splitlines()[-1])

@@ -6,7 +6,9 @@
 1. random vectors: smalfit_peer_allreduce == the rank-ordered sum, bit for bit, and == NCCL all_reduce to rounding,
    eager and replayed from a CUDA graph, identical on every rank;
 2. latency of both collectives on the fitter's payload (CUDA events, max over ranks);
-3. a few FusedFit epochs with either collective end at the same loss.
+3. a few FusedFit epochs -- with the exchange fused into the step-tail kernel (smalfit_fused_step, "peer"), with the
+   unfused NCCL sequence, and unsharded on one GPU -- end at the same loss and parameters; the replicas of the fused
+   run are bit-identical on every rank.
 Prints one JSON line on rank 0; exit code 1 on any mismatch.
 """
 import ctypes
@@ -37,8 +39,9 @@ def main():
     ok = True
 
     def make(collective):
-        f = SMALFitter(dev, data, N, 1, True, constants=c)
-        return f, FusedFit(f, N, frame_shard=(rank * per, (rank + 1) * per), process_group=dist.group.WORLD, collective=collective)
+        # the handle only holds this rank's frames (workspace and targets O(N / ranks))
+        f = SMALFitter(dev, data, N, 1, True, constants=c, frame_shard=(rank * per, (rank + 1) * per))
+        return f, FusedFit(f, N, process_group=dist.group.WORLD, collective=collective)
 
     f_peer, loop_peer = make("peer")
     assert loop_peer.collective == "peer"
@@ -102,8 +105,27 @@ def main():
             loop.step(row[:6], row[6], row[8], use_graph=True)
         torch.cuda.synchronize()
         finals[name] = float(loop.total_loss())
+    # the same epochs unsharded on this GPU alone
+    f_one = SMALFitter(dev, data, N, 1, True, constants=c)
+    loop_one = FusedFit(f_one, N)
+    loop_one.reset_optimizer()
+    for _ in range(12):
+        loop_one.step(row[:6], row[6], row[8], use_graph=True)
+    torch.cuda.synchronize()
+    finals["one_gpu"] = float(loop_one.total_loss())
     out["final_loss"] = finals
     ok &= abs(finals["peer"] - finals["nccl"]) <= 1e-4 * abs(finals["nccl"])
+    ok &= abs(finals["peer"] - finals["one_gpu"]) <= 1e-4 * abs(finals["one_gpu"])
+    dp = float((loop_peer.flat_p - loop_one.flat_p).abs().max())
+    dn = float((loop_peer.flat_p - loop_nccl.flat_p).abs().max())
+    out["max_param_diff"] = {"peer_vs_one_gpu": dp, "peer_vs_nccl": dn}
+    ok &= dp < 1e-4 and dn < 1e-4
+    # replicas of the fused run: bit-identical parameters and Adam state on every rank
+    mine = torch.cat([loop_peer.flat_p, loop_peer.flat_m, loop_peer.flat_v])
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    out["replicas_identical"] = all(bool(torch.equal(parts[0], q)) for q in parts[1:])
+    ok &= out["replicas_identical"]
     ok &= not loop_peer.peer_timed_out()
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
