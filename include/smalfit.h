@@ -270,7 +270,9 @@ SMALFIT_API int smalfit_peer_status(smalfit_t h, int* timed_out, void* stream);
 /* Per-phase device times of the most recent smalfit_loss_grad (CUDA events on the caller's
  * stream; do not enable while capturing a CUDA graph).  ms[0] shape+frame forward,
  * [1] face preparation + binning, [2] raster forward (hand-out list + tile kernel), [3] raster backward,
- * [4] frame backward, [5] shape backward + finalize, [6] whole call. */
+ * [4] frame backward, [5] shape backward + finalize, [6] whole call.
+ * enable = 2 additionally makes the backward count the pairs smalfit_work_counts reports in counts[2..3] (this slows
+ * the backward: do not read phase times from such a pass). */
 SMALFIT_API int smalfit_set_profiling(smalfit_t h, int enable);
 SMALFIT_API int smalfit_get_profile(smalfit_t h, float ms[8]);
 
@@ -298,7 +300,7 @@ SMALFIT_API int smalfit_counters(smalfit_t h, int64_t counters[4], void* stream)
  * counts[1] = (face, 32x32 tile) entries binned
  * counts[2] = of counts[0], the pairs whose pixel carries a silhouette gradient (the backward evaluates only those)
  * counts[3] = of counts[2], the pairs that are fragments selected by the K-nearest rule (contribute to the gradient).
- * counts[2..3] are accumulated by the backward while profiling is on (smalfit_set_profiling) since the last call. */
+ * counts[2..3] are accumulated by the backward while smalfit_set_profiling(h, 2) is in effect, since the last call. */
 SMALFIT_API int smalfit_work_counts(smalfit_t h, int frame0, int n, int64_t counts[4], void* stream);
 
 /* Measured FP32 ceiling of this GPU for the roofline: TFLOP/s of a register-resident FMA chain on every SM,

@@ -458,7 +458,93 @@ namespace smf {
 // ---------------------------------------------------------------------------
 // raster_backward: one warp per (frame, face); lanes sweep the face's pixel rectangle
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) raster_backward_kernel(ModelDev m, Workspace w, int frame0) {
+#ifndef BW_PACK_MIN
+#define BW_PACK_MIN 33          // rectangles of at least this many pixels are swept two pixels per lane (packed FP32)
+#endif
+#ifndef BW_MIN_CTAS
+#define BW_MIN_CTAS 4           // resident CTAs per SM the register allocation aims for (64 registers: measured best)
+#endif
+
+struct BwFace {                 // what a sweep needs beside the prepared face
+    const uint2* pix;           // the frame's (coef, depth threshold) per pixel
+    const uint16_t* tfid;       // the frame's tie face ids
+    int S, f, c0, c1, r0, r1;
+    float inv_s;
+};
+
+// a fragment the K-nearest rule kept? (the forward's threshold: depth key, ties by face id)
+__device__ __forceinline__ bool bw_selected(const BwFace& b, uint2 pr, float pz, int x, int y) {
+    if (pr.y == 0xffffffffu) return true;
+    const unsigned key = __float_as_uint(pz + 0.f);
+    if (key > pr.y) return false;
+    return !(key == pr.y && (unsigned)b.f > (unsigned)b.tfid[(size_t)y * b.S + x]);
+}
+
+// one pixel per lane and step; the same arithmetic as the forward's fragment test: bit-identical acceptance and depth keys
+template <bool REGULAR>
+__device__ __forceinline__ void bw_sweep1(const FaceSetup& fs, const BwFace& b, int lane, float* g, unsigned& n_live, unsigned& n_used) {
+    const int wd = b.c1 - b.c0 + 1, npx = wd * (b.r1 - b.r0 + 1);
+    RectWalk wk(wd, lane);
+    for (int i = lane; i < npx; i += 32, wk.next(wd)) {
+        const int x = b.c0 + wk.cc, y = b.r0 + wk.rr;
+        const uint2 pr = b.pix[(size_t)y * b.S + x];
+        const float coef = __uint_as_float(pr.x);
+        if (coef == 0.f) continue;
+        ++n_live;
+        Fragment frag;
+        if (!face_eval_core<REGULAR>(fs, pix_to_ndc(x, b.inv_s), pix_to_ndc(y, b.inv_s), frag)) continue;
+        if (!bw_selected(b, pr, frag.pz, x, y)) continue;
+        float p, mv;
+        frag_prob(frag.sd, p, mv);
+        frag_grad(frag, -coef * p, g);
+        ++n_used;
+    }
+}
+
+// two horizontally adjacent pixels per lane (packed FP32, face_eval2): 64 pixels per step; faces without degenerate edges
+__device__ __forceinline__ void bw_sweep2(const FaceSetup& fs, const BwFace& b, int lane, float* g, unsigned& n_live, unsigned& n_used) {
+    const int wp = (b.c1 - b.c0 + 2) >> 1, npairs = wp * (b.r1 - b.r0 + 1);
+    RectWalk wk(wp, lane);
+    for (int j = lane; j < npairs; j += 32, wk.next(wp)) {
+        const int x = b.c0 + 2 * wk.cc, y = b.r0 + wk.rr;
+        const bool has1 = x < b.c1;
+        const uint2* pp = b.pix + (size_t)y * b.S + x;
+        uint2 pr[2];
+        pr[0] = pp[0];
+        pr[1] = has1 ? pp[1] : make_uint2(0u, 0u);
+        const float coef[2] = {__uint_as_float(pr[0].x), __uint_as_float(pr[1].x)};
+        if (coef[0] == 0.f && coef[1] == 0.f) continue;
+        n_live += (coef[0] != 0.f ? 1u : 0u) + (coef[1] != 0.f ? 1u : 0u);
+        const float t0 = ffma(2.f, (float)x, 1.f);
+        const f32x2 px = f2_fma(f2_pack(t0, t0 + 2.f), f2_bc(-b.inv_s), f2_bc(1.f));       // pix_to_ndc of both columns
+        bool ok[2];
+        Fragment2 f2;
+        face_eval2<true>(fs, px, pix_to_ndc(y, b.inv_s), ok, f2);
+        float p2[2], m2[2];
+        frag_prob2(f2.sd, p2, m2);
+        float d01[2], d02[2], d12[2], t01[2], t02[2], t12[2], ax01[2], ay01[2], ax02[2], ay02[2], ax12[2], ay12[2];
+        f2_unpack(f2.d01, d01[0], d01[1]); f2_unpack(f2.d02, d02[0], d02[1]); f2_unpack(f2.d12, d12[0], d12[1]);
+        f2_unpack(f2.t01, t01[0], t01[1]); f2_unpack(f2.t02, t02[0], t02[1]); f2_unpack(f2.t12, t12[0], t12[1]);
+        f2_unpack(f2.nq01x, ax01[0], ax01[1]); f2_unpack(f2.nq01y, ay01[0], ay01[1]);
+        f2_unpack(f2.nq02x, ax02[0], ax02[1]); f2_unpack(f2.nq02y, ay02[0], ay02[1]);
+        f2_unpack(f2.nq12x, ax12[0], ax12[1]); f2_unpack(f2.nq12y, ay12[0], ay12[1]);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (coef[k] == 0.f || !ok[k]) continue;
+            if (!bw_selected(b, pr[k], f2.pz[k], x + k, y)) continue;
+            // closest edge, ties 01 -> 02 -> 12 (PointTriangleDistanceBackward order); (qx, qy) hold -(p_proj - p)
+            Fragment frag;
+            if (d01[k] <= d02[k] && d01[k] <= d12[k]) { frag.edge = 0; frag.t = t01[k]; frag.qx = ax01[k]; frag.qy = ay01[k]; }
+            else if (d02[k] <= d01[k] && d02[k] <= d12[k]) { frag.edge = 1; frag.t = t02[k]; frag.qx = ax02[k]; frag.qy = ay02[k]; }
+            else { frag.edge = 2; frag.t = t12[k]; frag.qx = ax12[k]; frag.qy = ay12[k]; }
+            frag.sd = f2.sd[k];
+            frag_grad(frag, coef[k] * p2[k], g);          // = frag_grad(q, -coef p): the sign sits in (qx, qy)
+            ++n_used;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, BW_MIN_CTAS) raster_backward_kernel(ModelDev m, Workspace w, int frame0) {
     const int lane = threadIdx.x & 31;
     const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int fr = frame0 + blockIdx.y;
@@ -467,10 +553,11 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(ModelDev m, Worksp
     const float4* rec = w.face_rec + ((size_t)fr * m.Fp + f) * 4;
     const float4 q3 = __ldg(rec + 3);
     const unsigned rx = __float_as_uint(q3.z), ry = __float_as_uint(q3.w);
-    const int c0 = (int)(rx & 0xffffu), c1 = (int)(rx >> 16), r0 = (int)(ry & 0xffffu), r1 = (int)(ry >> 16);
+    BwFace b;
+    b.c0 = (int)(rx & 0xffffu); b.c1 = (int)(rx >> 16); b.r0 = (int)(ry & 0xffffu); b.r1 = (int)(ry >> 16);
     float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     unsigned n_live = 0u, n_used = 0u;
-    if (c0 <= c1) {
+    if (b.c0 <= b.c1) {
         const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
         FaceSetup fs;
         fs.x0 = q0.x; fs.y0 = q0.y; fs.x1 = q0.z; fs.y1 = q0.w; fs.x2 = q1.x; fs.y2 = q1.y;
@@ -479,34 +566,14 @@ __global__ void __launch_bounds__(256) raster_backward_kernel(ModelDev m, Worksp
         fs.e01x = fsub(fs.x1, fs.x0); fs.e01y = fsub(fs.y1, fs.y0);
         fs.e02x = fsub(fs.x2, fs.x0); fs.e02y = fsub(fs.y2, fs.y0);
         fs.e12x = fsub(fs.x2, fs.x1); fs.e12y = fsub(fs.y2, fs.y1);
-        const int S = w.S;
-        const float inv_s = 1.f / (float)S;
-        const int wd = c1 - c0 + 1, npx = wd * (r1 - r0 + 1);
-        float inv_w;      // MUFU reciprocal: (i + 0.5) / wd stays far from an integer for rectangles of sane width
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_w) : "f"((float)wd));
-        const uint2* pix = w.pix + (size_t)fr * S * S;
-        for (int i = lane; i < npx; i += 32) {
-            int rr = (int)(((float)i + 0.5f) * inv_w);
-            int cc = i - rr * wd;
-            if (cc < 0) { cc += wd; --rr; } else if (cc >= wd) { cc -= wd; ++rr; }      // very wide rectangles: exact anyway
-            const int x = c0 + cc, y = r0 + rr;
-            const uint2 pr = pix[(size_t)y * S + x];
-            const float coef = __uint_as_float(pr.x);
-            if (coef == 0.f) continue;
-            ++n_live;
-            // the same arithmetic as the forward's fragment test: bit-identical acceptance and depth keys
-            Fragment frag;
-            if (!face_eval_core(fs, pix_to_ndc(x, inv_s), pix_to_ndc(y, inv_s), frag)) continue;
-            if (pr.y != 0xffffffffu) {
-                const unsigned key = __float_as_uint(frag.pz + 0.f);
-                if (key > pr.y) continue;
-                if (key == pr.y && (unsigned)f > (unsigned)w.pix_tfid[((size_t)fr * S + y) * S + x]) continue;
-            }
-            float p, mv;
-            frag_prob(frag.sd, p, mv);
-            frag_grad(frag, -coef * p, g);
-            ++n_used;
-        }
+        b.S = w.S; b.f = f; b.inv_s = 1.f / (float)w.S;
+        b.pix = w.pix + (size_t)fr * b.S * b.S;
+        b.tfid = w.pix_tfid + (size_t)fr * b.S * b.S;
+        const int npx = (b.c1 - b.c0 + 1) * (b.r1 - b.r0 + 1);
+        const bool regular = (fs.rl01 != 0.f) && (fs.rl02 != 0.f) && (fs.rl12 != 0.f);       // no degenerate edge (warp-uniform)
+        if (!regular) bw_sweep1<false>(fs, b, lane, g, n_live, n_used);
+        else if (npx >= BW_PACK_MIN) bw_sweep2(fs, b, lane, g, n_live, n_used);
+        else bw_sweep1<true>(fs, b, lane, g, n_live, n_used);
         if (w.count_pairs) {
             n_live = __reduce_add_sync(0xffffffffu, n_live);
             n_used = __reduce_add_sync(0xffffffffu, n_used);
@@ -955,6 +1022,18 @@ void launch_temporal(const Workspace& w, const Params& p, const Grads& g, int N,
 // Adam (torch.optim.Adam semantics, no weight decay / amsgrad).  The step count and the
 // bias corrections live on the device so that a whole step can sit in a CUDA graph.
 // ---------------------------------------------------------------------------
+// One element of torch.optim.Adam.step() (no weight decay / amsgrad), every rounding pinned so that the three kernels
+// that apply it (adam, adam5, step_tail) agree bit for bit: exp_avg.mul_(b1).add_(g, alpha = 1 - b1),
+// exp_avg_sq.mul_(b2).addcmul_(g, g, value = 1 - b2), p.addcdiv_(exp_avg, sqrt(exp_avg_sq) / sqrt(bc2) + eps, value = -lr / bc1).
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float lr, float b1, float b2, float eps,
+                                            float bc1, float bc2_sqrt) {
+    const float mi = __fmaf_rn(1.f - b1, g, __fmul_rn(b1, m));
+    const float vi = __fmaf_rn(__fmul_rn(1.f - b2, g), g, __fmul_rn(b2, v));
+    m = mi; v = vi;
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+    p = __fsub_rn(p, __fmul_rn(__fdiv_rn(lr, bc1), __fdiv_rn(mi, denom)));
+}
+
 __global__ void adam_tick_kernel(AdamState* s, float b1, float b2, int host_step) {
     const int step = (host_step > 0) ? host_step : s->step + 1;
     s->step = step;
@@ -966,13 +1045,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* p, const float* g, flo
                                                    float b1, float b2, float eps, const AdamState* s) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float bc1 = s->bc1, bc2_sqrt = s->bc2_sqrt;
-    const float gi = g[i];
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi; v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] -= (lr / bc1) * (mi / denom);
+    adam_update(p[i], g[i], m[i], v[i], lr, b1, b2, eps, s->bc1, s->bc2_sqrt);
 }
 
 __global__ void __launch_bounds__(256) adam5_kernel(AdamSegments seg, float lr, float b1, float b2, float eps, const AdamState* s) {
@@ -983,13 +1056,7 @@ __global__ void __launch_bounds__(256) adam5_kernel(AdamSegments seg, float lr, 
         if (k == q && i >= seg.len[q]) { i -= seg.len[q]; k = q + 1; }
     }
     if (k >= 5 || !seg.train[k]) return;
-    const float bc1 = s->bc1, bc2_sqrt = s->bc2_sqrt;
-    const float gi = seg.g[k][i];
-    const float mi = b1 * seg.m[k][i] + (1.f - b1) * gi;
-    const float vi = b2 * seg.v[k][i] + (1.f - b2) * gi * gi;
-    seg.m[k][i] = mi; seg.v[k][i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    seg.p[k][i] -= (lr / bc1) * (mi / denom);
+    adam_update(seg.p[k][i], seg.g[k][i], seg.m[k][i], seg.v[k][i], lr, b1, b2, eps, s->bc1, s->bc2_sqrt);
 }
 
 void launch_adam5(const AdamSegments& seg, float lr, float b1, float b2, float eps, const AdamState* s, cudaStream_t st) {
@@ -1211,11 +1278,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) step_tail_kernel(PeerDev pd, Tai
             gi = a.g[k] ? a.g[k][idx] : 0.f;
         }
         if (!a.train[k]) continue;
-        const float mi = a.b1 * a.m[k][idx] + (1.f - a.b1) * gi;
-        const float vi = a.b2 * a.v[k][idx] + (1.f - a.b2) * gi * gi;
-        a.m[k][idx] = mi; a.v[k][idx] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + a.eps;
-        a.p[k][idx] -= (a.lr / bc1) * (mi / denom);
+        adam_update(a.p[k][idx], gi, a.m[k][idx], a.v[k][idx], a.lr, a.b1, a.b2, a.eps, bc1, bc2_sqrt);
     }
     if (a.exchange && blockIdx.x == 0 && tid < 12) {
         float t = 0.f;

@@ -253,7 +253,8 @@ SMF_HD void screen_fwd(float xn, float yn, float half, float& row, float& col) {
 }
 
 // pixel centre of the rasteriser (x is flipped: +X left, +Y up)
-SMF_HD float pix_to_ndc(int i, float inv_s) { return 1.f - (2.f * (float)i + 1.f) * inv_s; }
+// (one rounding-pinned FMA, so that the packed two-pixel steps form bit-identical coordinates)
+SMF_HD float pix_to_ndc(int i, float inv_s) { return ffma(-ffma(2.f, (float)i, 1.f), inv_s, 1.f); }
 
 // ---------------------------------------------------------------------------
 // Soft rasteriser: one face against one pixel
@@ -320,15 +321,17 @@ struct Fragment {
 };
 
 // CheckPixelInsideFace.  Returns true when (face, pixel) yields a fragment.
-SMF_HD bool face_eval_core(const FaceSetup& f, float px, float py, Fragment& fr);
+// REGULAR: the caller knows that no edge of the face is degenerate (rl* != 0): the "distance to the end point" selects
+// are compiled out; the value computed is the same.
+template <bool REGULAR = false> SMF_HD bool face_eval_core(const FaceSetup& f, float px, float py, Fragment& fr);
 SMF_HD bool face_eval(const FaceSetup& f, float px, float py, Fragment& fr) {
     if (f.valid == 0.f) return false;
     if (px > f.bx1 || px < f.bx0 || py > f.by1 || py < f.by0) return false;
-    return face_eval_core(f, px, py, fr);
+    return face_eval_core<false>(f, px, py, fr);
 }
 // face_eval without the validity / bounding-box tests (implied for the pixels of a valid face's
 // rectangle by the distance test): needs only the vertices, edges, rden and rl* of the set-up.
-SMF_HD bool face_eval_core(const FaceSetup& f, float px, float py, Fragment& fr) {
+template <bool REGULAR> SMF_HD bool face_eval_core(const FaceSetup& f, float px, float py, Fragment& fr) {
     const float ax = fsub(px, f.x0), ay = fsub(py, f.y0);     // p - v0
     const float bx = fsub(px, f.x1), by = fsub(py, f.y1);     // p - v1
     const float cx = fsub(px, f.x2), cy = fsub(py, f.y2);     // p - v2
@@ -340,13 +343,13 @@ SMF_HD bool face_eval_core(const FaceSetup& f, float px, float py, Fragment& fr)
     const float pz = ffma(w2, f.z2, ffma(w1, f.z1, fmul(w0, f.z0)));
     if (pz < 0.f) return false;
     // squared distances to the three segments
-    const float t01 = (f.rl01 == 0.f) ? 1.f : fsat(fmul(dot2(f.e01x, f.e01y, ax, ay), f.rl01));
+    const float t01 = (!REGULAR && f.rl01 == 0.f) ? 1.f : fsat(fmul(dot2(f.e01x, f.e01y, ax, ay), f.rl01));
     const float q01x = ffma(t01, f.e01x, -ax), q01y = ffma(t01, f.e01y, -ay);
     const float d01 = dot2(q01x, q01y, q01x, q01y);
-    const float t02 = (f.rl02 == 0.f) ? 1.f : fsat(fmul(dot2(f.e02x, f.e02y, ax, ay), f.rl02));
+    const float t02 = (!REGULAR && f.rl02 == 0.f) ? 1.f : fsat(fmul(dot2(f.e02x, f.e02y, ax, ay), f.rl02));
     const float q02x = ffma(t02, f.e02x, -ax), q02y = ffma(t02, f.e02y, -ay);
     const float d02 = dot2(q02x, q02y, q02x, q02y);
-    const float t12 = (f.rl12 == 0.f) ? 1.f : fsat(fmul(dot2(f.e12x, f.e12y, bx, by), f.rl12));
+    const float t12 = (!REGULAR && f.rl12 == 0.f) ? 1.f : fsat(fmul(dot2(f.e12x, f.e12y, bx, by), f.rl12));
     const float q12x = ffma(t12, f.e12x, -bx), q12y = ffma(t12, f.e12y, -by);
     const float d12 = dot2(q12x, q12y, q12x, q12y);
     // closest edge, ties 01 -> 02 -> 12 (PointTriangleDistanceBackward order)
@@ -365,7 +368,7 @@ SMF_HD bool face_eval_core(const FaceSetup& f, float px, float py, Fragment& fr)
 // the closest-edge bookkeeping.  Depth and signed distance are formed with exactly face_eval's
 // operations, so the forward's K-nearest thresholds and acceptance decisions agree bit for bit
 // with what the backward recomputes.  Branch-free after the depth test.
-SMF_HD bool frag_setup_forward(const FaceSetup& f, float px, float py, float& sd, float& pz) {
+template <bool REGULAR = false> SMF_HD bool frag_setup_forward(const FaceSetup& f, float px, float py, float& sd, float& pz) {
     const float ax = fsub(px, f.x0), ay = fsub(py, f.y0);
     const float bx = fsub(px, f.x1), by = fsub(py, f.y1);
     const float cx = fsub(px, f.x2), cy = fsub(py, f.y2);
@@ -375,13 +378,13 @@ SMF_HD bool frag_setup_forward(const FaceSetup& f, float px, float py, float& sd
     const float w0 = fmul(n0, f.rden), w1 = fmul(n1, f.rden), w2 = fmul(n2, f.rden);
     pz = ffma(w2, f.z2, ffma(w1, f.z1, fmul(w0, f.z0)));
     if (pz < 0.f) return false;
-    const float t01 = (f.rl01 == 0.f) ? 1.f : fsat(fmul(dot2(f.e01x, f.e01y, ax, ay), f.rl01));
+    const float t01 = (!REGULAR && f.rl01 == 0.f) ? 1.f : fsat(fmul(dot2(f.e01x, f.e01y, ax, ay), f.rl01));
     const float q01x = ffma(t01, f.e01x, -ax), q01y = ffma(t01, f.e01y, -ay);
     const float d01 = dot2(q01x, q01y, q01x, q01y);
-    const float t02 = (f.rl02 == 0.f) ? 1.f : fsat(fmul(dot2(f.e02x, f.e02y, ax, ay), f.rl02));
+    const float t02 = (!REGULAR && f.rl02 == 0.f) ? 1.f : fsat(fmul(dot2(f.e02x, f.e02y, ax, ay), f.rl02));
     const float q02x = ffma(t02, f.e02x, -ax), q02y = ffma(t02, f.e02y, -ay);
     const float d02 = dot2(q02x, q02y, q02x, q02y);
-    const float t12 = (f.rl12 == 0.f) ? 1.f : fsat(fmul(dot2(f.e12x, f.e12y, bx, by), f.rl12));
+    const float t12 = (!REGULAR && f.rl12 == 0.f) ? 1.f : fsat(fmul(dot2(f.e12x, f.e12y, bx, by), f.rl12));
     const float q12x = ffma(t12, f.e12x, -bx), q12y = ffma(t12, f.e12y, -by);
     const float d12 = dot2(q12x, q12y, q12x, q12y);
     const float d = fminf(d01, fminf(d02, d12));
@@ -390,6 +393,90 @@ SMF_HD bool frag_setup_forward(const FaceSetup& f, float px, float py, float& sd
     sd = inside ? -d : d;
     return true;
 }
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------
+// Packed FP32 (Blackwell FFMA2 / FMUL2 / FADD2, PTX *.f32x2): one instruction works on two floats held in a 64-bit
+// register pair.  The rasteriser sweeps a face's rectangle two horizontally adjacent pixels per lane: the x terms
+// are packed, the y terms (same row) are scalars that the instructions broadcast.  Every packed operation is the IEEE
+// round-to-nearest operation of its scalar twin, applied in the same order, so depths and signed distances are
+// bit-identical to frag_setup_forward / face_eval_core (which the single-pixel steps and the host checks use).
+// ---------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 f2_bc(float s) { return f2_pack(s, s); }
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+struct Fragment2 {         // two pixels of one row against one face
+    float pz[2], sd[2];
+    // backward only: squared distances to the three segments, clamped parameters and -(p_proj - p) per edge
+    f32x2 d01, d02, d12, t01, t02, t12, nq01x, nq01y, nq02x, nq02y, nq12x, nq12y;
+};
+
+// Two pixels (px.lo, py) and (px.hi, py) against a prepared face WITHOUT degenerate edges (rl* != 0; callers send the
+// others through the scalar functions).  ok[k]: the pixel yields a fragment.  Same acceptance, depth and signed
+// distance as frag_setup_forward / face_eval_core, operation for operation:
+//   cross2(a, b) = fma(ax, by, -(ay * bx)),  dot2 = fma(ax, bx, ay * by)   (the rounded product is the y term where a
+//   scalar is available; negations are moved onto scalars: (-a) * b == -(a * b), fma(t, -e, a) == -fma(t, e, -a))
+template <bool BACKWARD>
+__device__ __forceinline__ void face_eval2(const FaceSetup& f, f32x2 px, float py, bool ok[2], Fragment2& fr) {
+    const f32x2 ax = f2_sub(px, f2_bc(f.x0)), bx = f2_sub(px, f2_bc(f.x1)), cx = f2_sub(px, f2_bc(f.x2));
+    const float ay = fsub(py, f.y0), by = fsub(py, f.y1), cy = fsub(py, f.y2);
+    // barycentric numerators
+    const f32x2 n0 = f2_fma(bx, f2_bc(f.e12y), f2_bc(-fmul(by, f.e12x)));            // cross2(b, e12)
+    const f32x2 n1 = f2_fma(f2_bc(f.e02x), f2_bc(cy), f2_mul(cx, f2_bc(-f.e02y)));   // cross2(e02, c)
+    const f32x2 n2 = f2_fma(ax, f2_bc(f.e01y), f2_bc(-fmul(ay, f.e01x)));            // cross2(a, e01)
+    const f32x2 rden = f2_bc(f.rden);
+    const f32x2 w0 = f2_mul(n0, rden), w1 = f2_mul(n1, rden), w2 = f2_mul(n2, rden);
+    const f32x2 pz = f2_fma(w2, f2_bc(f.z2), f2_fma(w1, f2_bc(f.z1), f2_mul(w0, f2_bc(f.z0))));
+    // clamped projections on the three segments
+    float u0, u1;
+    f2_unpack(f2_mul(f2_fma(f2_bc(f.e01x), ax, f2_bc(fmul(f.e01y, ay))), f2_bc(f.rl01)), u0, u1);
+    const f32x2 t01 = f2_pack(fsat(u0), fsat(u1));
+    f2_unpack(f2_mul(f2_fma(f2_bc(f.e02x), ax, f2_bc(fmul(f.e02y, ay))), f2_bc(f.rl02)), u0, u1);
+    const f32x2 t02 = f2_pack(fsat(u0), fsat(u1));
+    f2_unpack(f2_mul(f2_fma(f2_bc(f.e12x), bx, f2_bc(fmul(f.e12y, by))), f2_bc(f.rl12)), u0, u1);
+    const f32x2 t12 = f2_pack(fsat(u0), fsat(u1));
+    // -(t e - a): the same magnitude bits as q = t e - a
+    const f32x2 q01x = f2_fma(t01, f2_bc(-f.e01x), ax), q01y = f2_fma(t01, f2_bc(-f.e01y), f2_bc(ay));
+    const f32x2 q02x = f2_fma(t02, f2_bc(-f.e02x), ax), q02y = f2_fma(t02, f2_bc(-f.e02y), f2_bc(ay));
+    const f32x2 q12x = f2_fma(t12, f2_bc(-f.e12x), bx), q12y = f2_fma(t12, f2_bc(-f.e12y), f2_bc(by));
+    const f32x2 d01 = f2_fma(q01x, q01x, f2_mul(q01y, q01y));
+    const f32x2 d02 = f2_fma(q02x, q02x, f2_mul(q02y, q02y));
+    const f32x2 d12 = f2_fma(q12x, q12x, f2_mul(q12y, q12y));
+    float pz0, pz1, a0, a1, b0, b1, c0, c1, wa0, wa1, wb0, wb1, wc0, wc1;
+    f2_unpack(pz, pz0, pz1);
+    f2_unpack(d01, a0, a1); f2_unpack(d02, b0, b1); f2_unpack(d12, c0, c1);
+    f2_unpack(w0, wa0, wa1); f2_unpack(w1, wb0, wb1); f2_unpack(w2, wc0, wc1);
+    const float d0 = fminf(a0, fminf(b0, c0)), d1 = fminf(a1, fminf(b1, c1));
+    const bool in0 = (wa0 > 0.f) && (wb0 > 0.f) && (wc0 > 0.f), in1 = (wa1 > 0.f) && (wb1 > 0.f) && (wc1 > 0.f);
+    ok[0] = !(pz0 < 0.f) && (in0 || !(d0 >= RAST_BLUR));
+    ok[1] = !(pz1 < 0.f) && (in1 || !(d1 >= RAST_BLUR));
+    fr.pz[0] = pz0; fr.pz[1] = pz1;
+    fr.sd[0] = in0 ? -d0 : d0; fr.sd[1] = in1 ? -d1 : d1;
+    if (BACKWARD) {
+        fr.d01 = d01; fr.d02 = d02; fr.d12 = d12; fr.t01 = t01; fr.t02 = t02; fr.t12 = t12;
+        fr.nq01x = q01x; fr.nq01y = q01y; fr.nq02x = q02x; fr.nq02y = q02y; fr.nq12x = q12x; fr.nq12y = q12y;
+    }
+}
+
+// frag_prob for two pixels: m = 1 - sigmoid(-sd / sigma)
+__device__ __forceinline__ void frag_prob2(const float sd[2], float p[2], float m[2]) {
+    float x0, x1;
+    f2_unpack(f2_mul(f2_pack(sd[0], sd[1]), f2_bc(1.4426950408889634f / RAST_SIGMA)), x0, x1);
+    float e0, e1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+    f2_unpack(f2_add(f2_bc(1.f), f2_pack(e0, e1)), x0, x1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(p[0]) : "f"(x0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(p[1]) : "f"(x1));
+    f2_unpack(f2_sub(f2_bc(1.f), f2_pack(p[0], p[1])), m[0], m[1]);
+}
+#endif  // __CUDACC__
 
 // 1 - sigmoid(-sd/sigma) the way the reference forms it in fp32: p = sigmoid(x), m = 1 - p.
 SMF_HD void frag_prob(float sd, float& p, float& m) {

@@ -43,6 +43,8 @@ constexpr unsigned char RT_CLS_DIRECT = 0, RT_CLS_LISTED = 1, RT_CLS_IDLE = 2;
 constexpr int RT_MAXCHUNK = 512;                // tile lists up to 8192 faces are split by cost, longer ones evenly
 constexpr int RT_FAIR = 4;                      // a hand-out item holds at most 1/RT_FAIR of a CTA's fair share of the pairs
 constexpr unsigned RT_FACE_COST = 16u;          // per-face overhead of the sweep, in pair evaluations
+// (interpolated pivots in the K-th order statistic search were measured: +2 % on the kernel -- the depths of one pixel's
+//  candidates cluster on the front and back surfaces, bisection on the key bits with an exact-split exit does better)
 
 struct RtSmem {
     unsigned plane[RT_WARPS][RT_PLANE];
@@ -75,6 +77,10 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
 }
 __device__ __forceinline__ void st_list_entry(uint2* p, unsigned a, unsigned b, unsigned long long pol) {
     asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(a), "r"(b), "l"(pol) : "memory");
+}
+// the slot a plane cursor points at: RT_LISTED | entry index (< 2^29) -> byte offset in 32 bits (the flag shifts out)
+__device__ __forceinline__ uint2* list_slot(uint2* list, unsigned cursor) {
+    return reinterpret_cast<uint2*>(reinterpret_cast<char*>(list) + (size_t)(cursor << 3));
 }
 __device__ __forceinline__ void l2_discard_line(const void* p) {
     asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
@@ -229,8 +235,93 @@ __device__ __forceinline__ float rt_select(const uint2* __restrict__ L, const ui
     return warp_prod(prod);
 }
 
-// One prepared face (64-byte record in the warp's stage) against the pixels of its rectangle, 32 per step.
+// One prepared face (64-byte record in the warp's stage) against the pixels of its rectangle, 32 per step
+// (rt_sweep_face2 below: 64 per step).
 // SKIPS: some pixels of the tile are not handled in this pass (multi-pass tiles only).
+// Lanes walk the rectangle's pixels (or pixel pairs) in row-major order, 32 per step: position (rr, cc) of a lane's
+// item advances by 32 = sq * wd + sr per step, with one carry (no division in the loop).
+struct RectWalk {
+    int rr, cc, sq, sr;
+    __device__ __forceinline__ RectWalk(int wd, int lane) {
+        float inv_w;      // MUFU reciprocal: (i + 0.5) / wd is at least 0.5 / wd away from an integer; exact for wd <= 1024
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_w) : "f"((float)wd));
+        rr = (int)(((float)lane + 0.5f) * inv_w);
+        cc = lane - rr * wd;
+        sq = (int)(32.5f * inv_w);
+        sr = 32 - sq * wd;
+    }
+    __device__ __forceinline__ void next(int wd) {
+        rr += sq; cc += sr;
+        if (cc >= wd) { cc -= wd; ++rr; }
+    }
+};
+
+template <bool SKIPS, bool REGULAR>
+__device__ __forceinline__ void rt_sweep_face1(const FaceSetup& fs, unsigned* __restrict__ plane, uint2* __restrict__ list,
+                                               int lane, int x0, int y0, float inv_s, int c0, int c1, int r0, int r1,
+                                               unsigned long long pol) {
+    const int wd = c1 - c0 + 1, npx = wd * (r1 - r0 + 1);
+    RectWalk wk(wd, lane);
+    for (int i = lane; i < npx; i += 32, wk.next(wd)) {
+        const int lx = c0 + wk.cc, ly = r0 + wk.rr;
+        const int idx = ly * RT_PITCH + lx;
+        const unsigned v = plane[idx];
+        if (SKIPS && v == RT_SKIP) continue;
+        float sd, pz, mv = 1.f;
+        const bool ok = frag_setup_forward<REGULAR>(fs, pix_to_ndc(x0 + lx, inv_s), pix_to_ndc(y0 + ly, inv_s), sd, pz);
+        if (ok) { float pp; frag_prob(sd, pp, mv); }
+        if (v & RT_LISTED) {
+            plane[idx] = v + 1u;
+            st_list_entry(list_slot(list, v), ok ? __float_as_uint(pz + 0.f) : 0xffffffffu, __float_as_uint(mv), pol);
+        } else if (ok) {
+            plane[idx] = __float_as_uint(__uint_as_float(v) * mv);
+        }
+    }
+    __syncwarp();        // the next face's lanes may touch the same pixels
+}
+
+// The same sweep two horizontally adjacent pixels per lane (packed FP32, face_eval2): 64 pixels per step.  Used for
+// rectangles of more than 32 pixels of faces without degenerate edges; results are bit-identical to rt_sweep_face.
+template <bool SKIPS>
+__device__ __forceinline__ void rt_sweep_face2(const FaceSetup& fs, unsigned* __restrict__ plane, uint2* __restrict__ list,
+                                               int lane, int x0, int y0, float inv_s, int c0, int c1, int r0, int r1,
+                                               unsigned long long pol) {
+    const int wp = (c1 - c0 + 2) >> 1, npairs = wp * (r1 - r0 + 1);
+    RectWalk wk(wp, lane);
+    for (int j = lane; j < npairs; j += 32, wk.next(wp)) {
+        const int lx = c0 + 2 * wk.cc, ly = r0 + wk.rr;
+        const int idx = ly * RT_PITCH + lx;
+        const bool has1 = lx < c1;
+        unsigned v[2];
+        v[0] = plane[idx];
+        v[1] = plane[idx + 1];           // (column 32 of the pitch-33 plane exists; never written when !has1)
+        bool act[2] = {true, has1};
+        if (SKIPS) { act[0] = v[0] != RT_SKIP; act[1] = has1 && v[1] != RT_SKIP; if (!act[0] && !act[1]) continue; }
+        const float t0 = ffma(2.f, (float)(x0 + lx), 1.f);
+        const f32x2 px = f2_fma(f2_pack(t0, t0 + 2.f), f2_bc(-inv_s), f2_bc(1.f));       // pix_to_ndc of both columns
+        bool ok[2];
+        Fragment2 fr;
+        face_eval2<false>(fs, px, pix_to_ndc(y0 + ly, inv_s), ok, fr);
+        float pp[2], mv[2];
+        frag_prob2(fr.sd, pp, mv);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (!act[k]) continue;
+            if (v[k] & RT_LISTED) {
+                plane[idx + k] = v[k] + 1u;
+                st_list_entry(list_slot(list, v[k]), ok[k] ? __float_as_uint(fr.pz[k] + 0.f) : 0xffffffffu,
+                              __float_as_uint(ok[k] ? mv[k] : 1.f), pol);
+            } else if (ok[k]) {
+                plane[idx + k] = __float_as_uint(__uint_as_float(v[k]) * mv[k]);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+#ifndef RT_PACK_MIN
+#define RT_PACK_MIN 33          // rectangles of at least this many pixels are swept two pixels per lane
+#endif
 template <bool SKIPS>
 __device__ __forceinline__ void rt_sweep_face(const float4* __restrict__ rec, unsigned* __restrict__ plane, uint2* __restrict__ list,
                                               int lane, int x0, int y0, float inv_s, int b0, int b1, unsigned long long pol) {
@@ -247,26 +338,11 @@ __device__ __forceinline__ void rt_sweep_face(const float4* __restrict__ rec, un
     fs.e01x = fsub(fs.x1, fs.x0); fs.e01y = fsub(fs.y1, fs.y0);
     fs.e02x = fsub(fs.x2, fs.x0); fs.e02y = fsub(fs.y2, fs.y0);
     fs.e12x = fsub(fs.x2, fs.x1); fs.e12y = fsub(fs.y2, fs.y1);
-    const int wd = c1 - c0 + 1, npx = wd * (r1 - r0 + 1);
-    float inv_w;      // MUFU reciprocal: (i + 0.5) / wd is at least 0.5 / 32 away from an integer
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_w) : "f"((float)wd));
-    for (int i = lane; i < npx; i += 32) {
-        const int rr = (int)(((float)i + 0.5f) * inv_w);
-        const int lx = c0 + (i - rr * wd), ly = r0 + rr;
-        const int idx = ly * RT_PITCH + lx;
-        const unsigned v = plane[idx];
-        if (SKIPS && v == RT_SKIP) continue;
-        float sd, pz, mv = 1.f;
-        const bool ok = frag_setup_forward(fs, pix_to_ndc(x0 + lx, inv_s), pix_to_ndc(y0 + ly, inv_s), sd, pz);
-        if (ok) { float pp; frag_prob(sd, pp, mv); }
-        if (v & RT_LISTED) {
-            plane[idx] = v + 1u;
-            st_list_entry(list + (v & 0x7fffffffu), ok ? __float_as_uint(pz + 0.f) : 0xffffffffu, __float_as_uint(mv), pol);
-        } else if (ok) {
-            plane[idx] = __float_as_uint(__uint_as_float(v) * mv);
-        }
-    }
-    __syncwarp();        // the next face's lanes may touch the same pixels
+    const int npx = (c1 - c0 + 1) * (r1 - r0 + 1);
+    const bool regular = (fs.rl01 != 0.f) && (fs.rl02 != 0.f) && (fs.rl12 != 0.f);       // no degenerate edge (warp-uniform)
+    if (!regular) rt_sweep_face1<SKIPS, false>(fs, plane, list, lane, x0, y0, inv_s, c0, c1, r0, r1, pol);
+    else if (npx >= RT_PACK_MIN) rt_sweep_face2<SKIPS>(fs, plane, list, lane, x0, y0, inv_s, c0, c1, r0, r1, pol);
+    else rt_sweep_face1<SKIPS, true>(fs, plane, list, lane, x0, y0, inv_s, c0, c1, r0, r1, pol);
 }
 
 __global__ void __launch_bounds__(RT_THREADS, RT_CTAS_PER_SM)
@@ -324,7 +400,14 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                     const unsigned rect = pool[e].z;
                     const int rows = min((int)(rect >> 24), b1 - 1) - max((int)((rect >> 16) & 0xffu), b0) + 1;
                     const unsigned npx = (((rect >> 8) & 0xffu) - (rect & 0xffu) + 1u) * (unsigned)max(rows, 0);
-                    cost = npx ? ((npx + 31u) & ~31u) + RT_FACE_COST : 2u;        // the sweep takes whole 32-lane steps
+                    // the sweep takes whole 32-lane steps: one pixel per lane, or -- rectangles of RT_PACK_MIN pixels and
+                    // more -- a pixel pair per lane at about 1.3x the cost of a step
+                    if (npx >= (unsigned)RT_PACK_MIN) {
+                        const unsigned wdp = (((rect >> 8) & 0xffu) - (rect & 0xffu) + 2u) >> 1;
+                        cost = ((wdp * (unsigned)rows + 31u) >> 5) * 42u + RT_FACE_COST;
+                    } else {
+                        cost = npx ? ((npx + 31u) & ~31u) + RT_FACE_COST : 2u;
+                    }
                 }
 #pragma unroll
                 for (int o = RT_BLK / 2; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
@@ -423,7 +506,9 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                         const unsigned o = run;
                         run += (c + RT_LIST_ALIGN - 1) & ~(unsigned)(RT_LIST_ALIGN - 1);
                         const bool act = (o >= win_lo) && (o - win_lo < cap);
-                        unsigned cur = RT_LISTED | (o - win_lo);
+                        // (cursors address the whole scratch, not this CTA's part: the sweep then forms a store address from
+                        //  the kernel parameter alone; n_ctas * list_stride < 2^29 is checked at create)
+                        unsigned cur = RT_LISTED | (blockIdx.x * (unsigned)ts.list_stride + (o - win_lo));
 #pragma unroll
                         for (int q = 0; q < RT_WARPS; ++q) {
                             const unsigned cw = sm.plane[q][idx];
@@ -451,7 +536,7 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
             // ---- P1: sweep this warp's faces (TMA double buffer of RT_BLK prepared faces)
             {
                 const float4* recs = w.tile_rec + ((size_t)fr * w.pool_cap + off) * 4;
-                uint2* list = ts.list + (size_t)blockIdx.x * ts.list_stride;
+                uint2* list = ts.list;             // cursors carry the CTA's offset
                 const float inv_s = 1.f / (float)w.S;
                 const int nblk = (hi - lo + RT_BLK - 1) / RT_BLK;
                 const bool skips = (round != 0u) || (sm.total > (unsigned)ts.list_cap);       // otherwise no plane holds RT_SKIP

@@ -448,9 +448,11 @@ class SMALFitter(nn.Module):
                 img = (np.transpose(rows[b].numpy(), (1, 2, 0)) * 255.0).astype(np.uint8)
                 image_exporter.export(img, b, gid, self.export_parameters(gid), verts, np.asarray(self.constants.faces))
 
-    def set_profiling(self, enable: bool):
+    def set_profiling(self, enable, count_pairs: bool = False):
+        """Per-phase CUDA events on every loss_grad call; count_pairs additionally makes the backward count the
+        pairs work_counts() reports (slows it down: not for timed passes)."""
         h = self._handle
-        h.check(h.lib.smalfit_set_profiling(h.h, int(bool(enable))), "smalfit_set_profiling")
+        h.check(h.lib.smalfit_set_profiling(h.h, 2 if (enable and count_pairs) else int(bool(enable))), "smalfit_set_profiling")
 
     def profile(self):
         """Per-phase device milliseconds of the last loss_grad call (see smalfit_get_profile)."""
