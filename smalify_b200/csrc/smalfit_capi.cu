@@ -208,6 +208,23 @@ int smalfit_create_ex(const smalfit_model_t* md, int device, int max_frames, int
     m.skinT_ptr = P.upload(md->skinT_ptr, NJ + 1);
     m.skinT_vert = P.upload(md->skinT_vert, md->skinT_ptr[NJ]);
     m.skinT_weight = P.upload(md->skinT_weight, md->skinT_ptr[NJ]);
+    {   // chunks of the per-joint entry ranges (frame_backward sums a chunk per warp, then the chunks of a joint in order)
+        std::vector<int> cj, clo, chi, jptr(NJ + 1, 0);
+        for (int j = 0; j < NJ; ++j) {
+            jptr[j] = (int)cj.size();
+            for (int e = md->skinT_ptr[j]; e < md->skinT_ptr[j + 1]; e += SKIN_CHUNK) {
+                cj.push_back(j); clo.push_back(e);
+                chi.push_back(e + SKIN_CHUNK < md->skinT_ptr[j + 1] ? e + SKIN_CHUNK : md->skinT_ptr[j + 1]);
+            }
+        }
+        jptr[NJ] = (int)cj.size();
+        if ((int)cj.size() > MAX_SKIN_CHUNKS) { P.release(); delete h; return fail(nullptr, SMALFIT_EINVAL, "too many skinning-weight chunks (%d)", (int)cj.size()); }
+        m.n_skin_chunks = (int)cj.size();
+        m.chunk_joint = P.upload(cj.data(), cj.size());
+        m.chunk_lo = P.upload(clo.data(), clo.size());
+        m.chunk_hi = P.upload(chi.data(), chi.size());
+        m.joint_chunk_ptr = P.upload(jptr.data(), jptr.size());
+    }
     m.jreg_ptr = P.upload(md->jreg_ptr, NJ + 1);
     m.jreg_vert = P.upload(md->jreg_vert, md->jreg_ptr[NJ]);
     m.jreg_weight = P.upload(md->jreg_weight, md->jreg_ptr[NJ]);
@@ -278,16 +295,16 @@ int smalfit_create_ex(const smalfit_model_t* md, int device, int max_frames, int
         h->ts.nsub = e_nsub ? atoi(e_nsub) : 0;
         { const char* e_fair = getenv("SMALFIT_RT_FAIR"); h->ts.fair = e_fair ? atoi(e_fair) : 0; }
         h->ts.split_len = e_split ? atoi(e_split) : 0;
+        { const char* e_min = getenv("SMALFIT_RT_MINITEM"); h->ts.min_item = e_min ? atoi(e_min) : 0; }
     }
     w.tile_off = SHIFT(P.alloc<unsigned>(N * (tiles + 1), true), tiles + 1);
     w.tile_cost = SHIFT(P.alloc<unsigned>(N * tiles, true), tiles);
-    w.bin_cnt = SHIFT(P.alloc<unsigned>(N * BIN_WARPS * tiles, true), BIN_WARPS * tiles);
-    w.bin_cost = SHIFT(P.alloc<unsigned>(N * BIN_PARTS * tiles, true), BIN_PARTS * tiles);
     w.pix = SHIFT(P.alloc<uint2>(N * SS, true), SS);
     w.pix_tfid = SHIFT(P.alloc<uint16_t>(N * SS, true), SS);
     w.region_l1 = SHIFT(P.alloc<float>(N * tiles * REGIONS_PER_TILE * REGION_H, true), tiles * REGIONS_PER_TILE * REGION_H);
     w.face_grad = SHIFT(P.alloc<float>(N * m.Fp * 8, true), m.Fp * 8);
     w.dvs = SHIFT(P.alloc<float>(N * V * 3, true), V * 3);
+    w.gw = SHIFT(P.alloc<float>(N * V * 3, true), V * 3);
     w.gJ = SHIFT(P.alloc<float>(N * NJ * 3, true), NJ * 3);
     w.gls = SHIFT(P.alloc<float>(N * NLS, true), NLS);
     w.frame_loss = SHIFT(P.alloc<float>(N * 8, true), 8);
@@ -428,14 +445,14 @@ static int run_forward(smalfit_t h, const Params& p, int frame0, int n, Weights 
                        float* verts_out, cudaStream_t st) {
     h->mark(0, st);
     launch_shape_forward(h->m, h->w, p, frame0, n, st);
-    launch_frame_forward(h->m, h->w, p, frame0, n, wt, verts_out, st);
+    // frame_forward + binning of a frame in one launch over a 4-CTA cluster (profile phases 0 and 1 are reported together)
+    launch_frame_front(h->m, h->w, p, frame0, n, wt, verts_out, raster, st);
     h->n_launches += 2;
     h->mark(1, st);
     if (raster) {
-        launch_bin_faces(h->m, h->w, frame0, n, st);
         h->mark(2, st);
         launch_raster_tile_forward(h->m, h->w, h->ts, frame0, n, wt, alpha_out, h->tile_ctas, st);
-        h->n_launches += 5;
+        h->n_launches += 2;
     } else {
         h->mark(2, st);
     }

@@ -4,25 +4,40 @@
 // (all on one stream, no host synchronisation, no allocation):
 //
 //   shape_forward      v_shaped = v_template + betas . shapedirs              (smal_torch.py:115)
-//   frame_forward      per frame: rest joints, Rodrigues, kinematic chain, sparse LBS,
+//   frame_front        per frame (4-CTA cluster): rest joints, Rodrigues, kinematic chain, sparse LBS,
 //                      camera, 41 model joints, keypoint projection + loss     (smal_torch.py:125-184,
-//                      and dL/d(joints)                                         smal_fitter.py:129-144)
-//   bin_faces          per face: prepared form + conservative pixel rectangle, binned into 32x32 tiles
+//                      and dL/d(joints);                                        smal_fitter.py:129-144)
+//                      per face: prepared form + conservative pixel rectangle, binned into 32x32 tiles
 //   raster_tile_fwd    soft silhouette (PyTorch3D 0.2.5 semantics, exact K=100 nearest-z
 //                      rule) fused with the L1 silhouette loss                 (p3d_renderer.py:26-39,66;
 //                      writes per pixel (coef, z-threshold) for the backward    smal_fitter.py:172-173)
 //   raster_backward    face-parallel analytic backward -> per-face xy gradients (RasterizeMeshesBackward)
-//   frame_backward     per frame: face->vertex gather, camera^T, LBS^T, chain^T, Rodrigues^T,
-//                      pose prior + splay (value and gradient)                 (smal_fitter.py:153-160)
+//   frame_backward     per frame (4-CTA cluster): face->vertex gather, camera^T, LBS^T, chain^T, Rodrigues^T,
+//                      pose prior + splay (value and gradient), temporal term  (smal_fitter.py:153-160,177-190)
 //   shape_backward     cross-frame reduction -> dL/dbetas, dL/dlog_beta_scales, shape prior,
 //                      loss_terms[8]                                            (smal_fitter.py:162-175)
-//   temporal / adam    get_temporal + Adam                                      (smal_fitter.py:177-190,
-//                                                                               optimize_to_joints.py:96,137)
+//   step_tail          [exchange with the peer ranks over NVLink] + Adam        (optimize_to_joints.py:96,137)
+//   (temporal / adam / adam5 / peer_allreduce: the same pieces as separate launches, for the drop-in surface)
 #include "smalfit_kernels.cuh"
+
+#include <cooperative_groups.h>
+#include <cstdio>
+namespace cg = cooperative_groups;
 
 namespace smf {
 
 __constant__ SkeletonConst c_sk;
+
+// -DSMF_PHASE_CLOCKS: the per-frame kernels print the cycles between their phases (first frame, CTA 0, thread 0)
+#ifdef SMF_PHASE_CLOCKS
+#define PHASE_CLOCK_DECL long long pc_t[16]; int pc_n = 0; pc_t[pc_n++] = clock64();
+#define PHASE_CLOCK() pc_t[pc_n++] = clock64();
+#define PHASE_CLOCK_PRINT(name, cond) if (cond) { printf("%s cycles:", name); for (int q = 1; q < pc_n; ++q) printf(" %lld", pc_t[q] - pc_t[q - 1]); printf(" total %lld\n", pc_t[pc_n - 1] - pc_t[0]); }
+#else
+#define PHASE_CLOCK_DECL
+#define PHASE_CLOCK()
+#define PHASE_CLOCK_PRINT(name, cond)
+#endif
 
 void upload_skeleton(const SkeletonConst& sk) { cudaMemcpyToSymbol(c_sk, &sk, sizeof(SkeletonConst)); }
 
@@ -98,6 +113,10 @@ struct FrameSmem {
     float Gb[NJ * 9], offb[NJ * 3], tb[NJ * 3], Rwb[NJ * 9], sb[NJ * 3], Jb[NJ * 3], Rb[NJ * 9];
     float thg[NJ * 3], res[NJ * 3];
     float ttr[3];           // dL/dtrans before the temporal term
+    float cpart[8][8];      // frame_backward: per cluster CTA (dL/dtrans partial x3, dL/dfocal partial, silhouette loss partial)
+    float chunk_sum[MAX_SKIN_CHUNKS][12];     // frame_backward: per skinning-weight chunk, sums for dL/dG (9) and dL/doff (3)
+    float prior_g[NJ * 3];  // frame_backward: gradient of pose prior + splay + joint limits (formed by another CTA of the cluster)
+    float prior_l[4];       //                 and their loss values (pose, splay, limit)
 };
 
 __device__ __forceinline__ ChainFwd chain_of(FrameSmem& S) {
@@ -112,13 +131,20 @@ __device__ void frame_pose_forward(FrameSmem& S, const ModelDev& m, const Worksp
                                    int fr, int slot, int pslot) {
     const int tid = threadIdx.x;
     const float* vs = w.v_shaped + (size_t)slot * m.V * 3;
-    if (tid < NJ * 3) {
+    if (tid < NJ * 3)
         S.theta[tid] = (tid < 3) ? p.glob[fr * 3 + tid] * w.gmask[tid]
                                  : p.joint[(size_t)fr * (NJ - 1) * 3 + (tid - 3)] * w.rmask[tid - 3];
-        const int j = tid / 3, c = tid - j * 3;
-        float acc = 0.f;
-        for (int e = m.jreg_ptr[j]; e < m.jreg_ptr[j + 1]; ++e) acc = fmaf(m.jreg_weight[e], vs[m.jreg_vert[e] * 3 + c], acc);
-        S.J[tid] = acc;
+    // rest joints J = Jreg . v_shaped: a warp per joint, lanes over the joint's (<= 34) regressor entries
+    for (int j = tid >> 5; j < NJ; j += (int)(blockDim.x >> 5)) {
+        const int lane = tid & 31;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int e = m.jreg_ptr[j] + lane; e < m.jreg_ptr[j + 1]; e += 32) {
+            const float wk = m.jreg_weight[e];
+            const float* v = vs + m.jreg_vert[e] * 3;
+            a0 = fmaf(wk, v[0], a0); a1 = fmaf(wk, v[1], a1); a2 = fmaf(wk, v[2], a2);
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+        if (lane == 0) { S.J[j * 3] = a0; S.J[j * 3 + 1] = a1; S.J[j * 3 + 2] = a2; }
     }
     if (tid < NLS) S.ls[tid] = p.logscale[pslot * NLS + tid];
     if (tid < 3) S.tr[tid] = p.trans[fr * 3 + tid];
@@ -140,112 +166,13 @@ __device__ void frame_pose_forward(FrameSmem& S, const ModelDev& m, const Worksp
 }
 
 // ---------------------------------------------------------------------------
-// frame_forward
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(FRAME_FWD_THREADS)
-frame_forward_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, float* verts_out) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    FrameSmem& S = *reinterpret_cast<FrameSmem*>(smem_raw);
-    float* vw = reinterpret_cast<float*>(smem_raw + sizeof(FrameSmem));     // [V*3] world verts, no trans
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int fr = frame0 + blockIdx.x;
-    const int slot = (w.n_shapes == 1) ? w.slot0 : fr;
-    const float* vs = w.v_shaped + (size_t)slot * m.V * 3;
-
-    frame_pose_forward(S, m, w, p, fr, slot, (w.n_shapes == 1) ? 0 : fr);
-    const float focal = w.focal ? *w.focal : CAM_F;
-
-    // sparse linear-blend skinning + camera
-    float4* ndc = w.ndc + (size_t)fr * m.Vp;
-    for (int v = tid; v < m.V; v += blockDim.x) {
-        const float x = vs[v * 3 + 0], y = vs[v * 3 + 1], z = vs[v * 3 + 2];
-        float ax = 0.f, ay = 0.f, az = 0.f;
-#pragma unroll
-        for (int k = 0; k < MAXINF; ++k) {
-            const float wk = m.skin_weight[v * MAXINF + k];
-            if (wk != 0.f) {
-                const int j = m.skin_joint[v * MAXINF + k];
-                const float* G = S.G + j * 9;
-                const float* o = S.off + j * 3;
-                ax = fmaf(wk, G[0] * x + G[1] * y + G[2] * z + o[0], ax);
-                ay = fmaf(wk, G[3] * x + G[4] * y + G[5] * z + o[1], ay);
-                az = fmaf(wk, G[6] * x + G[7] * y + G[8] * z + o[2], az);
-            }
-        }
-        vw[v * 3 + 0] = ax; vw[v * 3 + 1] = ay; vw[v * 3 + 2] = az;
-        const float X = ax + S.tr[0], Y = ay + S.tr[1], Z = az + S.tr[2];
-        float xn, yn, zv;
-        camera_fwd(X, Y, Z, xn, yn, zv, focal);
-        ndc[v] = make_float4(xn, yn, zv, 0.f);
-        if (verts_out) {
-            float* o = verts_out + ((size_t)blockIdx.x * m.V + v) * 3;
-            o[0] = X; o[1] = Y; o[2] = Z;
-        }
-    }
-    for (int v = m.V + tid; v < m.Vp; v += blockDim.x) ndc[v] = make_float4(0.f, 0.f, -1.f, 0.f);
-    __syncthreads();
-
-    // 41 model joints: regressed from the posed vertices (+ trans), smal_torch.py:171-184
-    for (int j = wid; j < NMJ; j += (int)(blockDim.x >> 5)) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        for (int e = m.mj_ptr[j] + lane; e < m.mj_ptr[j + 1]; e += 32) {
-            const float wk = m.mj_weight[e];
-            const int v = m.mj_vert[e];
-            a0 = fmaf(wk, vw[v * 3 + 0], a0); a1 = fmaf(wk, vw[v * 3 + 1], a1); a2 = fmaf(wk, vw[v * 3 + 2], a2);
-        }
-        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-        if (lane == 0) { S.mj[j * 3 + 0] = a0 + S.tr[0]; S.mj[j * 3 + 1] = a1 + S.tr[1]; S.mj[j * 3 + 2] = a2 + S.tr[2]; }
-    }
-    __syncthreads();
-
-    // keypoint projection + masked MSE (smal_fitter.py:140-144) and its gradient
-    float lk = 0.f, gf = 0.f;
-    if (tid < NKP) {
-        const int j = c_sk.kp_joint[tid];
-        float xn, yn, zv, row, col;
-        camera_fwd(S.mj[j * 3 + 0], S.mj[j * 3 + 1], S.mj[j * 3 + 2], xn, yn, zv, focal);
-        const float half = 0.5f * (float)(w.S - 1);
-        screen_fwd(xn, yn, half, row, col);
-        w.kp_proj[(size_t)fr * NKP * 2 + tid * 2 + 0] = row;
-        w.kp_proj[(size_t)fr * NKP * 2 + tid * 2 + 1] = col;
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-        if (wt.j2d > 0.f && w.vis[(size_t)fr * NKP + tid] != 0) {
-            const float dr = row - w.kp_target[(size_t)fr * NKP * 2 + tid * 2 + 0];
-            const float dc = col - w.kp_target[(size_t)fr * NKP * 2 + tid * 2 + 1];
-            const float scale = wt.j2d * w.inv_window[fr] * (1.f / (float)(NKP * 2));
-            lk = scale * (dr * dr + dc * dc);
-            const float gyn = -half * 2.f * scale * dr, gxn = -half * 2.f * scale * dc;
-            camera_bwd(xn, yn, zv, gxn, gyn, g0, g1, g2, focal);
-            gf = camera_bwd_focal(xn, yn, gxn, gyn, focal);
-        }
-        S.gkp[tid * 3 + 0] = g0; S.gkp[tid * 3 + 1] = g1; S.gkp[tid * 3 + 2] = g2;
-    }
-    const float lsum = block_sum(lk, S.red);
-    if (w.gfocal) { gf = block_sum(gf, S.red); if (tid == 0) w.gfocal_frame[fr * 2 + 0] = gf; }
-    if (tid < NMJ) {
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-        for (int k = 0; k < NKP; ++k)
-            if (c_sk.kp_joint[k] == tid) { g0 += S.gkp[k * 3]; g1 += S.gkp[k * 3 + 1]; g2 += S.gkp[k * 3 + 2]; }
-        float* gj = w.gjoint + (size_t)fr * NMJ * 3 + tid * 3;
-        gj[0] = g0; gj[1] = g1; gj[2] = g2;
-    }
-    if (tid == 0) w.frame_loss[fr * 8 + 0] = lsum;
-}
-
-void launch_frame_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n,
-                          Weights wt, float* verts_out, cudaStream_t st) {
-    const size_t smem = sizeof(FrameSmem) + (size_t)m.V * 3 * sizeof(float);
-    frame_forward_kernel<<<n, FRAME_FWD_THREADS, smem, st>>>(m, w, p, frame0, wt, verts_out);
-}
-
-// ---------------------------------------------------------------------------
-// bin_faces: every face gets its prepared form (face_setup) and its conservative pixel rectangle; faces are
-// binned into the 32x32-pixel tiles they touch.  Deterministic (no global atomics): the faces of a frame are
-// cut into BIN_WARPS contiguous segments, one per warp, spread over BIN_PARTS CTAs;
-//   bin_count  counts per (segment, tile), writes the per-face records and rectangles,
-//   bin_scan   (one CTA per frame) turns the counts into tile offsets and per-(segment, tile) cursors,
-//   bin_fill   fills in face order within a segment (lanes that hit the same tile in the same step are
-//              ranked with match_any), so every tile list is in ascending face order.
+// Binning (part of frame_front below): every face gets its prepared form (face_setup) and its conservative pixel
+// rectangle; faces are binned into the 32x32-pixel tiles they touch.  Deterministic (no global atomics): the faces of a
+// frame are cut into BIN_WARPS contiguous segments, one per warp, spread over the BIN_PARTS CTAs of the frame's cluster;
+//   count   per (segment, tile) in shared memory, writing the per-face records and rectangles,
+//   scan    tile offsets and per-(segment, tile) cursors from the counts of the whole cluster (distributed shared memory),
+//   fill    in face order within a segment (lanes that hit the same tile in the same step are ranked with match_any),
+//           so every tile list is in ascending face order.
 // Pool entry (16 B): face id + its three vertex ids + the rectangle in tile-local pixel coordinates;
 // tile_rec (64 B): the prepared face for the tile rasteriser's TMA stage.
 // ---------------------------------------------------------------------------
@@ -262,19 +189,149 @@ __device__ __forceinline__ void bin_segment(const ModelDev& m, int seg_id, int& 
     f_hi = min(f_lo + seg, m.Fp);
 }
 
-__global__ void __launch_bounds__(BIN_PART_THREADS) bin_count_kernel(ModelDev m, Workspace w, int frame0) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = w.tiles_x * w.tiles_y;
-    unsigned* cnt = reinterpret_cast<unsigned*>(smem_raw);          // [BIN_PART_WARPS][T]
-    unsigned* cost = cnt + BIN_PART_WARPS * T;                      // [T] (pixel, face) pairs per tile, this CTA's faces
+// ---------------------------------------------------------------------------
+// frame_front: frame_forward + bin_count + bin_scan + bin_fill of one frame in ONE launch, the frame spread over a
+// thread-block cluster of FRONT_CTAS CTAs (4 x 16 warps = the BIN_WARPS face segments):
+//   every CTA   runs the (small) pose chain redundantly, skins and projects its quarter of the vertices;
+//   CTA 0       also regresses the 41 model joints (re-skinning the ~260 vertices they depend on) and forms the
+//               keypoint loss and its gradient;
+//   cluster.sync -- the frame's NDC vertices are visible to the whole cluster --
+//   every CTA   prepares and counts its 8 face segments into shared memory;
+//   cluster.sync, then every CTA reads the other CTAs' counts through distributed shared memory: tile totals,
+//               tile offsets (prefix), its own write cursors = offset + counts of the segments before it;
+//   cluster.sync (nobody reads remote counts any more), cursors replace the counts, and the segments are filled.
+// Same arithmetic, same deterministic tile lists (ascending face id) as the four kernels it replaces; with few frames
+// per GPU (frame-sharded runs) it puts 4x as many SMs to work and saves three launch boundaries.
+// ---------------------------------------------------------------------------
+constexpr int FRONT_CTAS = BIN_PARTS, FRONT_THREADS = BIN_PART_THREADS, FRONT_WARPS = BIN_PART_WARPS;
+
+// skinned vertex (world, no translation): the one expression both the vertex loop and the joint regression use
+__device__ __forceinline__ void lbs_vertex(const FrameSmem& S, const ModelDev& m, const float* vs, int v, float& ax, float& ay, float& az) {
+    const float x = vs[v * 3 + 0], y = vs[v * 3 + 1], z = vs[v * 3 + 2];
+    ax = 0.f; ay = 0.f; az = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXINF; ++k) {
+        const float wk = m.skin_weight[v * MAXINF + k];
+        if (wk != 0.f) {
+            const int j = m.skin_joint[v * MAXINF + k];
+            const float* G = S.G + j * 9;
+            const float* o = S.off + j * 3;
+            ax = fmaf(wk, fmaf(G[2], z, fmaf(G[1], y, fmaf(G[0], x, o[0]))), ax);
+            ay = fmaf(wk, fmaf(G[5], z, fmaf(G[4], y, fmaf(G[3], x, o[1]))), ay);
+            az = fmaf(wk, fmaf(G[8], z, fmaf(G[7], y, fmaf(G[6], x, o[2]))), az);
+        }
+    }
+}
+
+__global__ void __cluster_dims__(FRONT_CTAS, 1, 1) __launch_bounds__(FRONT_THREADS)
+frame_front_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, float* verts_out, int do_bin) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FrameSmem& S = *reinterpret_cast<FrameSmem*>(smem_raw);
+    cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int fr = frame0 + blockIdx.y, seg_id = blockIdx.x * BIN_PART_WARPS + wid;
-    const float4* ndc = w.ndc + (size_t)fr * m.Vp;
-    uint2* rects = w.face_rect + (size_t)fr * m.Fp;
-    for (int i = tid; i < (BIN_PART_WARPS + 1) * T; i += BIN_PART_THREADS) cnt[i] = 0u;
-    __syncthreads();
+    const int crank = blockIdx.x;                     // gridDim.x == FRONT_CTAS: one cluster per frame
+    const int fr = frame0 + blockIdx.y;
+    const int slot = (w.n_shapes == 1) ? w.slot0 : fr;
+    const float* vs = w.v_shaped + (size_t)slot * m.V * 3;
+
+    PHASE_CLOCK_DECL
+    frame_pose_forward(S, m, w, p, fr, slot, (w.n_shapes == 1) ? 0 : fr);
+    PHASE_CLOCK()   /* pose chain */
+    const float focal = w.focal ? *w.focal : CAM_F;
+
+    // sparse linear-blend skinning + camera: this CTA's share of the vertices
+    float4* ndc = w.ndc + (size_t)fr * m.Vp;
+    {
+        const int vq = (m.V + FRONT_CTAS - 1) / FRONT_CTAS;
+        const int v_lo = crank * vq, v_hi = min(m.V, v_lo + vq);
+        for (int v = v_lo + tid; v < v_hi; v += FRONT_THREADS) {
+            float ax, ay, az;
+            lbs_vertex(S, m, vs, v, ax, ay, az);
+            const float X = ax + S.tr[0], Y = ay + S.tr[1], Z = az + S.tr[2];
+            float xn, yn, zv;
+            camera_fwd(X, Y, Z, xn, yn, zv, focal);
+            ndc[v] = make_float4(xn, yn, zv, 0.f);
+            if (verts_out) {
+                float* o = verts_out + ((size_t)blockIdx.y * m.V + v) * 3;
+                o[0] = X; o[1] = Y; o[2] = Z;
+            }
+        }
+        if (crank == FRONT_CTAS - 1)
+            for (int v = m.V + tid; v < m.Vp; v += FRONT_THREADS) ndc[v] = make_float4(0.f, 0.f, -1.f, 0.f);
+    }
+
+    PHASE_CLOCK()   /* lbs */
+    // 41 model joints: regressed from the posed vertices (+ trans), smal_torch.py:171-184 -- dealt over the cluster's
+    // warps (each re-skins the vertices its joint depends on), gathered in CTA 0 through distributed shared memory
+    {
+        FrameSmem* S0 = cluster.map_shared_rank(&S, 0);
+        for (int j = crank + FRONT_CTAS * wid; j < NMJ; j += FRONT_CTAS * FRONT_WARPS) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            for (int e = m.mj_ptr[j] + lane; e < m.mj_ptr[j + 1]; e += 32) {
+                const float wk = m.mj_weight[e];
+                float vx, vy, vz;
+                lbs_vertex(S, m, vs, m.mj_vert[e], vx, vy, vz);
+                a0 = fmaf(wk, vx, a0); a1 = fmaf(wk, vy, a1); a2 = fmaf(wk, vz, a2);
+            }
+            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+            if (lane == 0) { S0->mj[j * 3 + 0] = a0 + S.tr[0]; S0->mj[j * 3 + 1] = a1 + S.tr[1]; S0->mj[j * 3 + 2] = a2 + S.tr[2]; }
+        }
+    }
+    const int T = w.tiles_x * w.tiles_y;
+    unsigned* cnt = reinterpret_cast<unsigned*>(smem_raw + sizeof(FrameSmem));     // [FRONT_WARPS][T] counts, later write cursors
+    if (do_bin)
+        for (int i = tid; i < (FRONT_WARPS + 1) * T; i += FRONT_THREADS) cnt[i] = 0u;
+    PHASE_CLOCK()   /* model joints */
+    cluster.sync();                                   // every vertex of the frame is projected, every model joint is in CTA 0
+    PHASE_CLOCK()   /* sync1 */
+
+    if (crank == 0) {
+        // keypoint projection + masked MSE (smal_fitter.py:140-144) and its gradient
+        float lk = 0.f, gf = 0.f;
+        if (tid < NKP) {
+            const int j = c_sk.kp_joint[tid];
+            float xn, yn, zv, row, col;
+            camera_fwd(S.mj[j * 3 + 0], S.mj[j * 3 + 1], S.mj[j * 3 + 2], xn, yn, zv, focal);
+            const float half = 0.5f * (float)(w.S - 1);
+            screen_fwd(xn, yn, half, row, col);
+            w.kp_proj[(size_t)fr * NKP * 2 + tid * 2 + 0] = row;
+            w.kp_proj[(size_t)fr * NKP * 2 + tid * 2 + 1] = col;
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+            if (wt.j2d > 0.f && w.vis[(size_t)fr * NKP + tid] != 0) {
+                const float dr = row - w.kp_target[(size_t)fr * NKP * 2 + tid * 2 + 0];
+                const float dc = col - w.kp_target[(size_t)fr * NKP * 2 + tid * 2 + 1];
+                const float scale = wt.j2d * w.inv_window[fr] * (1.f / (float)(NKP * 2));
+                lk = scale * (dr * dr + dc * dc);
+                const float gyn = -half * 2.f * scale * dr, gxn = -half * 2.f * scale * dc;
+                camera_bwd(xn, yn, zv, gxn, gyn, g0, g1, g2, focal);
+                gf = camera_bwd_focal(xn, yn, gxn, gyn, focal);
+            }
+            S.gkp[tid * 3 + 0] = g0; S.gkp[tid * 3 + 1] = g1; S.gkp[tid * 3 + 2] = g2;
+        }
+        const float lsum = block_sum(lk, S.red);
+        if (w.gfocal) { gf = block_sum(gf, S.red); if (tid == 0) w.gfocal_frame[fr * 2 + 0] = gf; }
+        if (tid < NMJ) {
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+            for (int k = 0; k < NKP; ++k)
+                if (c_sk.kp_joint[k] == tid) { g0 += S.gkp[k * 3]; g1 += S.gkp[k * 3 + 1]; g2 += S.gkp[k * 3 + 2]; }
+            float* gj = w.gjoint + (size_t)fr * NMJ * 3 + tid * 3;
+            gj[0] = g0; gj[1] = g1; gj[2] = g2;
+        }
+        if (tid == 0) w.frame_loss[fr * 8 + 0] = lsum;
+    }
+    PHASE_CLOCK()   /* keypoints (CTA 0) */
+    if (!do_bin) return;                              // (uniform over the grid)
+
+    // ---- binning ---------------------------------------------------------------------------------------------
+    unsigned* cost = cnt + FRONT_WARPS * T;           // [T] (pixel, face) pairs per tile, this CTA's faces
+    unsigned* tot = cost + T;                         // [T] entries per tile, then tile offsets
+    unsigned* before = tot + T;                       // [T] entries of the CTAs (= face segments) before this one
+    __shared__ unsigned part[FRONT_THREADS];
+
+    const int seg_id = crank * FRONT_WARPS + wid;
     int f_lo, f_hi;
     bin_segment(m, seg_id, f_lo, f_hi);
+    uint2* rects = w.face_rect + (size_t)fr * m.Fp;
     for (int f = f_lo + lane; f < f_hi; f += 32) {
         const FaceSetup fs = load_face(ndc, m.faces4[f]);
         int c0, c1, r0, r1;
@@ -297,70 +354,77 @@ __global__ void __launch_bounds__(BIN_PART_THREADS) bin_count_kernel(ModelDev m,
         fr4[2] = make_float4(fs.z2, fs.rden, fs.rl01, fs.rl02);
         fr4[3] = make_float4(fs.rl12, 0.f, __uint_as_float(rc.x), __uint_as_float(rc.y));
     }
-    __syncthreads();
-    unsigned* gcnt = w.bin_cnt + ((size_t)fr * BIN_WARPS + (size_t)blockIdx.x * BIN_PART_WARPS) * T;
-    for (int i = tid; i < BIN_PART_WARPS * T; i += BIN_PART_THREADS) gcnt[i] = cnt[i];
-    unsigned* gcost = w.bin_cost + ((size_t)fr * BIN_PARTS + blockIdx.x) * T;
-    for (int i = tid; i < T; i += BIN_PART_THREADS) gcost[i] = cost[i];
-}
+    cluster.sync();                                   // all counts of the frame are final
+    PHASE_CLOCK()   /* count + sync2 */
 
-__global__ void __launch_bounds__(256) bin_scan_kernel(Workspace w, int frame0) {
-    __shared__ unsigned part[256];
-    const int T = w.tiles_x * w.tiles_y, tid = threadIdx.x;
-    const int fr = frame0 + blockIdx.x;
-    unsigned* gcnt = w.bin_cnt + (size_t)fr * BIN_WARPS * T;
-    const unsigned* gcost = w.bin_cost + (size_t)fr * BIN_PARTS * T;
-    // blocked prefix over tiles: each thread owns a run of consecutive tiles
-    const int per = (T + 255) / 256;
-    unsigned local = 0u;
-    for (int k = 0; k < per; ++k) {
-        const int t = tid * per + k;
-        if (t < T) {
-            unsigned a = 0u;
-            for (int q = 0; q < BIN_WARPS; ++q) a += gcnt[q * T + t];
-            local += a;
-            unsigned c = 0u;
-            for (int q = 0; q < BIN_PARTS; ++q) c += gcost[q * T + t];
-            w.tile_cost[(size_t)fr * T + t] = c;
+    // tile totals over the 32 segments (distributed shared memory), entries of the lower-ranked CTAs, pair counts
+    {
+        const unsigned* rcnt[FRONT_CTAS];
+#pragma unroll
+        for (int c = 0; c < FRONT_CTAS; ++c) rcnt[c] = cluster.map_shared_rank(cnt, c);
+        for (int t = tid; t < T; t += FRONT_THREADS) {
+            unsigned a = 0u, b = 0u, cs = 0u;
+#pragma unroll
+            for (int c = 0; c < FRONT_CTAS; ++c) {
+                unsigned x = 0u;
+#pragma unroll
+                for (int q = 0; q < FRONT_WARPS; ++q) x += rcnt[c][q * T + t];
+                a += x;
+                if (c < crank) b += x;
+                cs += rcnt[c][FRONT_WARPS * T + t];
+            }
+            tot[t] = a; before[t] = b;
+            if (crank == 0) w.tile_cost[(size_t)fr * T + t] = cs;
         }
     }
-    part[tid] = local;
     __syncthreads();
-    if (tid == 0) {
-        unsigned run = 0u;
-        for (int i = 0; i < 256; ++i) { const unsigned v = part[i]; part[i] = run; run += v; }
+    // exclusive prefix over the tiles (each thread owns a run of consecutive tiles)
+    const int per = (T + FRONT_THREADS - 1) / FRONT_THREADS;
+    {
+        unsigned local = 0u;
+        for (int k = 0; k < per; ++k) { const int t = tid * per + k; if (t < T) local += tot[t]; }
+        part[tid] = local;
+        __syncthreads();
+        if (wid == 0) {                               // 256 partials: 8 per lane
+            unsigned v8[FRONT_THREADS / 32], sum = 0u;
+#pragma unroll
+            for (int k = 0; k < FRONT_THREADS / 32; ++k) { v8[k] = part[lane * (FRONT_THREADS / 32) + k]; sum += v8[k]; }
+            unsigned incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+            unsigned run = incl - sum;
+#pragma unroll
+            for (int k = 0; k < FRONT_THREADS / 32; ++k) { part[lane * (FRONT_THREADS / 32) + k] = run; run += v8[k]; }
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
-    unsigned run = part[tid];
-    for (int k = 0; k < per; ++k) {
-        const int t = tid * per + k;
-        if (t < T) {
-            toff[t] = run;
-            for (int q = 0; q < BIN_WARPS; ++q) { const unsigned c = gcnt[q * T + t]; gcnt[q * T + t] = run; run += c; }   // counts -> cursors
-            if (t == T - 1) {
-                toff[T] = run;
-                if (run > (unsigned)w.pool_cap) {       // bin_fill drops the entries past the pool: results inexact -> sticky fault
-                    *(volatile unsigned*)w.status = *(volatile unsigned*)w.status | STATUS_POOL_OVERFLOW;
-                    __threadfence_system();
+    cluster.sync();                                   // nobody reads another CTA's counts from here on
+    {
+        unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
+        unsigned run = part[tid];
+        for (int k = 0; k < per; ++k) {
+            const int t = tid * per + k;
+            if (t < T) {
+                const unsigned n_t = tot[t];
+                if (crank == 0) toff[t] = run;
+                unsigned cur = run + before[t];
+#pragma unroll
+                for (int q = 0; q < FRONT_WARPS; ++q) { const unsigned c = cnt[q * T + t]; cnt[q * T + t] = cur; cur += c; }   // counts -> cursors
+                run += n_t;
+                if (crank == 0 && t == T - 1) {
+                    toff[T] = run;
+                    if (run > (unsigned)w.pool_cap) {       // the fill drops the entries past the pool: results inexact -> sticky fault
+                        *(volatile unsigned*)w.status = *(volatile unsigned*)w.status | STATUS_POOL_OVERFLOW;
+                        __threadfence_system();
+                    }
                 }
             }
         }
     }
-}
-
-__global__ void __launch_bounds__(BIN_PART_THREADS) bin_fill_kernel(ModelDev m, Workspace w, int frame0) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = w.tiles_x * w.tiles_y;
-    unsigned* cur = reinterpret_cast<unsigned*>(smem_raw);          // [BIN_PART_WARPS][T] write cursors
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int fr = frame0 + blockIdx.y, seg_id = blockIdx.x * BIN_PART_WARPS + wid;
-    const uint2* rects = w.face_rect + (size_t)fr * m.Fp;
-    const unsigned* gcur = w.bin_cnt + ((size_t)fr * BIN_WARPS + (size_t)blockIdx.x * BIN_PART_WARPS) * T;
-    for (int i = tid; i < BIN_PART_WARPS * T; i += BIN_PART_THREADS) cur[i] = gcur[i];
     __syncthreads();
-    int f_lo, f_hi;
-    bin_segment(m, seg_id, f_lo, f_hi);
+
+    PHASE_CLOCK()   /* scan + sync3 + cursors */
+    // fill in face order within a segment (lanes that hit the same tile in the same step are ranked with match_any)
     const unsigned ltmask = lanemask_lt();
     uint4* pool = w.tile_pool + (size_t)fr * w.pool_cap;
     float4* recs = w.tile_rec + (size_t)fr * w.pool_cap * 4;
@@ -377,7 +441,7 @@ __global__ void __launch_bounds__(BIN_PART_THREADS) bin_fill_kernel(ModelDev m, 
         const ushort4 f4 = m.faces4[f];
         float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
         float rl12 = 0.f;
-        if (nt > 0) {        // the prepared face bin_count wrote
+        if (nt > 0) {        // the prepared face written above (by this thread)
             const float4* fr4 = w.face_rec + ((size_t)fr * m.Fp + f) * 4;
             q0 = fr4[0]; q1 = fr4[1]; q2 = fr4[2]; rl12 = fr4[3].x;
         }
@@ -387,9 +451,9 @@ __global__ void __launch_bounds__(BIN_PART_THREADS) bin_fill_kernel(ModelDev m, 
             const unsigned mm = __match_any_sync(0xffffffffu, t);
             unsigned basepos = 0;
             const int rank = __popc(mm & ltmask);
-            if (t >= 0) basepos = cur[wid * T + t];
+            if (t >= 0) basepos = cnt[wid * T + t];
             __syncwarp();
-            if (t >= 0 && rank == 0) cur[wid * T + t] = basepos + (unsigned)__popc(mm);
+            if (t >= 0 && rank == 0) cnt[wid * T + t] = basepos + (unsigned)__popc(mm);
             __syncwarp();
             if (t >= 0) {
                 const unsigned pos = basepos + (unsigned)rank;
@@ -408,16 +472,18 @@ __global__ void __launch_bounds__(BIN_PART_THREADS) bin_fill_kernel(ModelDev m, 
             }
         }
     }
+    PHASE_CLOCK() PHASE_CLOCK_PRINT("frame_front [pose lbs joints sync1 kp count+sync2 scan fill]", blockIdx.y == 0 && crank == 0 && tid == 0)
     if (dropped) atomicAdd(w.counters + 2, (unsigned long long)dropped);
 }
 
-size_t bin_smem_bytes(const Workspace& w) { return (size_t)(BIN_PART_WARPS + 1) * w.tiles_x * w.tiles_y * sizeof(unsigned); }
+size_t frame_front_smem_bytes(const Workspace& w) {
+    return sizeof(FrameSmem) + (size_t)(FRONT_WARPS + 3) * w.tiles_x * w.tiles_y * sizeof(unsigned);
+}
 
-void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st) {
-    const dim3 grid(BIN_PARTS, n);
-    bin_count_kernel<<<grid, BIN_PART_THREADS, bin_smem_bytes(w), st>>>(m, w, frame0);
-    bin_scan_kernel<<<n, 256, 0, st>>>(w, frame0);
-    bin_fill_kernel<<<grid, BIN_PART_THREADS, bin_smem_bytes(w), st>>>(m, w, frame0);
+void launch_frame_front(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n, Weights wt,
+                        float* verts_out, bool do_bin, cudaStream_t st) {
+    const dim3 grid(FRONT_CTAS, n);
+    frame_front_kernel<<<grid, FRONT_THREADS, frame_front_smem_bytes(w), st>>>(m, w, p, frame0, wt, verts_out, do_bin ? 1 : 0);
 }
 
 // ---------------------------------------------------------------------------
@@ -608,20 +674,34 @@ void launch_raster_backward(const ModelDev& m, const Workspace& w, int frame0, i
 }
 
 // ---------------------------------------------------------------------------
-// frame_backward
+// frame_backward: one frame per thread-block cluster of BACK_CTAS CTAs.
+//   every CTA   pose chain (redundant), then its share of the vertices: face -> vertex gather, camera^T, keypoint
+//               regressor^T, LBS^T (v_shaped part); its share of the silhouette-loss rows;
+//   cluster.sync
+//   every CTA   its share of the 35 joints: dL/dG_j, dL/doff_j (warp per joint over the CSC skinning weights), stored into
+//               CTA 0's shared memory (distributed shared memory);
+//   cluster.sync
+//   CTA 0       chain^T, Rodrigues^T, priors, temporal term, outputs.
+// With few frames per GPU the vertex and joint phases run on 4x as many SMs as with one CTA per frame.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(FRAME_BWD_THREADS)
+constexpr int BACK_CTAS = 4, BACK_THREADS = 512, BACK_PRIOR_CTA = BACK_CTAS - 1;
+
+__global__ void __cluster_dims__(BACK_CTAS, 1, 1) __launch_bounds__(BACK_THREADS)
 frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, Weights wt) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FrameSmem& S = *reinterpret_cast<FrameSmem*>(smem_raw);
-    float* gw = reinterpret_cast<float*>(smem_raw + sizeof(FrameSmem));     // [V*3] dL/d(world verts)
+    cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int fr = frame0 + blockIdx.x;
+    const int crank = blockIdx.x;                     // gridDim.x == BACK_CTAS: one cluster per frame
+    const int fr = frame0 + blockIdx.y;
     const int slot = (w.n_shapes == 1) ? w.slot0 : fr;
     const float* vs = w.v_shaped + (size_t)slot * m.V * 3;
     const bool use_sil = wt.sil > 0.f;
+    FrameSmem* S0 = cluster.map_shared_rank(&S, 0);   // CTA 0's copy: receives the partial results
+    PHASE_CLOCK_DECL
 
     frame_pose_forward(S, m, w, p, fr, slot, (w.n_shapes == 1) ? 0 : fr);
+    PHASE_CLOCK()   /* pose chain */
     if (tid < NMJ * 3) S.gj[tid] = w.gjoint[(size_t)fr * NMJ * 3 + tid];
     __syncthreads();
 
@@ -629,16 +709,29 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
     const float4* ndc = w.ndc + (size_t)fr * m.Vp;
     const float* fg = w.face_grad + (size_t)fr * m.Fp * 8;
     float* dvs = w.dvs + (size_t)fr * m.V * 3;
+    float* gw = w.gw + (size_t)fr * m.V * 3;          // dL/d(world verts): read across the cluster in step 2
     float t0 = 0.f, t1 = 0.f, t2 = 0.f, gf = 0.f;
     const float focal = w.focal ? *w.focal : CAM_F;
-    for (int v = tid; v < m.V; v += blockDim.x) {
+    const int vq = (m.V + BACK_CTAS - 1) / BACK_CTAS;
+    const int v_lo = crank * vq, v_hi = min(m.V, v_lo + vq);
+    for (int v = v_lo + tid; v < v_hi; v += BACK_THREADS) {
         float g0 = 0.f, g1 = 0.f, g2 = 0.f;
         if (use_sil) {
+            // (a vertex has at most a dozen incident faces: blocks of 4 independent loads instead of a dependent chain)
             float gx = 0.f, gy = 0.f;
-            for (int e = m.v2f_ptr[v]; e < m.v2f_ptr[v + 1]; ++e) {
-                const int fc = m.v2f_fc[e];
-                const float2 q = *reinterpret_cast<const float2*>(fg + (size_t)(fc >> 2) * 8 + (fc & 3) * 2);
-                gx += q.x; gy += q.y;
+            const int e0 = m.v2f_ptr[v], e1 = m.v2f_ptr[v + 1];
+            for (int e = e0; e < e1; e += 4) {
+                float2 q[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    q[k] = make_float2(0.f, 0.f);
+                    if (e + k < e1) {
+                        const int fc = m.v2f_fc[e + k];
+                        q[k] = *reinterpret_cast<const float2*>(fg + (size_t)(fc >> 2) * 8 + (fc & 3) * 2);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { gx += q[k].x; gy += q[k].y; }
             }
             const float4 nd = ndc[v];
             camera_bwd(nd.x, nd.y, nd.z, gx, gy, g0, g1, g2, focal);
@@ -664,25 +757,36 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
         }
         dvs[v * 3 + 0] = d0; dvs[v * 3 + 1] = d1; dvs[v * 3 + 2] = d2;
     }
-    // dL/dtrans = sum_v (raster part) + sum_j dL/djoint_j   (verts + trans, joints + trans)
-    t0 = block_sum(t0, S.red); t1 = block_sum(t1, S.red); t2 = block_sum(t2, S.red);
-    if (w.gfocal) { gf = block_sum(gf, S.red); if (tid == 0) w.gfocal_frame[fr * 2 + 1] = gf; }
-    if (tid == 0) {
-        float a0 = t0, a1 = t1, a2 = t2;
-        for (int j = 0; j < NMJ; ++j) { a0 += S.gj[j * 3]; a1 += S.gj[j * 3 + 1]; a2 += S.gj[j * 3 + 2]; }
-        S.ttr[0] = a0; S.ttr[1] = a1; S.ttr[2] = a2;
+    // this CTA's share of the silhouette-loss rows (fixed order: by CTA, then by thread)
+    float lsil = 0.f;
+    if (use_sil) {
+        const int R4 = w.tiles_x * w.tiles_y * REGIONS_PER_TILE * REGION_H;
+        const int rq = (R4 + BACK_CTAS - 1) / BACK_CTAS;
+        const int r_hi = min(R4, (crank + 1) * rq);
+        for (int r = crank * rq + tid; r < r_hi; r += BACK_THREADS) lsil += w.region_l1[(size_t)fr * R4 + r];
     }
-    __syncthreads();
+    t0 = block_sum(t0, S.red); t1 = block_sum(t1, S.red); t2 = block_sum(t2, S.red);
+    gf = block_sum(gf, S.red);
+    lsil = block_sum(lsil, S.red);
+    if (tid == 0) {
+        float* cp = S0->cpart[crank];
+        cp[0] = t0; cp[1] = t1; cp[2] = t2; cp[3] = gf; cp[4] = lsil;
+    }
+    PHASE_CLOCK()   /* vertex phase */
+    cluster.sync();                                   // every vertex gradient of the frame is in gw
+    PHASE_CLOCK()   /* sync */
 
-    // 2. per joint: dL/dG_j = sum_v w gw_v vs_v^T, dL/doff_j = sum_v w gw_v
-    for (int j = wid; j < NJ; j += (int)(blockDim.x >> 5)) {
+    // 2. per joint: dL/dG_j = sum_v w gw_v vs_v^T, dL/doff_j = sum_v w gw_v.  The CSC skinning weights are cut into
+    //    chunks of <= SKIN_CHUNK entries of one joint; a warp sums a chunk, the chunks are dealt over the cluster's warps
+    //    and their sums land in CTA 0 (distributed shared memory), which adds a joint's chunks in order.
+    for (int ch = crank + BACK_CTAS * wid; ch < m.n_skin_chunks; ch += BACK_CTAS * (BACK_THREADS / 32)) {
         float a[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) a[k] = 0.f;
-        for (int e = m.skinT_ptr[j] + lane; e < m.skinT_ptr[j + 1]; e += 32) {
+        for (int e = m.chunk_lo[ch] + lane; e < m.chunk_hi[ch]; e += 32) {
             const int v = m.skinT_vert[e];
             const float wk = m.skinT_weight[e];
-            const float gx = wk * gw[v * 3], gy = wk * gw[v * 3 + 1], gz = wk * gw[v * 3 + 2];
+            const float gx = wk * __ldcg(gw + v * 3), gy = wk * __ldcg(gw + v * 3 + 1), gz = wk * __ldcg(gw + v * 3 + 2);
             const float x = vs[v * 3], y = vs[v * 3 + 1], z = vs[v * 3 + 2];
             a[0] = fmaf(gx, x, a[0]); a[1] = fmaf(gx, y, a[1]); a[2] = fmaf(gx, z, a[2]);
             a[3] = fmaf(gy, x, a[3]); a[4] = fmaf(gy, y, a[4]); a[5] = fmaf(gy, z, a[5]);
@@ -693,9 +797,73 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
         for (int k = 0; k < 12; ++k) a[k] = warp_sum(a[k]);
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) S.Gb[j * 9 + k] = a[k];
-            S.offb[j * 3] = a[9]; S.offb[j * 3 + 1] = a[10]; S.offb[j * 3 + 2] = a[11];
+            for (int k = 0; k < 12; ++k) S0->chunk_sum[ch][k] = a[k];
         }
+    }
+    PHASE_CLOCK()   /* joint chunks */
+    cluster.sync();                                   // CTA 0 holds every chunk's sums
+    PHASE_CLOCK()   /* sync */
+
+    // 5. (on its own CTA, while CTA 0 runs the chain backwards) pose prior (smal_fitter.py:153-157,
+    //    pose_prior_35.py:112-124), splay (:159-160) and the optional joint-limit hinge: values and gradient
+    const float invw = w.inv_window[fr];
+    if (crank == BACK_PRIOR_CTA) {
+        float lpose = 0.f, lsplay = 0.f, llimit = 0.f, gth = 0.f;
+        if (wt.pose > 0.f) {
+            if (tid < NJ * 3) {
+                float a = 0.f;
+                for (int i = 0; i < NJ * 3; ++i) a = fmaf(S.theta[i] - m.pose_mean[i], m.pose_prec[i * (NJ * 3) + tid], a);
+                a *= m.pose_use[tid];
+                S.res[tid] = a;
+                lpose = a * a;
+            }
+            __syncthreads();
+            const float cp = wt.pose * invw * (1.f / (float)(NJ * 3));
+            if (tid < NJ * 3) {
+                float a = 0.f;
+                for (int k = 0; k < NJ * 3; ++k) a = fmaf(m.pose_prec[tid * (NJ * 3) + k], S.res[k] * m.pose_use[k], a);
+                gth += 2.f * cp * a;
+            }
+            lpose *= cp;
+        }
+        if (wt.splay > 0.f && tid >= 3 && tid < NJ * 3) {
+            const int c3 = tid % 3;
+            if (c3 != 1) {
+                const float q = S.theta[tid];
+                lsplay = wt.splay * q * q;
+                gth += 2.f * wt.splay * q;
+            }
+        }
+        // joint-limit hinge (the term the reference keeps commented out at smal_fitter.py:146-151, limits of
+        // priors/joint_limits_prior.py): w_limit * mean over (B, 34, 3) of max(q - hi, 0) + max(lo - q, 0)
+        if (wt.limit > 0.f && w.limit_min && tid >= 3 && tid < NJ * 3) {
+            const float q = S.theta[tid], lo = w.limit_min[tid - 3], hi = w.limit_max[tid - 3];
+            const float cl = wt.limit * invw * (1.f / (float)((NJ - 1) * 3));
+            llimit = cl * (fmaxf(q - hi, 0.f) + fmaxf(lo - q, 0.f));
+            gth += cl * ((q > hi ? 1.f : 0.f) - (q < lo ? 1.f : 0.f));
+        }
+        lpose = block_sum(lpose, S.red);
+        lsplay = block_sum(lsplay, S.red);
+        llimit = block_sum(llimit, S.red);
+        if (tid < NJ * 3) S0->prior_g[tid] = gth;
+        if (tid == 0) { S0->prior_l[0] = lpose; S0->prior_l[1] = lsplay; S0->prior_l[2] = llimit; }
+    }
+    if (crank != 0) { cluster.sync(); return; }       // (the prior CTA's results are in CTA 0 when this barrier completes)
+
+    // per joint: its chunks in order
+    if (tid < NJ * 12) {
+        const int j = tid / 12, k = tid - j * 12;
+        float a = 0.f;
+        for (int ch = m.joint_chunk_ptr[j]; ch < m.joint_chunk_ptr[j + 1]; ++ch) a += S.chunk_sum[ch][k];
+        if (k < 9) S.Gb[j * 9 + k] = a; else S.offb[j * 3 + (k - 9)] = a;
+    }
+    // dL/dtrans = sum_v (raster part) + sum_j dL/djoint_j   (verts + trans, joints + trans); partials in CTA order
+    if (tid == BACK_THREADS - 1) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, af = 0.f;
+        for (int c = 0; c < BACK_CTAS; ++c) { a0 += S.cpart[c][0]; a1 += S.cpart[c][1]; a2 += S.cpart[c][2]; af += S.cpart[c][3]; }
+        if (w.gfocal) w.gfocal_frame[fr * 2 + 1] = af;
+        for (int j = 0; j < NMJ; ++j) { a0 += S.gj[j * 3]; a1 += S.gj[j * 3 + 1]; a2 += S.gj[j * 3 + 2]; }
+        S.ttr[0] = a0; S.ttr[1] = a1; S.ttr[2] = a2;
     }
     __syncthreads();
 
@@ -716,6 +884,7 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
     if (tid == 0) chain_bwd_push(c, b, 0, -1);
     __syncthreads();
 
+    PHASE_CLOCK()   /* chain^T */
     // 4. Rodrigues^T, log-scale gradient, rest-joint gradient
     if (tid < NJ) {
         float thb[3] = {0.f, 0.f, 0.f};
@@ -732,53 +901,18 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
     if (tid >= 96 && tid < 96 + NJ * 3) w.gJ[(size_t)fr * NJ * 3 + (tid - 96)] = S.Jb[tid - 96];
     __syncthreads();
 
-    // 5. pose prior (smal_fitter.py:153-157, pose_prior_35.py:112-124) and splay (:159-160)
-    float lpose = 0.f, lsplay = 0.f;
-    const float invw = w.inv_window[fr];
-    if (wt.pose > 0.f) {
-        if (tid < NJ * 3) {
-            float a = 0.f;
-            for (int i = 0; i < NJ * 3; ++i) a = fmaf(S.theta[i] - m.pose_mean[i], m.pose_prec[i * (NJ * 3) + tid], a);
-            a *= m.pose_use[tid];
-            S.res[tid] = a;
-            lpose = a * a;
-        }
-        __syncthreads();
-        const float cp = wt.pose * invw * (1.f / (float)(NJ * 3));
-        if (tid < NJ * 3) {
-            float a = 0.f;
-            for (int k = 0; k < NJ * 3; ++k) a = fmaf(m.pose_prec[tid * (NJ * 3) + k], S.res[k] * m.pose_use[k], a);
-            S.thg[tid] += 2.f * cp * a;
-        }
-        lpose *= cp;
-    }
-    if (wt.splay > 0.f && tid >= 3 && tid < NJ * 3) {
-        const int c3 = tid % 3;
-        if (c3 != 1) {
-            const float q = S.theta[tid];
-            lsplay = wt.splay * q * q;
-            S.thg[tid] += 2.f * wt.splay * q;
-        }
-    }
-    // joint-limit hinge (the term the reference keeps commented out at smal_fitter.py:146-151, limits of
-    // priors/joint_limits_prior.py): w_limit * mean over (B, 34, 3) of max(q - hi, 0) + max(lo - q, 0)
-    float llimit = 0.f;
-    if (wt.limit > 0.f && w.limit_min && tid >= 3 && tid < NJ * 3) {
-        const float q = S.theta[tid], lo = w.limit_min[tid - 3], hi = w.limit_max[tid - 3];
-        const float cl = wt.limit * invw * (1.f / (float)((NJ - 1) * 3));
-        llimit = cl * (fmaxf(q - hi, 0.f) + fmaxf(lo - q, 0.f));
-        S.thg[tid] += cl * ((q > hi ? 1.f : 0.f) - (q < lo ? 1.f : 0.f));
-    }
-    lpose = block_sum(lpose, S.red);
-    lsplay = block_sum(lsplay, S.red);
-    llimit = block_sum(llimit, S.red);
-    float lsil = 0.f;
+    PHASE_CLOCK()   /* rodrigues^T etc */
+    // 5. priors: formed by CTA BACK_PRIOR_CTA meanwhile
+    cluster.sync();
+    PHASE_CLOCK()   /* wait for the priors */
+    if (tid < NJ * 3) S.thg[tid] += S.prior_g[tid];
+    const float lpose = S.prior_l[0], lsplay = S.prior_l[1], llimit = S.prior_l[2];
+    float lsil_total = 0.f;
     if (use_sil) {
-        const int R4 = w.tiles_x * w.tiles_y * REGIONS_PER_TILE * REGION_H;
-        for (int r = tid; r < R4; r += blockDim.x) lsil += w.region_l1[(size_t)fr * R4 + r];
-        lsil = block_sum(lsil, S.red) * wt.sil * invw / ((float)w.S * (float)w.S);
+        for (int c = 0; c < BACK_CTAS; ++c) lsil_total += S.cpart[c][4];
+        lsil_total = lsil_total * wt.sil * invw / ((float)w.S * (float)w.S);
     }
-    if (tid == 0) { w.frame_loss[fr * 8 + 1] = lpose; w.frame_loss[fr * 8 + 2] = lsplay; w.frame_loss[fr * 8 + 3] = lsil; w.frame_loss[fr * 8 + 4] = llimit; }
+    if (tid == 0) { w.frame_loss[fr * 8 + 1] = lpose; w.frame_loss[fr * 8 + 2] = lsplay; w.frame_loss[fr * 8 + 3] = lsil_total; w.frame_loss[fr * 8 + 4] = llimit; }
     // get_temporal (smal_fitter.py:177-190) folded in (wt.temp > 0, smalfit_fused_step): frame fr owns the pair
     // (fr, fr + 1) and takes the gradient of both pairs it is part of.  The neighbours' parameters are read from
     // global memory (nothing writes them during this kernel).  Same operations as temporal_kernel, and the sum
@@ -811,12 +945,12 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
     if (tid < 3) { if (g.glob) g.glob[fr * 3 + tid] = __fadd_rn(__fmul_rn(S.thg[tid], w.gmask[tid]), __fmul_rn(tg, tmask)); }
     else if (tid < NJ * 3) { if (g.joint) g.joint[(size_t)fr * (NJ - 1) * 3 + (tid - 3)] = __fadd_rn(__fmul_rn(S.thg[tid], w.rmask[tid - 3]), __fmul_rn(tg, tmask)); }
     else if (tid < NJ * 3 + 3) { if (g.trans) g.trans[fr * 3 + (tid - NJ * 3)] = __fadd_rn(S.ttr[tid - NJ * 3], __fmul_rn(tg, tmask)); }
+    PHASE_CLOCK() PHASE_CLOCK_PRINT("frame_backward [pose vertex sync chunks sync chainT rodT prior-wait out]", blockIdx.y == 0 && tid == 0)
 }
 
 void launch_frame_backward(const ModelDev& m, const Workspace& w, const Params& p, const Grads& g,
                            int frame0, int n, Weights wt, cudaStream_t st) {
-    const size_t smem = sizeof(FrameSmem) + (size_t)m.V * 3 * sizeof(float);
-    frame_backward_kernel<<<n, FRAME_BWD_THREADS, smem, st>>>(m, w, p, g, frame0, wt);
+    frame_backward_kernel<<<dim3(BACK_CTAS, n), BACK_THREADS, sizeof(FrameSmem), st>>>(m, w, p, g, frame0, wt);
 }
 
 // ---------------------------------------------------------------------------
@@ -1343,14 +1477,11 @@ void launch_fp32_peak(float* out, int n_sm, int packed, int iters, cudaStream_t 
 }
 
 cudaError_t configure_kernels(const ModelDev& m) {
-    const int frame_smem = (int)(sizeof(FrameSmem) + (size_t)m.V * 3 * sizeof(float));
-    cudaError_t e = cudaFuncSetAttribute(frame_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);
+    (void)m;
+    cudaError_t e = cudaFuncSetAttribute(frame_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameSmem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(frame_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, frame_smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (BIN_PART_WARPS + 1) * MAX_TILES * (int)sizeof(unsigned));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(bin_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (BIN_PART_WARPS + 1) * MAX_TILES * (int)sizeof(unsigned));
+    e = cudaFuncSetAttribute(frame_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(sizeof(FrameSmem) + (size_t)(FRONT_WARPS + 3) * MAX_TILES * sizeof(unsigned)));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(raster_tile_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_tile_smem_bytes());
 }

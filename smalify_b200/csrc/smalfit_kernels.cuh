@@ -7,11 +7,9 @@
 
 namespace smf {
 
-constexpr int FRAME_FWD_THREADS = 512;
-constexpr int BIN_WARPS = 32;               // face segments per frame (one warp each)
-constexpr int BIN_PARTS = 4;                // CTAs per frame in bin_count / bin_fill
+constexpr int BIN_WARPS = 64;               // face segments per frame (one warp each)
+constexpr int BIN_PARTS = 4;                // CTAs of a frame's cluster in frame_front
 constexpr int BIN_PART_WARPS = BIN_WARPS / BIN_PARTS, BIN_PART_THREADS = BIN_PART_WARPS * 32;
-constexpr int FRAME_BWD_THREADS = 1024;
 constexpr int REGION_W = 8, REGION_H = 4;   // granularity of the per-row silhouette loss sums (region_l1 / region_tsum)
 constexpr int TILE_W = 32, TILE_H = 32;     // rasteriser work item
 constexpr int REGIONS_PER_TILE = (TILE_W / REGION_W) * (TILE_H / REGION_H);
@@ -25,6 +23,7 @@ constexpr int RT_PLANE = RT_PITCH * (TILE_H + 1) + 3;      // words per plane (3
 constexpr int RT_BLK = 16;                  // prepared faces per TMA block
 constexpr int MAX_TILES = 1024;             // 32x32 tiles per frame (image side <= 1024)
 constexpr int MAX_LEVELS = 16;
+constexpr int SKIN_CHUNK = 96, MAX_SKIN_CHUNKS = 192;
 constexpr float P_SKIP = 2.98023224e-8f;    // 2^-25: below this 1-P rounds to 1.0f in fp32
 
 struct ModelDev {
@@ -34,6 +33,8 @@ struct ModelDev {
     const ushort4* faces4;       // [Fp] (v0,v1,v2,valid) ; padding faces have valid = 0
     const int* skin_joint; const float* skin_weight;
     const int* skinT_ptr; const int* skinT_vert; const float* skinT_weight;
+    // the CSC skinning weights cut into chunks of at most SKIN_CHUNK entries of one joint (frame_backward: a warp per chunk)
+    int n_skin_chunks; const int* chunk_joint; const int* chunk_lo; const int* chunk_hi; const int* joint_chunk_ptr;
     const int* jreg_ptr; const int* jreg_vert; const float* jreg_weight;
     const int* jregT_ptr; const int* jregT_joint; const float* jregT_weight;
     const int* mj_ptr; const int* mj_vert; const float* mj_weight;
@@ -80,14 +81,13 @@ struct Workspace {
                                 //   (x0,y0,x1,y1) (x2,y2,z0,z1) (z2, 1/(area+eps), 1/|e01|^2, 1/|e02|^2) (1/|e12|^2, fid, rect, -)
     unsigned* tile_off;         // [N][tiles+1] offsets into the frame's pool
     unsigned* tile_cost;        // [N][tiles] (pixel, face) pairs of the tile
-    unsigned* bin_cnt;          // [N][BIN_WARPS][tiles] per (face segment, tile): count, then write cursor
-    unsigned* bin_cost;         // [N][BIN_PARTS][tiles] pair-count partials
     int pool_cap;
     uint2* pix;                 // [N][S*S] (float coef, u32 tkey)
     uint16_t* pix_tfid;         // [N][S*S] tie face id (capped pixels only)
     float* region_l1;           // [N][tiles*32*4] per region and pixel row: sum |alpha - T|
     float* face_grad;           // [N][Fp][8] (gx0,gy0,gx1,gy1,gx2,gy2,-,-)
     float* dvs;                 // [N][V*3]  per-frame dL/dv_shaped
+    float* gw;                  // [N][V*3]  per-frame dL/d(world vertices) (frame_backward, read across its cluster)
     float* gJ;                  // [N][105]  per-frame dL/dJ(rest joints)
     float* gls;                 // [N][6]    per-frame dL/dlogscale
     float* frame_loss;          // [N][8]    kp, pose, splay, silhouette, joint limit, temporal (joint, global, trans)
@@ -134,15 +134,15 @@ struct TileScratch {        // tile rasteriser: per resident CTA
     int nsub;               // > 0: force this many bands for every list longer than split_len (measurements)
     int fair;               // a band's list is at most 1/fair of a CTA's fair share of the launch (0: default 3)
     int split_len;          // > 0: overrides the list length above which a tile is cut into bands
+    int min_item;           // > 0: overrides RT_MIN_ITEM
 };
 
 // ---- launch wrappers (defined in smalfit_kernels.cu) ----------------------
 void upload_skeleton(const SkeletonConst& sk);
 cudaError_t configure_kernels(const ModelDev& m);
 void launch_shape_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n, cudaStream_t st);
-void launch_frame_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n,
-                          Weights wt, float* verts_out, cudaStream_t st);
-void launch_bin_faces(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st);
+void launch_frame_front(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n, Weights wt,
+                        float* verts_out, bool do_bin, cudaStream_t st);
 size_t raster_tile_smem_bytes();
 void launch_raster_tile_forward(const ModelDev& m, const Workspace& w, const TileScratch& ts, int frame0, int n, Weights wt,
                                 float* alpha_out, int n_ctas, cudaStream_t st);

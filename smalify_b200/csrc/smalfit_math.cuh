@@ -85,9 +85,10 @@ SMF_HD void mat3_mul_at(const float* A, const float* B, float* C) {   // C = A^T
 // Rodrigues (batch_lbs.py:33-52)
 // ---------------------------------------------------------------------------
 SMF_HD void rodrigues_fwd(const float* th, float* R) {
-    const float ux = th[0] + RODRIGUES_EPS, uy = th[1] + RODRIGUES_EPS, uz = th[2] + RODRIGUES_EPS;
+    const float t0 = th[0], t1 = th[1], t2 = th[2];
+    const float ux = t0 + RODRIGUES_EPS, uy = t1 + RODRIGUES_EPS, uz = t2 + RODRIGUES_EPS;
     const float a = sqrtf(ux * ux + uy * uy + uz * uz);
-    const float rx = th[0] / a, ry = th[1] / a, rz = th[2] / a;
+    const float rx = t0 / a, ry = t1 / a, rz = t2 / a;
     const float c = cosf(a), s = sinf(a), k = 1.f - c;
     R[0] = c + k * rx * rx; R[1] = k * rx * ry - s * rz; R[2] = k * rx * rz + s * ry;
     R[3] = k * ry * rx + s * rz; R[4] = c + k * ry * ry; R[5] = k * ry * rz - s * rx;
@@ -137,28 +138,27 @@ SMF_HD void chain_scale(int j, const float* ls, const int* scale_axis, float* s)
     }
 }
 
-// joint i given its parent p is done (root: p < 0)
+// joint i given its parent p is done (root: p < 0).  Inputs are read into locals first and results stored at the end:
+// the arrays live in shared memory, and stores interleaved with loads through pointers the compiler cannot prove
+// distinct would serialise every access (the chain is latency-bound: ~10 dependent levels per frame).
 SMF_HD void chain_fwd_joint(const ChainFwd& c, int i, int p) {
-    float* Rw = c.Rw + i * 9;
+    float Rw[9], G[9], t[3], off[3], J[3], si[3];
+    for (int k = 0; k < 3; ++k) { J[k] = c.J[i * 3 + k]; si[k] = c.s[i * 3 + k]; }
     if (p < 0) {
         for (int k = 0; k < 9; ++k) Rw[k] = c.R[k];
-        for (int k = 0; k < 3; ++k) c.t[k] = c.J[k];
+        for (int k = 0; k < 3; ++k) t[k] = J[k];
     } else {
-        mat3_mul(c.Rw + p * 9, c.R + i * 9, Rw);
-        const float* Rp = c.Rw + p * 9;
-        const float* sp = c.s + p * 3;
-        const float d[3] = {sp[0] * (c.J[i * 3 + 0] - c.J[p * 3 + 0]),
-                            sp[1] * (c.J[i * 3 + 1] - c.J[p * 3 + 1]),
-                            sp[2] * (c.J[i * 3 + 2] - c.J[p * 3 + 2])};
-        for (int r = 0; r < 3; ++r)
-            c.t[i * 3 + r] = c.t[p * 3 + r] + Rp[r * 3 + 0] * d[0] + Rp[r * 3 + 1] * d[1] + Rp[r * 3 + 2] * d[2];
+        float Rp[9], Ri[9], tp[3], d[3];
+        for (int k = 0; k < 9; ++k) { Rp[k] = c.Rw[p * 9 + k]; Ri[k] = c.R[i * 9 + k]; }
+        for (int k = 0; k < 3; ++k) { tp[k] = c.t[p * 3 + k]; d[k] = c.s[p * 3 + k] * (J[k] - c.J[p * 3 + k]); }
+        mat3_mul(Rp, Ri, Rw);
+        for (int r = 0; r < 3; ++r) t[r] = tp[r] + Rp[r * 3 + 0] * d[0] + Rp[r * 3 + 1] * d[1] + Rp[r * 3 + 2] * d[2];
     }
-    float* G = c.G + i * 9;
-    const float* si = c.s + i * 3;
     for (int r = 0; r < 3; ++r)
         for (int a = 0; a < 3; ++a) G[r * 3 + a] = Rw[r * 3 + a] * si[a];
-    for (int r = 0; r < 3; ++r)
-        c.off[i * 3 + r] = c.t[i * 3 + r] - (G[r * 3 + 0] * c.J[i * 3 + 0] + G[r * 3 + 1] * c.J[i * 3 + 1] + G[r * 3 + 2] * c.J[i * 3 + 2]);
+    for (int r = 0; r < 3; ++r) off[r] = t[r] - (G[r * 3 + 0] * J[0] + G[r * 3 + 1] * J[1] + G[r * 3 + 2] * J[2]);
+    for (int k = 0; k < 9; ++k) { c.Rw[i * 9 + k] = Rw[k]; c.G[i * 9 + k] = G[k]; }
+    for (int k = 0; k < 3; ++k) { c.t[i * 3 + k] = t[k]; c.off[i * 3 + k] = off[k]; }
 }
 
 struct ChainBwd {
@@ -172,59 +172,58 @@ struct ChainBwd {
 };
 
 // Step 1 (any order, per joint): fold the A_i = [G_i | t_i - G_i J_i] layer.
-// Initialises tb, Rwb, sb, Jb of joint i.
+// Initialises tb, Rwb, sb, Jb of joint i.  (locals first, stores last: see chain_fwd_joint)
 SMF_HD void chain_bwd_local(const ChainFwd& c, const ChainBwd& b, int i) {
-    const float* G = c.G + i * 9;
-    const float* Rw = c.Rw + i * 9;
-    const float* si = c.s + i * 3;
-    const float* ob = b.offb + i * 3;
-    const float* Ji = c.J + i * 3;
-    for (int r = 0; r < 3; ++r) b.tb[i * 3 + r] = ob[r];
+    float G[9], Rw[9], Gb[9], si[3], ob[3], Ji[3];
+    for (int k = 0; k < 9; ++k) { G[k] = c.G[i * 9 + k]; Rw[k] = c.Rw[i * 9 + k]; Gb[k] = b.Gb[i * 9 + k]; }
+    for (int k = 0; k < 3; ++k) { si[k] = c.s[i * 3 + k]; ob[k] = b.offb[i * 3 + k]; Ji[k] = c.J[i * 3 + k]; }
     // off = t - G J :  Gb_eff = Gb - offb J^T ,  Jb = -G^T offb
-    float Ge[9];
+    float Ge[9], Jb[3], sb[3], Rwb[9];
     for (int r = 0; r < 3; ++r)
-        for (int a = 0; a < 3; ++a) Ge[r * 3 + a] = b.Gb[i * 9 + r * 3 + a] - ob[r] * Ji[a];
-    for (int a = 0; a < 3; ++a)
-        b.Jb[i * 3 + a] = -(G[0 * 3 + a] * ob[0] + G[1 * 3 + a] * ob[1] + G[2 * 3 + a] * ob[2]);
+        for (int a = 0; a < 3; ++a) Ge[r * 3 + a] = Gb[r * 3 + a] - ob[r] * Ji[a];
+    for (int a = 0; a < 3; ++a) Jb[a] = -(G[0 * 3 + a] * ob[0] + G[1 * 3 + a] * ob[1] + G[2 * 3 + a] * ob[2]);
     // G = Rw diag(s)
     for (int a = 0; a < 3; ++a) {
-        b.sb[i * 3 + a] = Rw[0 * 3 + a] * Ge[0 * 3 + a] + Rw[1 * 3 + a] * Ge[1 * 3 + a] + Rw[2 * 3 + a] * Ge[2 * 3 + a];
-        for (int r = 0; r < 3; ++r) b.Rwb[i * 9 + r * 3 + a] = Ge[r * 3 + a] * si[a];
+        sb[a] = Rw[0 * 3 + a] * Ge[0 * 3 + a] + Rw[1 * 3 + a] * Ge[1 * 3 + a] + Rw[2 * 3 + a] * Ge[2 * 3 + a];
+        for (int r = 0; r < 3; ++r) Rwb[r * 3 + a] = Ge[r * 3 + a] * si[a];
     }
+    for (int k = 0; k < 3; ++k) { b.tb[i * 3 + k] = ob[k]; b.Jb[i * 3 + k] = Jb[k]; b.sb[i * 3 + k] = sb[k]; }
+    for (int k = 0; k < 9; ++k) b.Rwb[i * 9 + k] = Rwb[k];
 }
 
 // Step 2 (children before parents): push joint i's (complete) tb / Rwb to its parent p
-// and emit Rb_i.  Must be serialised per parent (the kernels pull per parent instead,
-// see chain_bwd_pull); kept for the serial host check.
+// and emit Rb_i.  Must be serialised per parent (the kernels let the parent's thread run its children in turn).
 SMF_HD void chain_bwd_push(const ChainFwd& c, const ChainBwd& b, int i, int p) {
     if (p < 0) {
         for (int k = 0; k < 9; ++k) b.Rb[k] = b.Rwb[k];
         for (int k = 0; k < 3; ++k) b.Jb[k] += b.tb[k];     // t_0 = J_0
         return;
     }
-    const float* Rp = c.Rw + p * 9;
-    const float* sp = c.s + p * 3;
-    const float* tbi = b.tb + i * 3;
-    float delta[3], RtT[3];
-    for (int a = 0; a < 3; ++a) {
-        delta[a] = c.J[i * 3 + a] - c.J[p * 3 + a];
-        RtT[a] = Rp[0 * 3 + a] * tbi[0] + Rp[1 * 3 + a] * tbi[1] + Rp[2 * 3 + a] * tbi[2];   // (Rw_p^T tb_i)_a
-    }
+    float Rp[9], Ri[9], Rwbi[9], sp[3], tbi[3], delta[3];
+    for (int k = 0; k < 9; ++k) { Rp[k] = c.Rw[p * 9 + k]; Ri[k] = c.R[i * 9 + k]; Rwbi[k] = b.Rwb[i * 9 + k]; }
+    for (int k = 0; k < 3; ++k) { sp[k] = c.s[p * 3 + k]; tbi[k] = b.tb[i * 3 + k]; delta[k] = c.J[i * 3 + k] - c.J[p * 3 + k]; }
+    float tbp[3], Rwbp[9], sbp[3], Jbi[3], Jbp[3];
+    for (int k = 0; k < 3; ++k) { tbp[k] = b.tb[p * 3 + k]; sbp[k] = b.sb[p * 3 + k]; Jbi[k] = b.Jb[i * 3 + k]; Jbp[k] = b.Jb[p * 3 + k]; }
+    for (int k = 0; k < 9; ++k) Rwbp[k] = b.Rwb[p * 9 + k];
+    float RtT[3];
+    for (int a = 0; a < 3; ++a) RtT[a] = Rp[0 * 3 + a] * tbi[0] + Rp[1 * 3 + a] * tbi[1] + Rp[2 * 3 + a] * tbi[2];   // (Rw_p^T tb_i)_a
     for (int r = 0; r < 3; ++r) {
-        b.tb[p * 3 + r] += tbi[r];
-        for (int a = 0; a < 3; ++a) b.Rwb[p * 9 + r * 3 + a] += tbi[r] * sp[a] * delta[a];
+        tbp[r] += tbi[r];
+        for (int a = 0; a < 3; ++a) Rwbp[r * 3 + a] += tbi[r] * sp[a] * delta[a];
     }
     for (int a = 0; a < 3; ++a) {
-        b.sb[p * 3 + a] += RtT[a] * delta[a];
+        sbp[a] += RtT[a] * delta[a];
         const float db = sp[a] * RtT[a];
-        b.Jb[i * 3 + a] += db;
-        b.Jb[p * 3 + a] -= db;
+        Jbi[a] += db;
+        Jbp[a] -= db;
     }
     // Rw_i = Rw_p R_i
-    float tmp[9];
-    mat3_mul_bt(b.Rwb + i * 9, c.R + i * 9, tmp);             // Rwb_i R_i^T
-    for (int k = 0; k < 9; ++k) b.Rwb[p * 9 + k] += tmp[k];
-    mat3_mul_at(Rp, b.Rwb + i * 9, b.Rb + i * 9);             // Rw_p^T Rwb_i
+    float tmp[9], Rbi[9];
+    mat3_mul_bt(Rwbi, Ri, tmp);             // Rwb_i R_i^T
+    for (int k = 0; k < 9; ++k) Rwbp[k] += tmp[k];
+    mat3_mul_at(Rp, Rwbi, Rbi);             // Rw_p^T Rwb_i
+    for (int k = 0; k < 3; ++k) { b.tb[p * 3 + k] = tbp[k]; b.sb[p * 3 + k] = sbp[k]; b.Jb[i * 3 + k] = Jbi[k]; b.Jb[p * 3 + k] = Jbp[k]; }
+    for (int k = 0; k < 9; ++k) { b.Rwb[p * 9 + k] = Rwbp[k]; b.Rb[i * 9 + k] = Rbi[k]; }
 }
 
 // ---------------------------------------------------------------------------

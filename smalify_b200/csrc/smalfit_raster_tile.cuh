@@ -38,11 +38,17 @@ namespace smf {
 constexpr unsigned RT_SKIP = 0xffffffffu;       // plane value: pixel not handled in this pass
 constexpr unsigned RT_LISTED = 0x80000000u;     // plane value: write cursor of a listed pixel (low 31 bits)
 constexpr int RT_SELCAP = 256;                  // keys of one pixel held in registers
+#ifdef RT_MIDCAP_OFF
+constexpr int RT_MIDCAP = RT_SELCAP;
+#else
+constexpr int RT_MIDCAP = 512;                  // lists up to this length are narrowed in shared memory (a whole plane), longer ones in global memory
+#endif
 constexpr int RT_PIX = TILE_W * TILE_H;
 constexpr unsigned char RT_CLS_DIRECT = 0, RT_CLS_LISTED = 1, RT_CLS_IDLE = 2;
 constexpr int RT_MAXCHUNK = 512;                // tile lists up to 8192 faces are split by cost, longer ones evenly
 constexpr int RT_FAIR = 4;                      // a hand-out item holds at most 1/RT_FAIR of a CTA's fair share of the pairs
 constexpr unsigned RT_FACE_COST = 16u;          // per-face overhead of the sweep, in pair evaluations
+constexpr int RT_MIN_ITEM = 4096;               // no tile is cut into bands of fewer pairs than this (an item has fixed costs)
 // (interpolated pivots in the K-th order statistic search were measured: +2 % on the kernel -- the depths of one pixel's
 //  candidates cluster on the front and back surfaces, bisection on the key bits with an exact-split exit does better)
 
@@ -61,6 +67,7 @@ struct RtSmem {
     unsigned cost_total;
     int item;
     unsigned n_active, total, p2_next;
+    unsigned n_mid;                      // listed pixels with RT_SELCAP < c <= RT_MIDCAP: kept at the back of active[]
     int t_f, t_tile, t_len;              // current item (kept here across the sweep, which needs the registers)
     unsigned t_off;
     unsigned n_capped, n_big;
@@ -76,14 +83,22 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
     return pol;
 }
 __device__ __forceinline__ void st_list_entry(uint2* p, unsigned a, unsigned b, unsigned long long pol) {
+#ifdef RT_NO_L2HINTS
+    (void)pol; *p = make_uint2(a, b);
+#else
     asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(a), "r"(b), "l"(pol) : "memory");
+#endif
 }
 // the slot a plane cursor points at: RT_LISTED | entry index (< 2^29) -> byte offset in 32 bits (the flag shifts out)
 __device__ __forceinline__ uint2* list_slot(uint2* list, unsigned cursor) {
     return reinterpret_cast<uint2*>(reinterpret_cast<char*>(list) + (size_t)(cursor << 3));
 }
 __device__ __forceinline__ void l2_discard_line(const void* p) {
+#if !defined(RT_NO_L2HINTS) && !defined(RT_NO_DISCARD)
     asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+#else
+    (void)p;
+#endif
 }
 constexpr int RT_LIST_ALIGN = 16;               // entries per 128-byte line
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
@@ -402,7 +417,11 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                     const unsigned npx = (((rect >> 8) & 0xffu) - (rect & 0xffu) + 1u) * (unsigned)max(rows, 0);
                     // the sweep takes whole 32-lane steps: one pixel per lane, or -- rectangles of RT_PACK_MIN pixels and
                     // more -- a pixel pair per lane at about 1.3x the cost of a step
+#ifdef RT_OLD_COST
+                    if (false) {
+#else
                     if (npx >= (unsigned)RT_PACK_MIN) {
+#endif
                         const unsigned wdp = (((rect >> 8) & 0xffu) - (rect & 0xffu) + 2u) >> 1;
                         cost = ((wdp * (unsigned)rows + 31u) >> 5) * 42u + RT_FACE_COST;
                     } else {
@@ -488,7 +507,7 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
                 if (lane == 31) sm.warp_tot[wid] = incl;
-                if (threadIdx.x == 0) { sm.n_active = 0u; sm.p2_next = 0u; }
+                if (threadIdx.x == 0) { sm.n_active = 0u; sm.p2_next = 0u; sm.n_mid = 0u; }
                 __syncthreads();
                 unsigned base = 0u, total = 0u;
 #pragma unroll
@@ -516,8 +535,13 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                             cur += cw;
                         }
                         if (act) {
-                            const unsigned a = atomicAdd(&sm.n_active, 1u);
-                            sm.active[a] = (unsigned short)px;
+                            if (c > (unsigned)RT_SELCAP && c <= (unsigned)RT_MIDCAP) {
+                                const unsigned a = atomicAdd(&sm.n_mid, 1u);
+                                sm.active[RT_PIX - 1 - a] = (unsigned short)px;
+                            } else {
+                                const unsigned a = atomicAdd(&sm.n_active, 1u);
+                                sm.active[a] = (unsigned short)px;
+                            }
                             sm.list_off[px] = o - win_lo;
                             sm.list_cnt[px] = (unsigned short)c;
                         }
@@ -578,19 +602,22 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
             }
             __syncthreads();
 
-            // ---- P2: ... and every warp's plane becomes its two staging buffers for the listed pixels of this pass:
-            //      one warp per pixel, the next pixel's list streaming in (cp.async) while this one is selected
+            // ---- P2: ... and every warp's plane becomes staging space for the listed pixels of this pass: one warp per
+            //      pixel.  Lists of up to RT_SELCAP entries use half a plane each, the next pixel's list streaming in
+            //      (cp.async) while this one is selected; lists of up to RT_MIDCAP entries take the whole plane and are
+            //      narrowed there; longer ones are narrowed in global memory.
             {
-                const unsigned na = sm.n_active;
+                const unsigned n_short = sm.n_active, na = n_short + sm.n_mid;        // mid-length lists come last
                 const uint2* list = ts.list + (size_t)blockIdx.x * ts.list_stride;
                 unsigned* scratch = reinterpret_cast<unsigned*>(sm.stage[wid][0]);     // the TMA stage is idle here
                 uint2* stg = reinterpret_cast<uint2*>(plane);                          // 2 x RT_SELCAP entries
-                auto stage_px = [&](unsigned a, int buf) {
-                    const int px = (int)sm.active[a];
+                auto pixel_of = [&](unsigned a) { return (int)sm.active[a < n_short ? a : (RT_PIX - 1) - (a - n_short)]; };
+                auto stage_px = [&](unsigned a, uint2* dst, int cap) {
+                    const int px = pixel_of(a);
                     const int c = (int)sm.list_cnt[px];
-                    if (c <= RT_SELCAP) {
+                    if (c <= cap) {
                         const uint2* src = list + sm.list_off[px];
-                        for (int ch = lane; ch * 2 < c; ch += 32) cp_async16(stg + buf * RT_SELCAP + ch * 2, src + ch * 2);
+                        for (int ch = lane; ch * 2 < c; ch += 32) cp_async16(dst + ch * 2, src + ch * 2);
                     }
                 };
                 // pixels are drawn from a shared counter (lists differ a lot in length; the results do not depend on
@@ -598,21 +625,29 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                 auto draw = [&]() { unsigned a = 0u; if (lane == 0) a = atomicAdd(&sm.p2_next, 1u); return __shfl_sync(0xffffffffu, a, 0); };
                 int buf = 0;
                 unsigned a = draw();
-                if (a < na) stage_px(a, 0);
+                if (a < n_short) stage_px(a, stg, RT_SELCAP);
                 cp_async_commit();
                 while (a < na) {
                     const unsigned a_next = draw();
-                    if (a_next < na) stage_px(a_next, buf ^ 1);
-                    cp_async_commit();
-                    cp_async_wait<1>();              // everything but the group just committed has landed
+                    const bool mid = a >= n_short;
+                    if (mid) {
+                        stage_px(a, stg, RT_MIDCAP);         // (nothing else is in flight: mid-length pixels are never prefetched)
+                        cp_async_commit();
+                        cp_async_wait<0>();
+                    } else {
+                        if (a_next < n_short) stage_px(a_next, stg + (buf ^ 1) * RT_SELCAP, RT_SELCAP);
+                        cp_async_commit();
+                        cp_async_wait<1>();              // everything but the group just committed has landed
+                    }
                     __syncwarp();
-                    const int px = (int)sm.active[a];
+                    const int px = pixel_of(a);
                     const int c = (int)sm.list_cnt[px];
+                    const uint2* src = list + sm.list_off[px];
                     unsigned tk, tf = 0xffffu;
                     int tslot;
                     bool capped;
-                    const float P = rt_select(list + sm.list_off[px], stg + buf * RT_SELCAP, c, lane, scratch, tk, tslot, capped);
-                    for (int ln = lane * RT_LIST_ALIGN; ln < c; ln += 32 * RT_LIST_ALIGN) l2_discard_line(list + sm.list_off[px] + ln);   // dead from here on
+                    const float P = rt_select(mid ? stg : src, mid ? stg : stg + buf * RT_SELCAP, c, lane, scratch, tk, tslot, capped);
+                    for (int ln = lane * RT_LIST_ALIGN; ln < c; ln += 32 * RT_LIST_ALIGN) l2_discard_line(src + ln);   // dead from here on
                     if (tslot >= 0)
                         tf = rt_slot_to_fid(w.tile_pool + (size_t)(frame0 + sm.t_f) * w.pool_cap + sm.t_off, sm.t_len, px % TILE_W, px / TILE_W, tslot, lane);
                     __syncwarp();                    // every lane is done with this buffer (it is refilled two pixels on)
@@ -708,7 +743,8 @@ __global__ void __launch_bounds__(1024) build_items_kernel(Workspace w, TileScra
         unsigned long long a = 0ull;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += red[i];
         const unsigned long long cmax = a / (unsigned long long)((ts.fair > 0 ? ts.fair : RT_FAIR) * n_ctas);
-        s_cmax = ts.split_len > 0 ? (unsigned)ts.split_len : (unsigned)(cmax < 4096ull ? 4096ull : cmax);
+        const unsigned long long floor_ = (unsigned long long)(ts.min_item > 0 ? ts.min_item : RT_MIN_ITEM);
+        s_cmax = ts.split_len > 0 ? (unsigned)ts.split_len : (unsigned)(cmax < floor_ ? floor_ : cmax);
     }
     __syncthreads();
     const unsigned cmax = s_cmax;

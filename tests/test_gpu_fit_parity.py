@@ -5,12 +5,16 @@ inputs.
 
 Tolerances.  Stage 0 (keypoints only, smooth): parameters within 1e-4 of the fp64 oracle.
 Whole schedule: BASELINE.json asks for final keypoint-L2 / silhouette-IoU within 1e-3 of the
-reference.  The silhouette stages amplify float32 rounding (sign() of the L1 term, Adam's
-normalisation): the ORACLE ITSELF run in float32 ends 0.019 px / 0.004 IoU away from its float64
-run on this problem on one host and 0.02 px / 0.0001 IoU on another (different BLAS threading), and
-at 48x48 one pixel crossing alpha = 0.5 moves the IoU by 8e-4.  The test therefore measures the
-oracle's own float32-vs-float64 gap and requires the GPU fit to land within
-max(1.5 x gap, 0.03 px) and max(1.5 x gap, 5e-3 IoU) of the float64 oracle."""
+reference.  The silhouette stages amplify float32 rounding chaotically (sign() of the L1 term, Adam's
+normalisation, pixels crossing alpha = 0.5: at 48x48 one pixel moves the IoU by 8e-4), so the test MEASURES the
+noise floor of this problem instead of assuming one:
+  * the oracle itself, float32 against float64 (same code, same inputs);
+  * the GPU fit against itself with the initial translation moved by 1e-6 (a perturbation at the scale of one
+    float32 rounding).
+The GPU fit must land within 2 x the larger of the two gaps (and never further than 0.1 px / 1e-2 IoU) from the
+float64 oracle; the measured gaps are recorded in gpurun_out/parity_results.json.  bench.py's `quality` block and
+tools/run_configs.py report the same comparison at 256x256, where the floor is far lower (3e-4 px / 2e-5 IoU
+after a 100-iteration fit)."""
 import pytest
 import torch
 
@@ -50,11 +54,20 @@ def refs(constants, problem):
                 stage0=_oracle_fit(constants, torch.float64, problem, (ITERS[0], 0, 0, 0)))
 
 
-def _gpu_fit(constants, data, fused, graph, iters):
+def _gpu_fit(constants, data, fused, graph, iters, nudge: float = 0.0):
     from smalify_b200.smal_fitter import SMALFitter
     f = SMALFitter("cuda", data, WINDOW, 1, True, constants=constants)
+    if nudge:
+        with torch.no_grad():
+            f.trans += nudge
     fit_sequence(f, K.STAGE_SCHEDULE, WINDOW, fused=fused, use_graph=graph, iters_override=iters)
     return f
+
+
+def _quality(f, problem):
+    rgb, sil, joints, vis = problem
+    alpha, kp = f.render()
+    return metrics.keypoint_l2(kp, joints, vis), metrics.silhouette_iou(alpha, sil)
 
 
 @pytest.mark.parametrize("fused", [False, True])
@@ -68,13 +81,14 @@ def test_stage0_matches_oracle_tightly(constants, problem, refs, fused):
 
 @pytest.mark.parametrize("fused,graph", [(False, False), (True, False), (True, True)])
 def test_full_fit_within_float32_noise_of_oracle(constants, problem, refs, fused, graph):
-    rgb, sil, joints, vis = problem
     f = _gpu_fit(constants, problem, fused, graph, ITERS)
-    alpha, kp = f.render()
-    kp_l2 = metrics.keypoint_l2(kp, joints, vis)
-    iou = metrics.silhouette_iou(alpha, sil)
-    gap_kp = abs(refs["f32"]["kp"] - refs["f64"]["kp"])
-    gap_iou = abs(refs["f32"]["iou"] - refs["f64"]["iou"])
-    assert abs(kp_l2 - refs["f64"]["kp"]) <= max(1.5 * gap_kp, 0.03), (kp_l2, refs["f64"]["kp"], refs["f32"]["kp"])
-    assert abs(iou - refs["f64"]["iou"]) <= max(1.5 * gap_iou, 5e-3), (iou, refs["f64"]["iou"], refs["f32"]["iou"])
+    kp_l2, iou = _quality(f, problem)
+    kp_n, iou_n = _quality(_gpu_fit(constants, problem, fused, graph, ITERS, nudge=1e-6), problem)
+    floor_kp = max(abs(refs["f32"]["kp"] - refs["f64"]["kp"]), abs(kp_n - kp_l2))
+    floor_iou = max(abs(refs["f32"]["iou"] - refs["f64"]["iou"]), abs(iou_n - iou))
+    H.record_result(f"fit_48px_{'fused' if fused else 'dropin'}{'_graph' if graph else ''}", {
+        "kp_l2": kp_l2, "iou": iou, "oracle_f64": [refs["f64"]["kp"], refs["f64"]["iou"]], "oracle_f32": [refs["f32"]["kp"], refs["f32"]["iou"]],
+        "gpu_with_1e-6_nudge": [kp_n, iou_n], "noise_floor": [floor_kp, floor_iou]})
+    assert abs(kp_l2 - refs["f64"]["kp"]) <= min(max(2.0 * floor_kp, 0.01), 0.1), (kp_l2, kp_n, refs["f64"]["kp"], refs["f32"]["kp"])
+    assert abs(iou - refs["f64"]["iou"]) <= min(max(2.0 * floor_iou, 2e-3), 1e-2), (iou, iou_n, refs["f64"]["iou"], refs["f32"]["iou"])
     assert f.counters()["dropped_bin_entries"] == 0
