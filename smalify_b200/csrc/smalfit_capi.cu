@@ -290,6 +290,7 @@ int smalfit_create_ex(const smalfit_model_t* md, int device, int max_frames, int
         h->ts.item_next = P.alloc<unsigned>(2, true);
         h->ts.n_items = h->ts.item_next + 1;
         h->ts.items = P.alloc<unsigned>(N * tiles * 8 + 8);
+        h->ts.band_idx = P.alloc<unsigned short>((size_t)h->tile_ctas * RT_WARPS * RT_BAND_MAX);
         const char* e_nsub = getenv("SMALFIT_RT_NSUB");         // tuning knobs for measurements
         const char* e_split = getenv("SMALFIT_RT_SPLITLEN");
         h->ts.nsub = e_nsub ? atoi(e_nsub) : 0;

@@ -21,6 +21,7 @@ constexpr int RT_CTAS_PER_SM = RT_CTAS;
 constexpr int RT_PITCH = TILE_W + 1;        // row pitch of a per-warp pixel plane (bank-conflict free in both directions)
 constexpr int RT_PLANE = RT_PITCH * (TILE_H + 1) + 3;      // words per plane (33 x 33 corner grid of the box counts)
 constexpr int RT_BLK = 16;                  // prepared faces per TMA block
+constexpr int RT_BAND_MAX = 2048;           // faces of one warp's range whose positions a band item compacts (longer ranges: streamed whole)
 constexpr int MAX_TILES = 1024;             // 32x32 tiles per frame (image side <= 1024)
 constexpr int MAX_LEVELS = 16;
 constexpr int SKIN_CHUNK = 96, MAX_SKIN_CHUNKS = 192;
@@ -131,8 +132,9 @@ struct TileScratch {        // tile rasteriser: per resident CTA
     unsigned* item_next;    // [1] next item to hand out
     unsigned* n_items;      // [1]
     unsigned* items;        // [N * tiles * 8] frame << 15 | tile << 5 | band << 2 | log2(bands)   (build_items_kernel)
+    unsigned short* band_idx;   // [n_ctas][RT_WARPS][RT_BAND_MAX] band items: list positions of the faces that reach the band
     int nsub;               // > 0: force this many bands for every list longer than split_len (measurements)
-    int fair;               // a band's list is at most 1/fair of a CTA's fair share of the launch (0: default 3)
+    int fair;               // > 0: overrides RT_FAIR (and lifts RT_MAX_ITEM)
     int split_len;          // > 0: overrides the list length above which a tile is cut into bands
     int min_item;           // > 0: overrides RT_MIN_ITEM
 };

@@ -46,9 +46,13 @@ constexpr int RT_MIDCAP = 512;                  // lists up to this length are n
 constexpr int RT_PIX = TILE_W * TILE_H;
 constexpr unsigned char RT_CLS_DIRECT = 0, RT_CLS_LISTED = 1, RT_CLS_IDLE = 2;
 constexpr int RT_MAXCHUNK = 512;                // tile lists up to 8192 faces are split by cost, longer ones evenly
-constexpr int RT_FAIR = 4;                      // a hand-out item holds at most 1/RT_FAIR of a CTA's fair share of the pairs
+constexpr int RT_FAIR = 2;                      // a hand-out item holds at most 1/RT_FAIR of a CTA's fair share of the pairs ...
+constexpr int RT_MAX_ITEM = 64000;              // ... but never more pairs than this: the fragment lists of the items in flight
+                                                // (n_ctas x ~0.6 x 8 B per pair) should fit the 126 MB L2 (measured at 128 frames:
+                                                // 61 k pairs per item 1.05 ms / 1.06 GB of DRAM traffic, 122 k: 1.14 ms / 1.67 GB)
 constexpr unsigned RT_FACE_COST = 16u;          // per-face overhead of the sweep, in pair evaluations
-constexpr int RT_MIN_ITEM = 4096;               // no tile is cut into bands of fewer pairs than this (an item has fixed costs)
+constexpr int RT_MIN_ITEM = 16000;              // ... and no tile is cut into bands of fewer pairs than this (an item has fixed costs;
+                                                // measured best at 16 / 32 / 64 frames per GPU: 16 k / 32 k / 48 k pairs)
 // (interpolated pivots in the K-th order statistic search were measured: +2 % on the kernel -- the depths of one pixel's
 //  candidates cluster on the front and back surfaces, bisection on the key bits with an exact-split exit does better)
 
@@ -71,6 +75,7 @@ struct RtSmem {
     int t_f, t_tile, t_len;              // current item (kept here across the sweep, which needs the registers)
     unsigned t_off;
     unsigned n_capped, n_big;
+    int ncomp[RT_WARPS];                 // band items: faces of the warp's range that reach the band (-1: range not compacted)
 };
 
 // L2 residency of the fragment lists.  A list is written in P1, read once in P2 and dead afterwards; without
@@ -463,29 +468,56 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
 
         for (unsigned round = 0;; ++round) {
             // ---- P0: candidates per (warp, pixel) = integral of the rectangles' corner grid
-            for (int i = lane; i < RT_PLANE; i += 32) plane[i] = 0u;
+            // (only the rows of the item's band, plus the closing corner row, are ever read back)
+            for (int i = b0 * RT_PITCH + lane; i < (b1 + 1) * RT_PITCH + 1; i += 32) plane[i] = 0u;
             __syncwarp();
-            for (int e = lo + lane; e < hi; e += 32) {
-                const unsigned rect = pool[e].z;
-                const int c0 = (int)(rect & 0xffu), c1 = (int)((rect >> 8) & 0xffu);
-                const int r0 = max((int)((rect >> 16) & 0xffu), b0), r1 = min((int)(rect >> 24), b1 - 1);
-                if (r0 > r1) continue;
-                atomicAdd(&plane[r0 * RT_PITCH + c0], 1u);
-                atomicAdd(&plane[r0 * RT_PITCH + c1 + 1], 0xffffffffu);
-                atomicAdd(&plane[(r1 + 1) * RT_PITCH + c0], 0xffffffffu);
-                atomicAdd(&plane[(r1 + 1) * RT_PITCH + c1 + 1], 1u);
+            // A band item only sweeps the faces of the tile list that reach its rows: their positions are compacted here
+            // (in list order) and P1 gathers those records instead of streaming the whole list -- a heavy tile cut into
+            // 8 bands would otherwise visit every face 8 times.
+#ifdef RT_NO_BAND_COMPACT
+            const bool compact = false;
+#else
+            const bool compact = (bh < TILE_H) && (hi - lo <= RT_BAND_MAX);
+#endif
+            unsigned short* bidx = ts.band_idx + ((size_t)blockIdx.x * RT_WARPS + wid) * RT_BAND_MAX;
+            {
+                int nc = 0;
+                for (int base = lo; base < hi; base += 32) {
+                    const int e = base + lane;
+                    bool ov = false;
+                    if (e < hi) {
+                        const unsigned rect = pool[e].z;
+                        const int c0 = (int)(rect & 0xffu), c1 = (int)((rect >> 8) & 0xffu);
+                        const int r0 = max((int)((rect >> 16) & 0xffu), b0), r1 = min((int)(rect >> 24), b1 - 1);
+                        ov = r0 <= r1;
+                        if (ov) {
+                            atomicAdd(&plane[r0 * RT_PITCH + c0], 1u);
+                            atomicAdd(&plane[r0 * RT_PITCH + c1 + 1], 0xffffffffu);
+                            atomicAdd(&plane[(r1 + 1) * RT_PITCH + c0], 0xffffffffu);
+                            atomicAdd(&plane[(r1 + 1) * RT_PITCH + c1 + 1], 1u);
+                        }
+                    }
+                    if (compact) {
+                        const unsigned bal = __ballot_sync(0xffffffffu, ov);
+                        if (ov) bidx[nc + __popc(bal & lanemask_lt())] = (unsigned short)(e - lo);
+                        nc += __popc(bal);
+                    }
+                }
+                if (lane == 0) sm.ncomp[wid] = compact ? nc : -1;
             }
             __syncwarp();
             {
                 unsigned run = 0u;
-#pragma unroll 8
-                for (int r = 0; r < TILE_H; ++r) { run += plane[r * RT_PITCH + lane]; plane[r * RT_PITCH + lane] = run; }
+#pragma unroll 4
+                for (int r = b0; r < b1; ++r) { run += plane[r * RT_PITCH + lane]; plane[r * RT_PITCH + lane] = run; }
             }
             __syncwarp();
             {
                 unsigned run = 0u;
+                if (lane >= b0 && lane < b1) {
 #pragma unroll 8
-                for (int c = 0; c < TILE_W; ++c) { run += plane[lane * RT_PITCH + c]; plane[lane * RT_PITCH + c] = run; }
+                    for (int c = 0; c < TILE_W; ++c) { run += plane[lane * RT_PITCH + c]; plane[lane * RT_PITCH + c] = run; }
+                }
             }
             __syncthreads();
 
@@ -496,10 +528,13 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                 unsigned mysum = 0u;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int idx = (wid + RT_WARPS * k) * RT_PITCH + lane;
+                    const int row = wid + RT_WARPS * k;
+                    const int idx = row * RT_PITCH + lane;
                     unsigned c = 0u;
+                    if (row >= b0 && row < b1) {             // (rows outside the item's band: nothing to do)
 #pragma unroll
-                    for (int q = 0; q < RT_WARPS; ++q) c += sm.plane[q][idx];
+                        for (int q = 0; q < RT_WARPS; ++q) c += sm.plane[q][idx];
+                    }
                     cnt4[k] = c;
                     if (c > (unsigned)RAST_K) mysum += (c + RT_LIST_ALIGN - 1) & ~(unsigned)(RT_LIST_ALIGN - 1);     // lists start on 128-byte lines
                 }
@@ -518,6 +553,7 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int row = wid + RT_WARPS * k;
+                    if (row < b0 || row >= b1) continue;
                     const int idx = row * RT_PITCH + lane, px = row * TILE_W + lane;
                     const unsigned c = cnt4[k];
                     unsigned char cls;
@@ -562,30 +598,53 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                 const float4* recs = w.tile_rec + ((size_t)fr * w.pool_cap + off) * 4;
                 uint2* list = ts.list;             // cursors carry the CTA's offset
                 const float inv_s = 1.f / (float)w.S;
-                const int nblk = (hi - lo + RT_BLK - 1) / RT_BLK;
+                const int ncomp = sm.ncomp[wid];
+                const bool gather = ncomp >= 0;          // band item: the compacted faces are gathered with cp.async
+                const int nface = gather ? ncomp : hi - lo;
+                const int nblk = (nface + RT_BLK - 1) / RT_BLK;
                 const bool skips = (round != 0u) || (sm.total > (unsigned)ts.list_cap);       // otherwise no plane holds RT_SKIP
                 const unsigned long long pol = l2_policy_evict_last();
-                if (nblk > 0 && lane == 0) {
+                const unsigned short* bidx = ts.band_idx + ((size_t)blockIdx.x * RT_WARPS + wid) * RT_BAND_MAX;
+                // block b of RT_BLK prepared faces -> stage buffer b & 1: one bulk copy (contiguous part of the list), or
+                // two 16-byte cp.async per lane (lane pair 2j, 2j + 1 fetches the two halves of compacted face j)
+                auto fetch = [&](int b) {
+                    if (gather) {
+                        const int k = b * RT_BLK + (lane >> 1);
+                        if (k < nface) {
+                            const float4* src = recs + ((size_t)lo + bidx[k]) * 4 + (lane & 1) * 2;
+                            float4* dst = sm.stage[wid][b & 1] + (lane >> 1) * 4 + (lane & 1) * 2;
+                            cp_async16(dst, src);
+                            cp_async16(dst + 1, src + 1);
+                        }
+                        cp_async_commit();
+                    } else if (lane == 0) {
+                        const int e0 = lo + b * RT_BLK;
+                        const unsigned bytes = (unsigned)min(RT_BLK, hi - e0) * 64u;
+                        mbar_expect_tx(&sm.bar[wid][b & 1], bytes);
+                        tma_load_1d(sm.stage[wid][b & 1], recs + (size_t)e0 * 4, bytes, &sm.bar[wid][b & 1]);
+                    }
+                };
+                if (nblk > 0) {
                     // the stage doubles as P2's scratch (generic-proxy writes): order them before the bulk copies
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    const unsigned bytes = (unsigned)min(RT_BLK, hi - lo) * 64u;
-                    mbar_expect_tx(&sm.bar[wid][0], bytes);
-                    tma_load_1d(sm.stage[wid][0], recs + (size_t)lo * 4, bytes, &sm.bar[wid][0]);
+                    if (!gather && lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    fetch(0);
                 }
                 for (int b = 0; b < nblk; ++b) {
-                    const int e0 = lo + b * RT_BLK;
-                    if (b + 1 < nblk && lane == 0) {
-                        const unsigned bytes = (unsigned)min(RT_BLK, hi - (e0 + RT_BLK)) * 64u;
-                        mbar_expect_tx(&sm.bar[wid][(b + 1) & 1], bytes);
-                        tma_load_1d(sm.stage[wid][(b + 1) & 1], recs + (size_t)(e0 + RT_BLK) * 4, bytes, &sm.bar[wid][(b + 1) & 1]);
+                    if (b + 1 < nblk) fetch(b + 1);
+                    else if (gather) cp_async_commit();
+                    if (gather) {
+                        cp_async_wait<1>();              // everything but the group just committed has landed
+                        __syncwarp();
+                    } else {
+                        mbar_wait(&sm.bar[wid][b & 1], (phase >> (b & 1)) & 1u);
+                        phase ^= 1u << (b & 1);
                     }
-                    mbar_wait(&sm.bar[wid][b & 1], (phase >> (b & 1)) & 1u);
-                    phase ^= 1u << (b & 1);
-                    const int nrec = min(RT_BLK, hi - e0);
+                    const int nrec = min(RT_BLK, nface - b * RT_BLK);
                     const float4* st = sm.stage[wid][b & 1];
                     if (skips) { for (int j = 0; j < nrec; ++j) rt_sweep_face<true>(st + j * 4, plane, list, lane, x0, y0, inv_s, b0, b1, pol); }
                     else       { for (int j = 0; j < nrec; ++j) rt_sweep_face<false>(st + j * 4, plane, list, lane, x0, y0, inv_s, b0, b1, pol); }
                 }
+                if (gather) cp_async_wait<0>();
             }
             __syncthreads();
 
@@ -594,7 +653,7 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
             for (int k = 0; k < 4; ++k) {
                 const int row = wid + RT_WARPS * k;
                 const int idx = row * RT_PITCH + lane;
-                if (sm.cls[row * TILE_W + lane] != RT_CLS_DIRECT) continue;
+                if (row < b0 || row >= b1 || sm.cls[row * TILE_W + lane] != RT_CLS_DIRECT) continue;
                 float P = __uint_as_float(sm.plane[0][idx]);
 #pragma unroll
                 for (int q = 1; q < RT_WARPS; ++q) P *= __uint_as_float(sm.plane[q][idx]);
@@ -674,8 +733,9 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
                 for (int k = 0; k < 4; ++k) {
                     const int row = wid + RT_WARPS * k;
                     const int px = row * TILE_W + lane;
+                    if (row < b0 || row >= b1) continue;
                     const unsigned cls = sm.cls[px];
-                    if (cls == RT_CLS_IDLE || row < b0 || row >= b1) continue;
+                    if (cls == RT_CLS_IDLE) continue;
                     const float P = sm.pl[px];
                     unsigned tk = 0xffffffffu, tf = 0xffffu;
                     if (cls == RT_CLS_LISTED) { tk = sm.list_off[px]; tf = sm.list_cnt[px]; }
@@ -744,7 +804,9 @@ __global__ void __launch_bounds__(1024) build_items_kernel(Workspace w, TileScra
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += red[i];
         const unsigned long long cmax = a / (unsigned long long)((ts.fair > 0 ? ts.fair : RT_FAIR) * n_ctas);
         const unsigned long long floor_ = (unsigned long long)(ts.min_item > 0 ? ts.min_item : RT_MIN_ITEM);
-        s_cmax = ts.split_len > 0 ? (unsigned)ts.split_len : (unsigned)(cmax < floor_ ? floor_ : cmax);
+        const unsigned long long ceil_ = (unsigned long long)(ts.fair > 0 ? 1u << 30 : RT_MAX_ITEM);      // (an explicit fair share is taken literally)
+        const unsigned long long cm = cmax < floor_ ? floor_ : (cmax > ceil_ ? ceil_ : cmax);
+        s_cmax = ts.split_len > 0 ? (unsigned)ts.split_len : (unsigned)cm;
     }
     __syncthreads();
     const unsigned cmax = s_cmax;

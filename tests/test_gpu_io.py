@@ -90,3 +90,41 @@ def test_script_main_and_generate_video(constants, stanford, tmp_path):
     # the reloaded parameters are the exported ones: same collage up to the png quantisation
     ref = cv2.imread(os.path.join(d, "st10_ep0.png"))
     assert float(np.mean(np.abs(img.astype(np.int32) - ref.astype(np.int32)) > 2)) < 0.01
+
+
+def test_checkpoint_round_trip_with_one_shape_per_frame(constants, oracle64, tmp_path):
+    """Every frame has its own shape (BASELINE config 4): the per-frame pickle holds that frame's (20,) betas and
+    (6,) log scales (the reference's layout, smal_fitter.py:213-219), load_checkpoint restores them per frame and
+    writes into the existing parameter storage -- a FusedFit created before keeps working on the loaded values."""
+    import pickle
+    from smalify_b200 import synthetic
+    from smalify_b200.smal_fitter import FusedFit, SMALFitter
+    S, n = 64, 3
+    data, gt = synthetic.make_subsequence(constants, n, range(n), S, H.oracle_renderer(oracle64, S), seed=2)
+    f = SMALFitter("cuda", data, 1, 1, True, constants=constants, per_frame_shapes=True)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        f.betas += 0.1 * torch.randn(n, 20, generator=g).to(f.device)
+        f.log_beta_scales += 0.05 * torch.randn(n, 6, generator=g).to(f.device)
+        f.trans += 0.02 * torch.randn(n, 3, generator=g).to(f.device)
+    for i in range(n):
+        d = f.export_parameters(i)
+        assert d["betas"].shape == (20,) and d["log_betascale"].shape == (6,) and d["joint_rotations"].shape == (34, 3)
+        os.makedirs(tmp_path / "{0:04}".format(i), exist_ok=True)
+        with open(tmp_path / "{0:04}".format(i) / "st10_ep0.pkl", "wb") as fh:
+            pickle.dump(d, fh)
+    h = SMALFitter("cuda", data, 1, 1, True, constants=constants, per_frame_shapes=True)
+    loop = FusedFit(h, 1)                                  # re-points the parameters at its flat buffer
+    ptrs = [p.data_ptr() for p in h.parameters()]
+    h.load_checkpoint(str(tmp_path), "st10_ep0")
+    assert ptrs == [p.data_ptr() for p in h.parameters()]
+    for k in ("betas", "log_beta_scales", "global_rotation", "joint_rotations", "trans"):
+        assert torch.equal(getattr(h, k).detach(), getattr(f, k).detach()), k
+    # the kernels see the loaded values: same loss from both fitters, and the fused loop steps without a fault
+    w = K.STAGE_SCHEDULE[1][:6]
+    la, _ = f(list(range(n)), w, 1)
+    lb, _ = h(list(range(n)), w, 1)
+    assert float(la) == float(lb)
+    loop.step(w, 0.0, 1e-3)
+    torch.cuda.synchronize()
+    h.check_faults()
