@@ -287,8 +287,9 @@ int smalfit_create_ex(const smalfit_model_t* md, int device, int max_frames, int
             return fail(nullptr, SMALFIT_EINVAL, "smalfit_create: fragment-list scratch too large for 29-bit cursors (SMALFIT_RT_LISTCAP)");
         }
         h->ts.list = P.alloc<uint2>((size_t)h->tile_ctas * h->ts.list_stride);
-        h->ts.item_next = P.alloc<unsigned>(2, true);
+        h->ts.item_next = P.alloc<unsigned>(4, true);
         h->ts.n_items = h->ts.item_next + 1;
+        h->ts.front_ticket = h->ts.item_next + 2;
         h->ts.items = P.alloc<unsigned>(N * tiles * 8 + 8);
         h->ts.band_idx = P.alloc<unsigned short>((size_t)h->tile_ctas * RT_WARPS * RT_BAND_MAX);
         const char* e_nsub = getenv("SMALFIT_RT_NSUB");         // tuning knobs for measurements
@@ -447,13 +448,13 @@ static int run_forward(smalfit_t h, const Params& p, int frame0, int n, Weights 
     h->mark(0, st);
     launch_shape_forward(h->m, h->w, p, frame0, n, st);
     // frame_forward + binning of a frame in one launch over a 4-CTA cluster (profile phases 0 and 1 are reported together)
-    launch_frame_front(h->m, h->w, p, frame0, n, wt, verts_out, raster, st);
+    launch_frame_front(h->m, h->w, h->ts, p, frame0, n, wt, verts_out, raster, h->tile_ctas, st);
     h->n_launches += 2;
     h->mark(1, st);
     if (raster) {
         h->mark(2, st);
         launch_raster_tile_forward(h->m, h->w, h->ts, frame0, n, wt, alpha_out, h->tile_ctas, st);
-        h->n_launches += 2;
+        h->n_launches += 1;
     } else {
         h->mark(2, st);
     }

@@ -42,6 +42,30 @@ __constant__ SkeletonConst c_sk;
 void upload_skeleton(const SkeletonConst& sk) { cudaMemcpyToSymbol(c_sk, &sk, sizeof(SkeletonConst)); }
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch: the kernels of one step are launched with the programmatic-stream-serialization
+// attribute, so a kernel's CTAs are scheduled while its predecessor drains; each begins with griddepcontrol.wait
+// (= cudaGridDependencySynchronize: the predecessor has completed and its writes are visible), before it reads or
+// writes anything.  This hides the launch bubble between the 8 kernels of a step (it matters with few frames per GPU);
+// SMALFIT_NO_PDL=1 launches them plainly (the wait is then a no-op).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+static bool pdl_enabled() {
+    static const bool on = getenv("SMALFIT_NO_PDL") == nullptr;
+    return on;
+}
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -80,6 +104,7 @@ __device__ float block_sum(float v, float* red /* >= 33 floats */) {
 // ---------------------------------------------------------------------------
 // (shared shape: parameter slot 0, workspace slot w.slot0; one shape per frame: both = the absolute frame id)
 __global__ void __launch_bounds__(256) shape_forward_kernel(ModelDev m, Workspace w, Params p, int frame0) {
+    grid_dep_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int pslot = (w.n_shapes == 1) ? 0 : frame0 + blockIdx.y;
     const int slot = (w.n_shapes == 1) ? w.slot0 : pslot;
@@ -96,7 +121,7 @@ __global__ void __launch_bounds__(256) shape_forward_kernel(ModelDev m, Workspac
 
 void launch_shape_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n, cudaStream_t st) {
     dim3 grid((m.V * 3 + 255) / 256, w.n_shapes == 1 ? 1 : n);
-    shape_forward_kernel<<<grid, 256, 0, st>>>(m, w, p, frame0);
+    launch_pdl(shape_forward_kernel, grid, dim3(256), 0, st, m, w, p, frame0);
 }
 
 // ---------------------------------------------------------------------------
@@ -189,6 +214,64 @@ __device__ __forceinline__ void bin_segment(const ModelDev& m, int seg_id, int& 
     f_hi = min(f_lo + seg, m.Fp);
 }
 
+// Hand-out list of the tile rasteriser: every (frame, tile) becomes 1, 2, 4 or 8 items (bands of rows) so that no
+// item holds more than about 1/fair of a CTA's fair share of the launch's (pixel, face) pairs (bin_faces counts them
+// per tile), ordered by decreasing pairs per item (counting sort into 256 classes; the order inside a class does not
+// matter: items are independent).  Also resets the hand-out counter.  One CTA (the last one of frame_front to finish).
+constexpr int RT_ITEM_CLASSES = 256;
+__device__ void build_items_block(const Workspace& w, const TileScratch& ts, int frame0, int n_frames, int n_ctas) {
+    __shared__ unsigned hist[RT_ITEM_CLASSES];
+    __shared__ unsigned long long red[32];
+    __shared__ unsigned s_cmax;
+    const int tid = threadIdx.x, T = w.tiles_x * w.tiles_y, NT = n_frames * T;
+    const unsigned* tcost = w.tile_cost + (size_t)frame0 * T;
+    for (int i = tid; i < RT_ITEM_CLASSES; i += blockDim.x) hist[i] = 0u;
+    unsigned long long tot = 0ull;
+    for (int i = tid; i < NT; i += blockDim.x) tot += tcost[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if ((tid & 31) == 0) red[tid >> 5] = tot;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long a = 0ull;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += red[i];
+        const unsigned long long cmax = a / (unsigned long long)((ts.fair > 0 ? ts.fair : RT_FAIR) * n_ctas);
+        const unsigned long long floor_ = (unsigned long long)(ts.min_item > 0 ? ts.min_item : RT_MIN_ITEM);
+        const unsigned long long ceil_ = (unsigned long long)(ts.fair > 0 ? 1u << 30 : RT_MAX_ITEM);      // (an explicit fair share is taken literally)
+        const unsigned long long cm = cmax < floor_ ? floor_ : (cmax > ceil_ ? ceil_ : cmax);
+        s_cmax = ts.split_len > 0 ? (unsigned)ts.split_len : (unsigned)cm;
+    }
+    __syncthreads();
+    const unsigned cmax = s_cmax;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = tid; i < NT; i += blockDim.x) {
+            const unsigned cost = tcost[i];
+            unsigned lg = 0u;                                   // bands: 1 << lg
+            while (lg < 3u && ((cost >> lg) > cmax || (cost >> lg) > (unsigned)ts.list_cap)) ++lg;     // (and keep the lists in one pass)
+            if (ts.nsub > 0) { lg = 0u; while ((1 << lg) < ts.nsub) ++lg; if (cost <= cmax) lg = 0u; }      // forced (measurements)
+            const unsigned long long per = cost >> lg;
+            const unsigned cls = (RT_ITEM_CLASSES - 1) - (unsigned)min(per * 128ull / cmax, (unsigned long long)(RT_ITEM_CLASSES - 1));   // big items first
+            if (pass == 0) {
+                atomicAdd(&hist[cls], 1u << lg);
+            } else {
+                const unsigned pos = atomicAdd(&hist[cls], 1u << lg);
+                for (unsigned b = 0; b < (1u << lg); ++b) ts.items[pos + b] = ((unsigned)(i / T) << 15) | ((unsigned)(i % T) << 5) | (b << 2) | lg;
+            }
+        }
+        __syncthreads();
+        if (pass == 0) {
+            if (tid == 0) {
+                unsigned run = 0u;
+                for (int c = 0; c < RT_ITEM_CLASSES; ++c) { const unsigned v = hist[c]; hist[c] = run; run += v; }
+                *ts.n_items = run;
+                *ts.item_next = 0u;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+
 // ---------------------------------------------------------------------------
 // frame_front: frame_forward + bin_count + bin_scan + bin_fill of one frame in ONE launch, the frame spread over a
 // thread-block cluster of FRONT_CTAS CTAs (4 x 16 warps = the BIN_WARPS face segments):
@@ -224,7 +307,9 @@ __device__ __forceinline__ void lbs_vertex(const FrameSmem& S, const ModelDev& m
 }
 
 __global__ void __cluster_dims__(FRONT_CTAS, 1, 1) __launch_bounds__(FRONT_THREADS)
-frame_front_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, float* verts_out, int do_bin) {
+frame_front_kernel(ModelDev m, Workspace w, TileScratch ts, Params p, int frame0, int n_frames, Weights wt, float* verts_out, int do_bin,
+                   int n_ctas) {
+    grid_dep_wait();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FrameSmem& S = *reinterpret_cast<FrameSmem*>(smem_raw);
     cg::cluster_group cluster = cg::this_cluster();
@@ -474,16 +559,34 @@ frame_front_kernel(ModelDev m, Workspace w, Params p, int frame0, Weights wt, fl
     }
     PHASE_CLOCK() PHASE_CLOCK_PRINT("frame_front [pose lbs joints sync1 kp count+sync2 scan fill]", blockIdx.y == 0 && crank == 0 && tid == 0)
     if (dropped) atomicAdd(w.counters + 2, (unsigned long long)dropped);
+    PHASE_CLOCK()   /* fill */
+    // the last frame to finish its binning builds the rasteriser's hand-out list from every frame's tile costs
+    // (CTA 0 of a cluster wrote its frame's tile_cost; each takes one ticket when it is done)
+    if (crank == 0) {
+        __shared__ bool s_last_frame;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            s_last_frame = (atomicAdd(ts.front_ticket, 1u) == (unsigned)n_frames - 1u);
+        }
+        __syncthreads();
+        if (s_last_frame) {
+            __threadfence();
+            if (tid == 0) *ts.front_ticket = 0u;
+            build_items_block(w, ts, frame0, n_frames, n_ctas);
+        }
+    }
+    PHASE_CLOCK_PRINT("frame_front [pose lbs joints sync1 kp count+sync2 scan fill]", blockIdx.y == 0 && crank == 0 && tid == 0)
 }
 
 size_t frame_front_smem_bytes(const Workspace& w) {
     return sizeof(FrameSmem) + (size_t)(FRONT_WARPS + 3) * w.tiles_x * w.tiles_y * sizeof(unsigned);
 }
 
-void launch_frame_front(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n, Weights wt,
-                        float* verts_out, bool do_bin, cudaStream_t st) {
+void launch_frame_front(const ModelDev& m, const Workspace& w, const TileScratch& ts, const Params& p, int frame0, int n, Weights wt,
+                        float* verts_out, bool do_bin, int n_ctas, cudaStream_t st) {
     const dim3 grid(FRONT_CTAS, n);
-    frame_front_kernel<<<grid, FRONT_THREADS, frame_front_smem_bytes(w), st>>>(m, w, p, frame0, wt, verts_out, do_bin ? 1 : 0);
+    launch_pdl(frame_front_kernel, grid, dim3(FRONT_THREADS), frame_front_smem_bytes(w), st, m, w, ts, p, frame0, n, wt, verts_out, do_bin ? 1 : 0, n_ctas);
 }
 
 // ---------------------------------------------------------------------------
@@ -611,6 +714,7 @@ __device__ __forceinline__ void bw_sweep2(const FaceSetup& fs, const BwFace& b, 
 }
 
 __global__ void __launch_bounds__(256, BW_MIN_CTAS) raster_backward_kernel(ModelDev m, Workspace w, int frame0) {
+    grid_dep_wait();
     const int lane = threadIdx.x & 31;
     const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int fr = frame0 + blockIdx.y;
@@ -670,7 +774,7 @@ __global__ void __launch_bounds__(256, BW_MIN_CTAS) raster_backward_kernel(Model
 
 void launch_raster_backward(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st) {
     dim3 grid((m.Fp + 7) / 8, n);
-    raster_backward_kernel<<<grid, 256, 0, st>>>(m, w, frame0);
+    launch_pdl(raster_backward_kernel, grid, dim3(256), 0, st, m, w, frame0);
 }
 
 // ---------------------------------------------------------------------------
@@ -688,6 +792,7 @@ constexpr int BACK_CTAS = 4, BACK_THREADS = 512, BACK_PRIOR_CTA = BACK_CTAS - 1;
 
 __global__ void __cluster_dims__(BACK_CTAS, 1, 1) __launch_bounds__(BACK_THREADS)
 frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, Weights wt) {
+    grid_dep_wait();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FrameSmem& S = *reinterpret_cast<FrameSmem*>(smem_raw);
     cg::cluster_group cluster = cg::this_cluster();
@@ -950,7 +1055,7 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
 
 void launch_frame_backward(const ModelDev& m, const Workspace& w, const Params& p, const Grads& g,
                            int frame0, int n, Weights wt, cudaStream_t st) {
-    frame_backward_kernel<<<dim3(BACK_CTAS, n), BACK_THREADS, sizeof(FrameSmem), st>>>(m, w, p, g, frame0, wt);
+    launch_pdl(frame_backward_kernel, dim3(BACK_CTAS, n), dim3(BACK_THREADS), sizeof(FrameSmem), st, m, w, p, g, frame0, wt);
 }
 
 // ---------------------------------------------------------------------------
@@ -958,6 +1063,7 @@ void launch_frame_backward(const ModelDev& m, const Workspace& w, const Params& 
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 shape_backward_kernel(ModelDev m, Workspace w, int frame0, int n_frames, int n_blocks) {
+    grid_dep_wait();
     __shared__ float red[8][NBETA];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int slot = (w.n_shapes == 1) ? w.slot0 : frame0 + blockIdx.y;
@@ -994,6 +1100,7 @@ shape_backward_kernel(ModelDev m, Workspace w, int frame0, int n_frames, int n_b
 __global__ void __launch_bounds__(256)
 finalize_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, int n_frames, Weights wt,
                 int prior_windows, int n_blocks, float* loss_terms) {
+    grid_dep_wait();
     __shared__ float red[40];
     __shared__ float diff[32], res[32];
     __shared__ bool s_last;
@@ -1092,8 +1199,8 @@ void launch_shape_backward(const ModelDev& m, const Workspace& w, const Params& 
     const int n_blocks = (m.V * 3 + 255) / 256;
     const int n_slots = (w.n_shapes == 1) ? 1 : n;
     dim3 grid(n_blocks, n_slots);
-    shape_backward_kernel<<<grid, 256, 0, st>>>(m, w, frame0, n, n_blocks);
-    finalize_kernel<<<n_slots, 256, 0, st>>>(m, w, p, g, frame0, n, wt, prior_windows, n_blocks, loss_terms);
+    launch_pdl(shape_backward_kernel, grid, dim3(256), 0, st, m, w, frame0, n, n_blocks);
+    launch_pdl(finalize_kernel, dim3(n_slots), dim3(256), 0, st, m, w, p, g, frame0, n, wt, prior_windows, n_blocks, loss_terms);
 }
 
 // ---------------------------------------------------------------------------
@@ -1338,6 +1445,7 @@ void launch_peer_allreduce(const PeerDev& pd, float* data, int n, cudaStream_t s
 // ---------------------------------------------------------------------------
 constexpr int TAIL_THREADS = 512, TAIL_HEAD = 40;
 __global__ void __launch_bounds__(TAIL_THREADS) step_tail_kernel(PeerDev pd, TailArgs a) {
+    grid_dep_wait();
     __shared__ float s_bc[2];
     __shared__ int s_step;
     const int tid = threadIdx.x;
@@ -1435,7 +1543,7 @@ void launch_step_tail(const PeerDev& pd, const TailArgs& a, cudaStream_t st) {
     const int total = (a.n_shapes == 1 ? 26 : f_n * 26) + f_n * 108;
     int grid = (total + TAIL_THREADS - 1) / TAIL_THREADS;
     grid = grid < 1 ? 1 : (grid > 32 ? 32 : grid);           // all CTAs must be co-resident (they wait on each other's pushes)
-    step_tail_kernel<<<grid, TAIL_THREADS, 0, st>>>(pd, a);
+    launch_pdl(step_tail_kernel, dim3(grid), dim3(TAIL_THREADS), 0, st, pd, a);
 }
 
 // ---------------------------------------------------------------------------

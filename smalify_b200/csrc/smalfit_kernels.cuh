@@ -23,6 +23,14 @@ constexpr int RT_PLANE = RT_PITCH * (TILE_H + 1) + 3;      // words per plane (3
 constexpr int RT_BLK = 16;                  // prepared faces per TMA block
 constexpr int RT_BAND_MAX = 2048;           // faces of one warp's range whose positions a band item compacts (longer ranges: streamed whole)
 constexpr int MAX_TILES = 1024;             // 32x32 tiles per frame (image side <= 1024)
+// item-size rule of the tile rasteriser's hand-out list (build_items)
+constexpr int RT_FAIR = 2;                      // a hand-out item holds at most 1/RT_FAIR of a CTA's fair share of the pairs ...
+constexpr int RT_MAX_ITEM = 64000;              // ... but never more pairs than this: the fragment lists of the items in flight
+                                                // (n_ctas x ~0.6 x 8 B per pair) should fit the 126 MB L2 (measured at 128 frames:
+                                                // 61 k pairs per item 1.05 ms / 1.06 GB of DRAM traffic, 122 k: 1.14 ms / 1.67 GB)
+constexpr int RT_MIN_ITEM = 16000;              // ... and no tile is cut into bands of fewer pairs than this (an item has fixed costs;
+                                                // measured best at 16 / 32 / 64 frames per GPU: 16 k / 32 k / 48 k pairs)
+
 constexpr int MAX_LEVELS = 16;
 constexpr int SKIN_CHUNK = 96, MAX_SKIN_CHUNKS = 192;
 constexpr float P_SKIP = 2.98023224e-8f;    // 2^-25: below this 1-P rounds to 1.0f in fp32
@@ -131,6 +139,7 @@ struct TileScratch {        // tile rasteriser: per resident CTA
     int list_stride;        // list_cap + Fp
     unsigned* item_next;    // [1] next item to hand out
     unsigned* n_items;      // [1]
+    unsigned* front_ticket; // [1] frames whose binning is complete (the last one builds the hand-out list)
     unsigned* items;        // [N * tiles * 8] frame << 15 | tile << 5 | band << 2 | log2(bands)   (build_items_kernel)
     unsigned short* band_idx;   // [n_ctas][RT_WARPS][RT_BAND_MAX] band items: list positions of the faces that reach the band
     int nsub;               // > 0: force this many bands for every list longer than split_len (measurements)
@@ -143,8 +152,8 @@ struct TileScratch {        // tile rasteriser: per resident CTA
 void upload_skeleton(const SkeletonConst& sk);
 cudaError_t configure_kernels(const ModelDev& m);
 void launch_shape_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n, cudaStream_t st);
-void launch_frame_front(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n, Weights wt,
-                        float* verts_out, bool do_bin, cudaStream_t st);
+void launch_frame_front(const ModelDev& m, const Workspace& w, const TileScratch& ts, const Params& p, int frame0, int n, Weights wt,
+                        float* verts_out, bool do_bin, int n_ctas, cudaStream_t st);
 size_t raster_tile_smem_bytes();
 void launch_raster_tile_forward(const ModelDev& m, const Workspace& w, const TileScratch& ts, int frame0, int n, Weights wt,
                                 float* alpha_out, int n_ctas, cudaStream_t st);

@@ -5,14 +5,15 @@
 // silhouette term of smal_fitter/smal_fitter.py:172-173.  Outputs: per pixel (coef, depth threshold, tie
 // face id) for raster_backward, per region row sum|alpha - T|, optionally alpha itself.
 //
-// Work item (build_items_kernel) = one 32x32-pixel tile of one frame, or one band of rows of a tile that
-// holds more than 1/RT_FAIR of a CTA's fair share of the launch's (pixel, face) pairs; items are handed out
-// largest first to persistent CTAs of 8 warps, 3 CTAs per SM.  The tile's face list (bin_faces, ascending
+// Work item (build_items, run by the last CTA of frame_front) = one 32x32-pixel tile of one frame, or one band of rows
+// of a tile that holds more than the item-size rule allows (RT_FAIR / RT_MIN_ITEM / RT_MAX_ITEM); items are handed out
+// largest first to persistent CTAs of 8 warps, 3 CTAs per SM.  The tile's face list (frame_front's binning, ascending
 // face id) is split into 8 contiguous ranges of equal cost, one per warp, and every warp is *face-parallel*:
-// it streams its prepared faces (64-byte records written by bin_faces) through a double-buffered
-// shared-memory stage with 1-D TMA bulk copies, and for each face its 32 lanes sweep the face's pixel
-// rectangle.  No pair is evaluated twice and nothing is gathered: the per-pair cost is the fragment
-// arithmetic itself (frag_setup_forward, operation for operation the backward's face_eval_core).
+// it streams its prepared faces (64-byte records written by the binning) through a double-buffered
+// shared-memory stage with 1-D TMA bulk copies (band items: cp.async gathers of the faces that reach the band), and
+// for each face its 32 lanes sweep the face's pixel rectangle, one pixel or -- packed FP32 -- two pixels per lane.
+// No pair is evaluated twice: the per-pair cost is the fragment arithmetic itself (frag_setup_forward / face_eval2,
+// operation for operation the backward's face_eval_core).
 //
 //   P0  box counts: each warp adds its faces' rectangles into its own 33x33 corner grid (native
 //       32-bit shared-memory atomics) and integrates it -> candidates per (warp, pixel).
@@ -26,9 +27,9 @@
 //       touch distinct pixels), listed pixels store (depth key, 1 - p) at their cursor (evict_last).
 //   P2a the direct pixels' products leave the planes (multiplied in warp order).
 //   P2  per listed pixel, one warp: the list is staged into the warp's (now free) plane with cp.async while
-//       the previous pixel is selected; keys in registers (8 per lane; longer lists first bisect in memory),
-//       exact K-th order statistic of (depth, slot) by bisection on the key bits, product over the selected
-//       set; the list's lines are then dropped from L2 without write-back.
+//       the previous pixel is selected; keys in registers (8 per lane; lists of 257..512 entries are first narrowed
+//       in the plane, longer ones in global memory), exact K-th order statistic of (depth, slot) by bisection on
+//       the key bits, product over the selected set; the list's lines are then dropped from L2 without write-back.
 //   P3  per pixel: alpha, |alpha - T|, coef = dL/dalpha * P / sigma; region row sums in fixed order.
 // Every reduction has a fixed order: results are run-to-run deterministic.
 #pragma once
@@ -46,13 +47,7 @@ constexpr int RT_MIDCAP = 512;                  // lists up to this length are n
 constexpr int RT_PIX = TILE_W * TILE_H;
 constexpr unsigned char RT_CLS_DIRECT = 0, RT_CLS_LISTED = 1, RT_CLS_IDLE = 2;
 constexpr int RT_MAXCHUNK = 512;                // tile lists up to 8192 faces are split by cost, longer ones evenly
-constexpr int RT_FAIR = 2;                      // a hand-out item holds at most 1/RT_FAIR of a CTA's fair share of the pairs ...
-constexpr int RT_MAX_ITEM = 64000;              // ... but never more pairs than this: the fragment lists of the items in flight
-                                                // (n_ctas x ~0.6 x 8 B per pair) should fit the 126 MB L2 (measured at 128 frames:
-                                                // 61 k pairs per item 1.05 ms / 1.06 GB of DRAM traffic, 122 k: 1.14 ms / 1.67 GB)
 constexpr unsigned RT_FACE_COST = 16u;          // per-face overhead of the sweep, in pair evaluations
-constexpr int RT_MIN_ITEM = 16000;              // ... and no tile is cut into bands of fewer pairs than this (an item has fixed costs;
-                                                // measured best at 16 / 32 / 64 frames per GPU: 16 k / 32 k / 48 k pairs)
 // (interpolated pivots in the K-th order statistic search were measured: +2 % on the kernel -- the depths of one pixel's
 //  candidates cluster on the front and back surfaces, bisection on the key bits with an exact-split exit does better)
 
@@ -367,6 +362,7 @@ __device__ __forceinline__ void rt_sweep_face(const float4* __restrict__ rec, un
 
 __global__ void __launch_bounds__(RT_THREADS, RT_CTAS_PER_SM)
 raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, int n_frames, Weights wt, float* alpha_out) {
+    grid_dep_wait();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     RtSmem& sm = *reinterpret_cast<RtSmem*>(smem_raw);
     int lane;                            // (asm volatile: kept in a register instead of being re-derived from S2R in the inner loops)
@@ -781,69 +777,12 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
 
 size_t raster_tile_smem_bytes() { return sizeof(RtSmem); }
 
-// Hand-out list of the tile rasteriser: every (frame, tile) becomes 1, 2, 4 or 8 items (bands of rows) so that no
-// item holds more than about 1/fair of a CTA's fair share of the launch's (pixel, face) pairs (bin_faces counts them
-// per tile), ordered by decreasing pairs per item (counting sort into 256 classes; the order inside a class does not
-// matter: items are independent).  Also resets the hand-out counter.  One CTA.
-constexpr int RT_ITEM_CLASSES = 256;
-__global__ void __launch_bounds__(1024) build_items_kernel(Workspace w, TileScratch ts, int frame0, int n_frames, int n_ctas) {
-    __shared__ unsigned hist[RT_ITEM_CLASSES];
-    __shared__ unsigned long long red[32];
-    __shared__ unsigned s_cmax;
-    const int tid = threadIdx.x, T = w.tiles_x * w.tiles_y, NT = n_frames * T;
-    const unsigned* tcost = w.tile_cost + (size_t)frame0 * T;
-    for (int i = tid; i < RT_ITEM_CLASSES; i += blockDim.x) hist[i] = 0u;
-    unsigned long long tot = 0ull;
-    for (int i = tid; i < NT; i += blockDim.x) tot += tcost[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if ((tid & 31) == 0) red[tid >> 5] = tot;
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long a = 0ull;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += red[i];
-        const unsigned long long cmax = a / (unsigned long long)((ts.fair > 0 ? ts.fair : RT_FAIR) * n_ctas);
-        const unsigned long long floor_ = (unsigned long long)(ts.min_item > 0 ? ts.min_item : RT_MIN_ITEM);
-        const unsigned long long ceil_ = (unsigned long long)(ts.fair > 0 ? 1u << 30 : RT_MAX_ITEM);      // (an explicit fair share is taken literally)
-        const unsigned long long cm = cmax < floor_ ? floor_ : (cmax > ceil_ ? ceil_ : cmax);
-        s_cmax = ts.split_len > 0 ? (unsigned)ts.split_len : (unsigned)cm;
-    }
-    __syncthreads();
-    const unsigned cmax = s_cmax;
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int i = tid; i < NT; i += blockDim.x) {
-            const unsigned cost = tcost[i];
-            unsigned lg = 0u;                                   // bands: 1 << lg
-            while (lg < 3u && ((cost >> lg) > cmax || (cost >> lg) > (unsigned)ts.list_cap)) ++lg;     // (and keep the lists in one pass)
-            if (ts.nsub > 0) { lg = 0u; while ((1 << lg) < ts.nsub) ++lg; if (cost <= cmax) lg = 0u; }      // forced (measurements)
-            const unsigned long long per = cost >> lg;
-            const unsigned cls = (RT_ITEM_CLASSES - 1) - (unsigned)min(per * 128ull / cmax, (unsigned long long)(RT_ITEM_CLASSES - 1));   // big items first
-            if (pass == 0) {
-                atomicAdd(&hist[cls], 1u << lg);
-            } else {
-                const unsigned pos = atomicAdd(&hist[cls], 1u << lg);
-                for (unsigned b = 0; b < (1u << lg); ++b) ts.items[pos + b] = ((unsigned)(i / T) << 15) | ((unsigned)(i % T) << 5) | (b << 2) | lg;
-            }
-        }
-        __syncthreads();
-        if (pass == 0) {
-            if (tid == 0) {
-                unsigned run = 0u;
-                for (int c = 0; c < RT_ITEM_CLASSES; ++c) { const unsigned v = hist[c]; hist[c] = run; run += v; }
-                *ts.n_items = run;
-                *ts.item_next = 0u;
-            }
-            __syncthreads();
-        }
-    }
-}
-
 void launch_raster_tile_forward(const ModelDev& m, const Workspace& w, const TileScratch& ts, int frame0, int n, Weights wt,
                                 float* alpha_out, int n_ctas, cudaStream_t st) {
-    build_items_kernel<<<1, 1024, 0, st>>>(w, ts, frame0, n, n_ctas);
+    // (the hand-out list was built by the last CTA of frame_front)
     const long long tiles = (long long)n * w.tiles_x * w.tiles_y;
     const int grid = (int)(tiles < n_ctas ? tiles : n_ctas);
-    raster_tile_forward_kernel<<<grid, RT_THREADS, raster_tile_smem_bytes(), st>>>(m, w, ts, frame0, n, wt, alpha_out);
+    launch_pdl(raster_tile_forward_kernel, dim3(grid), dim3(RT_THREADS), raster_tile_smem_bytes(), st, m, w, ts, frame0, n, wt, alpha_out);
 }
 
 }  // namespace smf

@@ -74,3 +74,24 @@ def test_joint_limits_table_shape():
     lo, hi = K.joint_limits()
     assert lo.shape == hi.shape == (K.N_POSE, 3) and np.all(lo <= hi)
     assert np.isfinite(lo[:32]).all() and np.isfinite(hi[:32]).all() and not np.isfinite(lo[32:]).any()
+
+
+def test_subsequence_is_a_slice_of_the_sequence(constants, oracle64):
+    """synthetic.make_subsequence: a rank that builds only its shard of the seeded sequence gets exactly the frames
+    (targets, keypoint noise, visibility rows, ground truth) the whole sequence has at those positions -- also in the
+    padded layout a frame-sharded fitter takes."""
+    import torch
+    import helpers as H
+    from smalify_b200 import synthetic
+    S, n, idx = 24, 5, [1, 3, 4]
+    render = H.oracle_renderer(oracle64, S)
+    (rgb, sil, joints, vis), gt = synthetic.make_sequence(constants, n, S, render, seed=0)
+    (rgb2, sil2, joints2, vis2), gt2 = synthetic.make_subsequence(constants, n, idx, S, render, seed=0)
+    assert torch.equal(sil2, sil[idx]) and torch.equal(joints2, joints[idx]) and torch.equal(vis2, vis[idx])
+    assert torch.equal(gt2["global_rotation"], gt["global_rotation"][idx]) and torch.equal(gt2["betas"], gt["betas"])
+    (_, sil3, joints3, vis3), _ = synthetic.make_subsequence(constants, n, [3, 4], S, render, seed=0, pad_to=(3, n))
+    assert sil3.shape[0] == n and torch.equal(sil3[3:5], sil[3:5]) and float(sil3[:3].abs().sum()) == 0.0
+    assert torch.equal(joints3[3:5], joints[3:5]) and torch.equal(vis3[3:5], vis[3:5])
+    # one shape per frame: the ground truth carries a row per frame
+    (_, sil4, _, _), gt4 = synthetic.make_subsequence(constants, n, [0, 2], S, render, seed=0, per_frame_shapes=True)
+    assert gt4["betas"].shape == (2, 20) and sil4.shape[0] == 2
