@@ -14,7 +14,6 @@ of the gradient when frames are sharded], Adam.  Prints ONE JSON line (rank 0).
 from __future__ import annotations
 
 import argparse
-import hashlib
 import json
 import os
 import statistics
@@ -67,9 +66,9 @@ def measured_peaks():
 
 
 def lib_hash() -> str:
-    from smalify_b200 import _cabi
-    with open(_cabi.LIB_PATH, "rb") as f:
-        return hashlib.sha256(f.read()).hexdigest()[:16]
+    """Identifies the kernels' source (nvcc output is not bit-reproducible: the hash is over csrc/ + include/smalfit.h)."""
+    from smalify_b200 import build as B
+    return B.source_hash()
 
 
 class ClockSampler:
@@ -495,11 +494,11 @@ def run_ours(args):
         with open(tpath) as fh:
             t = json.load(fh)
         if t.get("frames_per_gpu") == frames_rank and t.get("image_size") == S:
-            if t.get("lib_sha16") == lib_hash():
+            if t.get("src_sha16") == lib_hash():
                 traffic, traffic_note = t["dram_bytes_per_launch"], "ncu --set full capture of this build (profiles/raster_forward_traffic.json)"
             else:
                 traffic_note = (f"last capture ({t.get('dram_bytes_per_launch')} B per launch, {t.get('capture', 'earlier build')}) "
-                                f"is of another build of libsmalfit.so: not reported as this build's traffic")
+                                f"is of other kernel sources: not reported as this build's traffic")
     # The binding roof: FP32 pair tests.  F_alg = 90 flop per bounding-box-passing pair in the forward (70 in the
     # backward); peak = the FMA-chain ceiling measured on this GPU in this run (scalar FFMA; FFMA2 reported beside it).
     pairs = float(work["pairs"])
@@ -552,7 +551,7 @@ def run_ours(args):
         "capped_pixels_per_step": int(cnt["capped_pixels"]) // n_prof, "long_list_pixels_per_step": int(cnt["spilled_pixels"]) // n_prof,
         "dropped_bin_entries": int(cnt["dropped_bin_entries"]),
         "device_memory": {"torch_allocated_bytes": int(mem_after_setup), "device_used_bytes": int(total_b - free_b)},
-        "lib_sha16": lib_hash(),
+        "src_sha16": lib_hash(),
     }
     if replicas_identical is not None:
         line["replicas_identical"] = replicas_identical

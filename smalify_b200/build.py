@@ -35,6 +35,18 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def source_hash() -> str:
+    """sha256 (16 hex digits) over the CUDA sources, their headers and the public header: identifies the code a
+    measurement was taken on (nvcc's output is not bit-reproducible, the library file's own hash is not usable)."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    for path in [os.path.join(CSRC, f) for f in files] + [PUBLIC_HEADER]:
+        with open(path, "rb") as fh:
+            h.update(os.path.basename(path).encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
 def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
     """Build the library.  `defines` / `out` produce an experiment variant beside the product
     library (tools/ab_bench.py); the product is always the default build."""

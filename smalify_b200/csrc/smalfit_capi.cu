@@ -290,7 +290,7 @@ int smalfit_create_ex(const smalfit_model_t* md, int device, int max_frames, int
         h->ts.item_next = P.alloc<unsigned>(4, true);
         h->ts.n_items = h->ts.item_next + 1;
         h->ts.front_ticket = h->ts.item_next + 2;
-        h->ts.items = P.alloc<unsigned>(N * tiles * 8 + 8);
+        h->ts.items = P.alloc<uint4>(N * tiles * 8 + 8);
         h->ts.band_idx = P.alloc<unsigned short>((size_t)h->tile_ctas * RT_WARPS * RT_BAND_MAX);
         const char* e_nsub = getenv("SMALFIT_RT_NSUB");         // tuning knobs for measurements
         const char* e_split = getenv("SMALFIT_RT_SPLITLEN");
@@ -448,7 +448,7 @@ static int run_forward(smalfit_t h, const Params& p, int frame0, int n, Weights 
     h->mark(0, st);
     launch_shape_forward(h->m, h->w, p, frame0, n, st);
     // frame_forward + binning of a frame in one launch over a 4-CTA cluster (profile phases 0 and 1 are reported together)
-    launch_frame_front(h->m, h->w, h->ts, p, frame0, n, wt, verts_out, raster, h->tile_ctas, st);
+    launch_frame_front(h->m, h->w, h->ts, p, frame0, n, wt, verts_out, raster ? (alpha_out ? 2 : 1) : 0, h->tile_ctas, st);
     h->n_launches += 2;
     h->mark(1, st);
     if (raster) {

@@ -219,15 +219,23 @@ __device__ __forceinline__ void bin_segment(const ModelDev& m, int seg_id, int& 
 // per tile), ordered by decreasing pairs per item (counting sort into 256 classes; the order inside a class does not
 // matter: items are independent).  Also resets the hand-out counter.  One CTA (the last one of frame_front to finish).
 constexpr int RT_ITEM_CLASSES = 256;
-__device__ void build_items_block(const Workspace& w, const TileScratch& ts, int frame0, int n_frames, int n_ctas) {
+__device__ void build_items_block(const Workspace& w, const TileScratch& ts, int frame0, int n_frames, int n_ctas, bool keep_empty) {
     __shared__ unsigned hist[RT_ITEM_CLASSES];
     __shared__ unsigned long long red[32];
     __shared__ unsigned s_cmax;
     const int tid = threadIdx.x, T = w.tiles_x * w.tiles_y, NT = n_frames * T;
     const unsigned* tcost = w.tile_cost + (size_t)frame0 * T;
     for (int i = tid; i < RT_ITEM_CLASSES; i += blockDim.x) hist[i] = 0u;
+    // (this block runs alone at the end of frame_front: tile costs are fetched in batches of independent loads)
+    constexpr int U = 8;
     unsigned long long tot = 0ull;
-    for (int i = tid; i < NT; i += blockDim.x) tot += tcost[i];
+    for (int base = 0; base < NT; base += (int)blockDim.x * U) {
+        unsigned c[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) { const int i = base + q * (int)blockDim.x + tid; c[q] = (i < NT) ? tcost[i] : 0u; }
+#pragma unroll
+        for (int q = 0; q < U; ++q) tot += c[q];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     if ((tid & 31) == 0) red[tid >> 5] = tot;
@@ -244,27 +252,47 @@ __device__ void build_items_block(const Workspace& w, const TileScratch& ts, int
     __syncthreads();
     const unsigned cmax = s_cmax;
     for (int pass = 0; pass < 2; ++pass) {
-        for (int i = tid; i < NT; i += blockDim.x) {
-            const unsigned cost = tcost[i];
-            unsigned lg = 0u;                                   // bands: 1 << lg
-            while (lg < 3u && ((cost >> lg) > cmax || (cost >> lg) > (unsigned)ts.list_cap)) ++lg;     // (and keep the lists in one pass)
-            if (ts.nsub > 0) { lg = 0u; while ((1 << lg) < ts.nsub) ++lg; if (cost <= cmax) lg = 0u; }      // forced (measurements)
-            const unsigned long long per = cost >> lg;
-            const unsigned cls = (RT_ITEM_CLASSES - 1) - (unsigned)min(per * 128ull / cmax, (unsigned long long)(RT_ITEM_CLASSES - 1));   // big items first
-            if (pass == 0) {
-                atomicAdd(&hist[cls], 1u << lg);
-            } else {
-                const unsigned pos = atomicAdd(&hist[cls], 1u << lg);
-                for (unsigned b = 0; b < (1u << lg); ++b) ts.items[pos + b] = ((unsigned)(i / T) << 15) | ((unsigned)(i % T) << 5) | (b << 2) | lg;
+        for (int base = 0; base < NT; base += (int)blockDim.x * U) {
+            unsigned c[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) { const int i = base + q * (int)blockDim.x + tid; c[q] = (i < NT) ? tcost[i] : 0u; }
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int i = base + q * (int)blockDim.x + tid;
+                const unsigned cost = c[q];
+                if (i >= NT || (cost == 0u && !keep_empty)) continue;            // (frame_front has finished the tiles no face reaches)
+                unsigned lg = 0u;                                   // bands: 1 << lg
+                while (lg < 3u && ((cost >> lg) > cmax || (cost >> lg) > (unsigned)ts.list_cap)) ++lg;     // (and keep the lists in one pass)
+                if (ts.nsub > 0) { lg = 0u; while ((1 << lg) < ts.nsub) ++lg; if (cost <= cmax) lg = 0u; }      // forced (measurements)
+                const unsigned long long per = cost >> lg;
+                const unsigned cls = (RT_ITEM_CLASSES - 1) - (unsigned)min(per * 128ull / cmax, (unsigned long long)(RT_ITEM_CLASSES - 1));   // big items first
+                if (pass == 0) {
+                    atomicAdd(&hist[cls], 1u << lg);
+                } else {
+                    const unsigned pos = atomicAdd(&hist[cls], 1u << lg);
+                    // (the tile's slice of the frame's pool, clamped like every reader of tile_off clamps it)
+                    const unsigned* toff = w.tile_off + (size_t)(frame0 + i / T) * (T + 1);
+                    const unsigned off = min(toff[i % T], (unsigned)w.pool_cap), len = min(toff[i % T + 1], (unsigned)w.pool_cap) - off;
+                    for (unsigned b = 0; b < (1u << lg); ++b)
+                        ts.items[pos + b] = make_uint4(((unsigned)(i / T) << 15) | ((unsigned)(i % T) << 5) | (b << 2) | lg, off, len, 0u);
+                }
             }
         }
         __syncthreads();
         if (pass == 0) {
-            if (tid == 0) {
-                unsigned run = 0u;
-                for (int c = 0; c < RT_ITEM_CLASSES; ++c) { const unsigned v = hist[c]; hist[c] = run; run += v; }
-                *ts.n_items = run;
-                *ts.item_next = 0u;
+            // exclusive prefix over the classes (one warp, 8 classes per lane)
+            if (tid < 32) {
+                constexpr int PER = RT_ITEM_CLASSES / 32;
+                unsigned v[PER], sum = 0u;
+#pragma unroll
+                for (int q = 0; q < PER; ++q) { v[q] = hist[tid * PER + q]; sum += v[q]; }
+                unsigned incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += y; }
+                unsigned run = incl - sum;
+#pragma unroll
+                for (int q = 0; q < PER; ++q) { hist[tid * PER + q] = run; run += v[q]; }
+                if (tid == 31) { *ts.n_items = incl; *ts.item_next = 0u; }
             }
             __syncthreads();
         }
@@ -483,6 +511,16 @@ frame_front_kernel(ModelDev m, Workspace w, TileScratch ts, Params p, int frame0
         }
         __syncthreads();
     }
+    // tiles no face reaches: alpha = 0, |alpha - T| = T -- finished here (a quarter per CTA) instead of being handed to the
+    // rasteriser as items (5 of 6 tiles of a 256^2 frame; do_bin == 2: the caller wants alpha written, they stay items)
+    if (do_bin == 1) {
+        const int RPT = REGIONS_PER_TILE * REGION_H;
+        const int nq = (T * RPT + FRONT_CTAS - 1) / FRONT_CTAS;
+        const int i_hi = min(T * RPT, (crank + 1) * nq);
+        const size_t base = (size_t)fr * T * RPT;
+        for (int i = crank * nq + tid; i < i_hi; i += FRONT_THREADS)
+            if (tot[i / RPT] == 0u) w.region_l1[base + i] = w.region_tsum[base + i];
+    }
     cluster.sync();                                   // nobody reads another CTA's counts from here on
     {
         unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
@@ -573,7 +611,7 @@ frame_front_kernel(ModelDev m, Workspace w, TileScratch ts, Params p, int frame0
         if (s_last_frame) {
             __threadfence();
             if (tid == 0) *ts.front_ticket = 0u;
-            build_items_block(w, ts, frame0, n_frames, n_ctas);
+            build_items_block(w, ts, frame0, n_frames, n_ctas, do_bin == 2);
         }
     }
     PHASE_CLOCK_PRINT("frame_front [pose lbs joints sync1 kp count+sync2 scan fill]", blockIdx.y == 0 && crank == 0 && tid == 0)
@@ -584,9 +622,9 @@ size_t frame_front_smem_bytes(const Workspace& w) {
 }
 
 void launch_frame_front(const ModelDev& m, const Workspace& w, const TileScratch& ts, const Params& p, int frame0, int n, Weights wt,
-                        float* verts_out, bool do_bin, int n_ctas, cudaStream_t st) {
+                        float* verts_out, int do_bin, int n_ctas, cudaStream_t st) {
     const dim3 grid(FRONT_CTAS, n);
-    launch_pdl(frame_front_kernel, grid, dim3(FRONT_THREADS), frame_front_smem_bytes(w), st, m, w, ts, p, frame0, n, wt, verts_out, do_bin ? 1 : 0, n_ctas);
+    launch_pdl(frame_front_kernel, grid, dim3(FRONT_THREADS), frame_front_smem_bytes(w), st, m, w, ts, p, frame0, n, wt, verts_out, do_bin, n_ctas);
 }
 
 // ---------------------------------------------------------------------------

@@ -140,7 +140,7 @@ struct TileScratch {        // tile rasteriser: per resident CTA
     unsigned* item_next;    // [1] next item to hand out
     unsigned* n_items;      // [1]
     unsigned* front_ticket; // [1] frames whose binning is complete (the last one builds the hand-out list)
-    unsigned* items;        // [N * tiles * 8] frame << 15 | tile << 5 | band << 2 | log2(bands)   (build_items_kernel)
+    uint4* items;           // [N * tiles * 8] (frame << 15 | tile << 5 | band << 2 | log2(bands), list offset, list length, -)   (build_items)
     unsigned short* band_idx;   // [n_ctas][RT_WARPS][RT_BAND_MAX] band items: list positions of the faces that reach the band
     int nsub;               // > 0: force this many bands for every list longer than split_len (measurements)
     int fair;               // > 0: overrides RT_FAIR (and lifts RT_MAX_ITEM)
@@ -153,7 +153,8 @@ void upload_skeleton(const SkeletonConst& sk);
 cudaError_t configure_kernels(const ModelDev& m);
 void launch_shape_forward(const ModelDev& m, const Workspace& w, const Params& p, int frame0, int n, cudaStream_t st);
 void launch_frame_front(const ModelDev& m, const Workspace& w, const TileScratch& ts, const Params& p, int frame0, int n, Weights wt,
-                        float* verts_out, bool do_bin, int n_ctas, cudaStream_t st);
+                        float* verts_out, int do_bin /* 0: no rasteriser pass follows, 1: loss / gradient pass, 2: alpha is wanted too */,
+                        int n_ctas, cudaStream_t st);
 size_t raster_tile_smem_bytes();
 void launch_raster_tile_forward(const ModelDev& m, const Workspace& w, const TileScratch& ts, int frame0, int n, Weights wt,
                                 float* alpha_out, int n_ctas, cudaStream_t st);

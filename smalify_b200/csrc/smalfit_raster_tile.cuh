@@ -374,20 +374,24 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
     unsigned phase = 0;                  // bit b: parity the warp waits for next on its stage buffer b
 
     // Values that are only needed again after the sweep live in sm.t across it (the sweep needs the registers).
+    // The hand-out counter is a global atomic (~1 us round trip with the whole CTA waiting) and the item's record one more
+    // dependent load.  (Drawing the next item ahead -- at the start of an item in round 1, after its sweep in round 2 -- was
+    // measured worse both times, +2 ... +7 %: items reserved by busy CTAs are missing from the tail of the launch.)
+    const unsigned n_items = *ts.n_items;
     for (;;) {
         __syncthreads();                 // the previous item's shared state is no longer read
         if (threadIdx.x == 0) sm.item = (int)atomicAdd(ts.item_next, 1u);
         __syncthreads();
         const unsigned item = (unsigned)sm.item;
-        if (item >= *ts.n_items) break;
-        // item = one tile of one frame, or one band of rows of a tile with a long list (build_items)
-        const unsigned code = ts.items[item];
+        if (item >= n_items) break;
+        // item = one tile of one frame, or one band of rows of a tile with a long list (build_items): code, list offset, length
+        const uint4 rec = ts.items[item];
+        const unsigned code = rec.x;
         const int f = (int)(code >> 15), fr = frame0 + f, tile = (int)((code >> 5) & 0x3ffu);
         const int T = w.tiles_x * w.tiles_y;
         const int bh = TILE_H >> (code & 3u), b0 = (int)((code >> 2) & 7u) * bh, b1 = b0 + bh;
-        const unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
-        const unsigned off = min(toff[tile], (unsigned)w.pool_cap);
-        const int len = (int)(min(toff[tile + 1], (unsigned)w.pool_cap) - off);
+        const unsigned off = rec.y;
+        const int len = (int)rec.z;
         const int x0 = (tile % w.tiles_x) * TILE_W, y0 = (tile / w.tiles_x) * TILE_H;
         if (threadIdx.x == 0) { sm.t_f = f; sm.t_tile = tile; sm.t_len = len; sm.t_off = off; }
         if (len == 0) {

@@ -9,7 +9,9 @@ for k in raster_tile_forward_kernel raster_backward_kernel; do
   timeout 600 ncu --set full --import-source on --clock-control none -k regex:$k -s 6 -c 1 -o gpurun_out/${TAG}_$k -f python bench.py --steps 3 --warmup 1 --no-cpu-baseline --no-quality --no-dropin > /dev/null 2> gpurun_out/${TAG}_$k.err
 done
 python - "$TAG" <<'PY'
-import csv, hashlib, json, subprocess, sys
+import csv, json, subprocess, sys
+sys.path.insert(0, ".")
+from smalify_b200 import build as B
 tag = sys.argv[1]
 out = subprocess.run(["ncu", "-i", f"gpurun_out/{tag}_raster_tile_forward_kernel.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
@@ -18,8 +20,8 @@ def get(name):
     i = hdr.index(name); v = float(vals[i]); u = units[i]
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
 rd, wr = get("dram__bytes_read.sum"), get("dram__bytes_write.sum")
-sha = hashlib.sha256(open("smalify_b200/libsmalfit.so", "rb").read()).hexdigest()[:16]
+sha = B.source_hash()
 json.dump({"kernel": "raster_tile_forward_kernel", "frames_per_gpu": 128, "image_size": 256, "dram_bytes_read": rd, "dram_bytes_write": wr,
-           "dram_bytes_per_launch": rd + wr, "lib_sha16": sha, "capture": f"ncu --set full, {tag}"}, open(f"gpurun_out/{tag}_raster_forward_traffic.json", "w"), indent=1)
+           "dram_bytes_per_launch": rd + wr, "src_sha16": sha, "capture": f"ncu --set full, {tag}"}, open(f"gpurun_out/{tag}_raster_forward_traffic.json", "w"), indent=1)
 print("traffic", rd + wr, sha)
 PY

@@ -1,3 +1,4 @@
+# GPU box (8 GPUs): the 2/4/8-GPU scaling lines, the NCCL variant, config 4 on 8 GPUs and a 1-GPU line on the same box -> gpurun_out/r02_*
 B="--steps 20 --warmup 5"
 run() { n=$1; tag=$2; shift 2; python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 300)) bench.py --gpus $n $B "$@" > gpurun_out/r02_${tag}.json 2> gpurun_out/r02_${tag}.err; }
 run 8 bench_8gpu
