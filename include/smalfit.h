@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SMALFIT_ABI_VERSION 3
+#define SMALFIT_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define SMALFIT_API __attribute__((visibility("default")))
@@ -158,6 +158,17 @@ SMALFIT_API const char* smalfit_last_error(smalfit_t h);   /* h may be NULL: las
  * SMALFitter.forward repeats every call); 0: device pointers, copied D2D. */
 SMALFIT_API int smalfit_set_targets(smalfit_t h, int frame0, int n_frames, const uint8_t* sil,
                         const float* joints, const uint8_t* visibility, int from_host, void* stream);
+/* Pipelined uploads (not in the reference, which re-sends its targets inside every forward, smal_fitter.py:118-120):
+ * the handle keeps a second, BACK set of target buffers.  smalfit_stage_targets fills it exactly like
+ * smalfit_set_targets fills the front set, but on any stream -- typically a copy stream, while steps that read the
+ * front set are running.  smalfit_swap_targets exchanges the two sets for every call enqueued afterwards (kernels
+ * already enqueued keep the set they were launched with; a captured CUDA graph keeps the set it was captured with:
+ * *front_index, 0 or 1, tells which one is current).  The caller orders the streams: the first step after a swap waits
+ * for the staging copy (event), and a staging copy waits for the last step that read that set.  Stage every frame the
+ * following steps read: a set holds what was last written into it.  smalfit_set_visibility writes the front set. */
+SMALFIT_API int smalfit_stage_targets(smalfit_t h, int frame0, int n_frames, const uint8_t* sil,
+                          const float* joints, const uint8_t* visibility, int from_host, void* stream);
+SMALFIT_API int smalfit_swap_targets(smalfit_t h, int* front_index /* may be NULL */);
 /* only the visibility rows (optimize_to_joints.py:98-110 rewrites them per stage) */
 SMALFIT_API int smalfit_set_visibility(smalfit_t h, int frame0, int n_frames, const uint8_t* visibility,
                            int from_host, void* stream);

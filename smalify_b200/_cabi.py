@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # a missing file raises below)
 LIB_PATH = os.environ.get("SMALFIT_LIB") or os.path.join(_HERE, "libsmalfit.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 L_JOINT, L_SIL, L_BETAS, L_POSE, L_LIMIT, L_SPLAY, L_TEMPORAL, L_TOTAL = range(8)
 N_TERMS_FUSED = 12          # smalfit_fused_step: + (joint, global, trans) temporal values at [8..10]
 STATUS_POOL_OVERFLOW, STATUS_PEER_TIMEOUT = 1, 2
@@ -86,6 +86,8 @@ def load_library(path: str | None = None) -> C.CDLL:
         "smalfit_fp32_peak": ([vp, _f32p, vp], C.c_int),
         "smalfit_last_error": ([vp], C.c_char_p),
         "smalfit_set_targets": ([vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp], C.c_int),
+        "smalfit_stage_targets": ([vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp], C.c_int),
+        "smalfit_swap_targets": ([vp, C.POINTER(C.c_int)], C.c_int),
         "smalfit_set_visibility": ([vp, C.c_int, C.c_int, vp, C.c_int, vp], C.c_int),
         "smalfit_set_masks": ([vp, _f32p, _f32p], C.c_int),
         "smalfit_set_windows": ([vp, _i32p, C.c_int], C.c_int),
@@ -120,6 +122,7 @@ def load_library(path: str | None = None) -> C.CDLL:
 
 EXPORTED_SYMBOLS = (
     "smalfit_abi_version", "smalfit_create", "smalfit_create_ex", "smalfit_status", "smalfit_fused_step", "smalfit_fp32_peak", "smalfit_destroy", "smalfit_last_error", "smalfit_set_targets",
+    "smalfit_stage_targets", "smalfit_swap_targets",
     "smalfit_set_visibility", "smalfit_set_masks", "smalfit_set_windows", "smalfit_set_joint_limits", "smalfit_set_focal", "smalfit_set_per_frame_shapes",
     "smalfit_loss_grad", "smalfit_temporal", "smalfit_adam_step", "smalfit_adam_reset", "smalfit_render", "smalfit_vertices", "smalfit_render_color",
     "smalfit_peer_init", "smalfit_peer_connect", "smalfit_peer_allreduce", "smalfit_peer_status",
@@ -206,6 +209,7 @@ class Handle:
         self.h = h
         self.max_frames = max_frames
         self.image_size = image_size
+        self.target_set = 0             # which of the two target sets is current (smalfit_swap_targets)
 
     def check(self, rc: int, what: str):
         if rc != 0:
@@ -224,6 +228,19 @@ class Handle:
         if st & STATUS_POOL_OVERFLOW:
             raise SmalfitError("a step needed more (face, tile) entries than the bin pool holds: its silhouette loss and gradient "
                                "were inexact.  Recreate the fitter with a larger pool_entries_per_frame.")
+
+    def stage_targets(self, frame0: int, n: int, sil_ptr, joints_ptr, vis_ptr, from_host: bool, stream_ptr):
+        """smalfit_stage_targets: fills the BACK set of targets on the given stream (raw pointers; the caller keeps the
+        source tensors alive until that stream has passed the copy)."""
+        self.check(self.lib.smalfit_stage_targets(self.h, int(frame0), int(n), sil_ptr, joints_ptr, vis_ptr, 1 if from_host else 0,
+                                                  stream_ptr), "smalfit_stage_targets")
+
+    def swap_targets(self) -> int:
+        """smalfit_swap_targets: the staged set becomes current for every call enqueued from now on."""
+        v = C.c_int(0)
+        self.check(self.lib.smalfit_swap_targets(self.h, C.byref(v)), "smalfit_swap_targets")
+        self.target_set = int(v.value)
+        return self.target_set
 
     def close(self):
         if getattr(self, "h", None):

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/smalfit.h"
@@ -66,6 +67,10 @@ struct smalfit_ctx {
     uint8_t* sil = nullptr; float* kp_target = nullptr; uint8_t* vis = nullptr;
     float* region_tsum = nullptr; float* inv_window = nullptr; float* gmask = nullptr; float* rmask = nullptr;
     float* limit_buf = nullptr;      // [2][102] joint-rotation limits (min, max)
+    // back set of the targets (smalfit_stage_targets / smalfit_swap_targets): allocated on first use
+    uint8_t* sil_back = nullptr; float* kp_back = nullptr; uint8_t* vis_back = nullptr; float* tsum_back = nullptr;
+    bool back_staged = false;
+    int front_index = 0;             // which of the two sets the Workspace points to (0: the one created with the handle)
     bool targets_set = false;
     DevPool pool;
     std::string error;
@@ -287,10 +292,13 @@ int smalfit_create_ex(const smalfit_model_t* md, int device, int max_frames, int
             return fail(nullptr, SMALFIT_EINVAL, "smalfit_create: fragment-list scratch too large for 29-bit cursors (SMALFIT_RT_LISTCAP)");
         }
         h->ts.list = P.alloc<uint2>((size_t)h->tile_ctas * h->ts.list_stride);
-        h->ts.item_next = P.alloc<unsigned>(4, true);
-        h->ts.n_items = h->ts.item_next + 1;
-        h->ts.front_ticket = h->ts.item_next + 2;
-        h->ts.items = P.alloc<uint4>(N * tiles * 8 + 8);
+        h->ts.item_next = P.alloc<unsigned>(8 + RT_ITEM_BINS, true);
+        h->ts.exit_ticket = h->ts.item_next + 1;
+        h->ts.total_cost = reinterpret_cast<unsigned long long*>(h->ts.item_next + 2);       // (8-byte aligned: cudaMalloc base + 8)
+        h->ts.prev_total = reinterpret_cast<unsigned long long*>(h->ts.item_next + 4);
+        h->ts.bin_count = h->ts.item_next + 8;
+        h->ts.bin_cap = (unsigned)(N * tiles * 8);
+        h->ts.items = P.alloc<uint4>((size_t)RT_ITEM_BINS * h->ts.bin_cap + 8);
         h->ts.band_idx = P.alloc<unsigned short>((size_t)h->tile_ctas * RT_WARPS * RT_BAND_MAX);
         const char* e_nsub = getenv("SMALFIT_RT_NSUB");         // tuning knobs for measurements
         const char* e_split = getenv("SMALFIT_RT_SPLITLEN");
@@ -307,6 +315,7 @@ int smalfit_create_ex(const smalfit_model_t* md, int device, int max_frames, int
     w.face_grad = SHIFT(P.alloc<float>(N * m.Fp * 8, true), m.Fp * 8);
     w.dvs = SHIFT(P.alloc<float>(N * V * 3, true), V * 3);
     w.gw = SHIFT(P.alloc<float>(N * V * 3, true), V * 3);
+    w.pose_state = SHIFT(P.alloc<float>(N * POSE_STATE_FLOATS, true), POSE_STATE_FLOATS);
     w.gJ = SHIFT(P.alloc<float>(N * NJ * 3, true), NJ * 3);
     w.gls = SHIFT(P.alloc<float>(N * NLS, true), NLS);
     w.frame_loss = SHIFT(P.alloc<float>(N * 8, true), 8);
@@ -374,22 +383,71 @@ int smalfit_set_per_frame_shapes(smalfit_t h, int enable) {
     return SMALFIT_OK;
 }
 
+namespace {
+// copies one set of targets into (sil, kp, vis) and forms the per-region row sums of the mask into tsum, all on `st`
+int copy_targets(smalfit_t h, uint8_t* d_sil, float* d_kp, uint8_t* d_vis, float* d_tsum, int frame0, int n, const uint8_t* sil,
+                 const float* joints, const uint8_t* visibility, int from_host, cudaStream_t st, const char* who) {
+    const cudaMemcpyKind kind = from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const size_t SS = (size_t)h->S * h->S;
+    cudaError_t e = cudaMemcpyAsync(d_sil + frame0 * SS, sil, n * SS, kind, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_kp + (size_t)frame0 * NKP * 2, joints, (size_t)n * NKP * 2 * sizeof(float), kind, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_vis + (size_t)frame0 * NKP, visibility, (size_t)n * NKP, kind, st);
+    if (e != cudaSuccess) return check_cuda(h, e, who);
+    Workspace wv = h->w;
+    wv.sil = d_sil;
+    launch_region_tsum(wv, frame0, n, d_tsum, st);
+    h->n_launches += 1;
+    return check_launch(h, "region_tsum");
+}
+}  // namespace
+
 int smalfit_set_targets(smalfit_t h, int frame0, int n, const uint8_t* sil, const float* joints,
                         const uint8_t* visibility, int from_host, void* stream) {
     if (!h) return SMALFIT_EINVAL;
     if (!range_ok(h, frame0, n) || !sil || !joints || !visibility) return fail(h, SMALFIT_EINVAL, "smalfit_set_targets: bad arguments");
     cudaSetDevice(h->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    const cudaMemcpyKind kind = from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-    const size_t SS = (size_t)h->S * h->S;
-    cudaError_t e = cudaMemcpyAsync(h->sil + frame0 * SS, sil, n * SS, kind, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h->kp_target + (size_t)frame0 * NKP * 2, joints, (size_t)n * NKP * 2 * sizeof(float), kind, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h->vis + (size_t)frame0 * NKP, visibility, (size_t)n * NKP, kind, st);
-    if (e != cudaSuccess) return check_cuda(h, e, "smalfit_set_targets copy");
-    launch_region_tsum(h->w, frame0, n, h->region_tsum, st);
-    h->n_launches += 1;
+    const int rc = copy_targets(h, h->sil, h->kp_target, h->vis, h->region_tsum, frame0, n, sil, joints, visibility, from_host,
+                                (cudaStream_t)stream, "smalfit_set_targets copy");
+    if (rc == SMALFIT_OK) h->targets_set = true;
+    return rc;
+}
+
+int smalfit_stage_targets(smalfit_t h, int frame0, int n, const uint8_t* sil, const float* joints,
+                          const uint8_t* visibility, int from_host, void* stream) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!range_ok(h, frame0, n) || !sil || !joints || !visibility) return fail(h, SMALFIT_EINVAL, "smalfit_stage_targets: bad arguments");
+    cudaSetDevice(h->device);
+    if (!h->sil_back) {          // second set, same shape and frame shift as the first (smalfit_create_ex)
+        const size_t N = (size_t)h->frame_cap, B = (size_t)h->frame_base, SS = (size_t)h->S * h->S;
+        const size_t per_t = (size_t)h->w.tiles_x * h->w.tiles_y * REGIONS_PER_TILE * REGION_H;
+        uint8_t* a = h->pool.alloc<uint8_t>(N * SS, true);
+        float* b = h->pool.alloc<float>(N * NKP * 2, true);
+        uint8_t* c = h->pool.alloc<uint8_t>(N * NKP, true);
+        float* d = h->pool.alloc<float>(N * per_t, true);
+        if (h->pool.err != cudaSuccess) {
+            const cudaError_t e = h->pool.err;
+            h->pool.err = cudaSuccess;           // (the handle stays usable with its one set)
+            return check_cuda(h, e, "smalfit_stage_targets: allocating the second set of targets");
+        }
+        h->sil_back = a - B * SS; h->kp_back = b - B * NKP * 2; h->vis_back = c - B * NKP; h->tsum_back = d - B * per_t;
+    }
+    const int rc = copy_targets(h, h->sil_back, h->kp_back, h->vis_back, h->tsum_back, frame0, n, sil, joints, visibility, from_host,
+                                (cudaStream_t)stream, "smalfit_stage_targets copy");
+    if (rc == SMALFIT_OK) h->back_staged = true;
+    return rc;
+}
+
+int smalfit_swap_targets(smalfit_t h, int* front_index) {
+    if (!h) return SMALFIT_EINVAL;
+    if (!h->back_staged) return fail(h, SMALFIT_ESTATE, "smalfit_swap_targets: nothing was staged (smalfit_stage_targets)");
+    std::swap(h->sil, h->sil_back); std::swap(h->kp_target, h->kp_back); std::swap(h->vis, h->vis_back);
+    std::swap(h->region_tsum, h->tsum_back);
+    h->w.sil = h->sil; h->w.kp_target = h->kp_target; h->w.vis = h->vis; h->w.region_tsum = h->region_tsum;
+    h->back_staged = h->targets_set;     // the old front is a complete set again (if it ever was)
     h->targets_set = true;
-    return check_launch(h, "region_tsum");
+    h->front_index ^= 1;
+    if (front_index) *front_index = h->front_index;
+    return SMALFIT_OK;
 }
 
 int smalfit_set_visibility(smalfit_t h, int frame0, int n, const uint8_t* visibility, int from_host, void* stream) {

@@ -21,6 +21,7 @@
 #include "smalfit_kernels.cuh"
 
 #include <cooperative_groups.h>
+#include <cstddef>
 #include <cstdio>
 namespace cg = cooperative_groups;
 
@@ -99,6 +100,32 @@ __device__ float block_sum(float v, float* red /* >= 33 floats */) {
     return red[32];
 }
 
+// block sums of N floats per thread at once (the two-level tree of block_sum, value for value the same order: one barrier
+// pair instead of three per value, one copy of the code); results valid in all threads.  red: >= 32 * N + N floats
+template <int N>
+__device__ __forceinline__ void block_sum_n(float (&v)[N], float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) red[wid * N + k] = v[k];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            float t = (lane < nw) ? red[lane * N + k] : 0.f;
+            t = warp_sum(t);
+            if (lane == 0) red[32 * N + k] = t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = red[32 * N + k];
+}
+
 // ---------------------------------------------------------------------------
 // shape_forward: v_shaped[slot][i] = v_template[i] + sum_k betas[slot][k] shapedirs[k][i]
 // ---------------------------------------------------------------------------
@@ -143,6 +170,12 @@ struct FrameSmem {
     float prior_g[NJ * 3];  // frame_backward: gradient of pose prior + splay + joint limits (formed by another CTA of the cluster)
     float prior_l[4];       //                 and their loss values (pose, splay, limit)
 };
+
+// the part of FrameSmem frame_pose_forward produces (R ... tr, contiguous): frame_front stores it, frame_backward reloads it
+// instead of running the chain again (the same parameters: one step)
+constexpr int POSE_STATE_FLOATS_ = NJ * (9 + 9 + 3 + 3 + 3 + 9 + 3 + 3) + NLS + 3;
+static_assert(POSE_STATE_FLOATS_ == POSE_STATE_FLOATS, "pose state layout");
+static_assert(offsetof(FrameSmem, mj) == sizeof(float) * POSE_STATE_FLOATS, "pose state must be the head of FrameSmem");
 
 __device__ __forceinline__ ChainFwd chain_of(FrameSmem& S) {
     ChainFwd c;
@@ -214,89 +247,37 @@ __device__ __forceinline__ void bin_segment(const ModelDev& m, int seg_id, int& 
     f_hi = min(f_lo + seg, m.Fp);
 }
 
-// Hand-out list of the tile rasteriser: every (frame, tile) becomes 1, 2, 4 or 8 items (bands of rows) so that no
-// item holds more than about 1/fair of a CTA's fair share of the launch's (pixel, face) pairs (bin_faces counts them
-// per tile), ordered by decreasing pairs per item (counting sort into 256 classes; the order inside a class does not
-// matter: items are independent).  Also resets the hand-out counter.  One CTA (the last one of frame_front to finish).
-constexpr int RT_ITEM_CLASSES = 256;
-__device__ void build_items_block(const Workspace& w, const TileScratch& ts, int frame0, int n_frames, int n_ctas, bool keep_empty) {
-    __shared__ unsigned hist[RT_ITEM_CLASSES];
-    __shared__ unsigned long long red[32];
-    __shared__ unsigned s_cmax;
-    const int tid = threadIdx.x, T = w.tiles_x * w.tiles_y, NT = n_frames * T;
-    const unsigned* tcost = w.tile_cost + (size_t)frame0 * T;
-    for (int i = tid; i < RT_ITEM_CLASSES; i += blockDim.x) hist[i] = 0u;
-    // (this block runs alone at the end of frame_front: tile costs are fetched in batches of independent loads)
-    constexpr int U = 8;
-    unsigned long long tot = 0ull;
-    for (int base = 0; base < NT; base += (int)blockDim.x * U) {
-        unsigned c[U];
-#pragma unroll
-        for (int q = 0; q < U; ++q) { const int i = base + q * (int)blockDim.x + tid; c[q] = (i < NT) ? tcost[i] : 0u; }
-#pragma unroll
-        for (int q = 0; q < U; ++q) tot += c[q];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if ((tid & 31) == 0) red[tid >> 5] = tot;
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long a = 0ull;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += red[i];
-        const unsigned long long cmax = a / (unsigned long long)((ts.fair > 0 ? ts.fair : RT_FAIR) * n_ctas);
-        const unsigned long long floor_ = (unsigned long long)(ts.min_item > 0 ? ts.min_item : RT_MIN_ITEM);
-        const unsigned long long ceil_ = (unsigned long long)(ts.fair > 0 ? 1u << 30 : RT_MAX_ITEM);      // (an explicit fair share is taken literally)
-        const unsigned long long cm = cmax < floor_ ? floor_ : (cmax > ceil_ ? ceil_ : cmax);
-        s_cmax = ts.split_len > 0 ? (unsigned)ts.split_len : (unsigned)cm;
-    }
-    __syncthreads();
-    const unsigned cmax = s_cmax;
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int base = 0; base < NT; base += (int)blockDim.x * U) {
-            unsigned c[U];
-#pragma unroll
-            for (int q = 0; q < U; ++q) { const int i = base + q * (int)blockDim.x + tid; c[q] = (i < NT) ? tcost[i] : 0u; }
-#pragma unroll
-            for (int q = 0; q < U; ++q) {
-                const int i = base + q * (int)blockDim.x + tid;
-                const unsigned cost = c[q];
-                if (i >= NT || (cost == 0u && !keep_empty)) continue;            // (frame_front has finished the tiles no face reaches)
-                unsigned lg = 0u;                                   // bands: 1 << lg
-                while (lg < 3u && ((cost >> lg) > cmax || (cost >> lg) > (unsigned)ts.list_cap)) ++lg;     // (and keep the lists in one pass)
-                if (ts.nsub > 0) { lg = 0u; while ((1 << lg) < ts.nsub) ++lg; if (cost <= cmax) lg = 0u; }      // forced (measurements)
-                const unsigned long long per = cost >> lg;
-                const unsigned cls = (RT_ITEM_CLASSES - 1) - (unsigned)min(per * 128ull / cmax, (unsigned long long)(RT_ITEM_CLASSES - 1));   // big items first
-                if (pass == 0) {
-                    atomicAdd(&hist[cls], 1u << lg);
-                } else {
-                    const unsigned pos = atomicAdd(&hist[cls], 1u << lg);
-                    // (the tile's slice of the frame's pool, clamped like every reader of tile_off clamps it)
-                    const unsigned* toff = w.tile_off + (size_t)(frame0 + i / T) * (T + 1);
-                    const unsigned off = min(toff[i % T], (unsigned)w.pool_cap), len = min(toff[i % T + 1], (unsigned)w.pool_cap) - off;
-                    for (unsigned b = 0; b < (1u << lg); ++b)
-                        ts.items[pos + b] = make_uint4(((unsigned)(i / T) << 15) | ((unsigned)(i % T) << 5) | (b << 2) | lg, off, len, 0u);
-                }
-            }
-        }
-        __syncthreads();
-        if (pass == 0) {
-            // exclusive prefix over the classes (one warp, 8 classes per lane)
-            if (tid < 32) {
-                constexpr int PER = RT_ITEM_CLASSES / 32;
-                unsigned v[PER], sum = 0u;
-#pragma unroll
-                for (int q = 0; q < PER; ++q) { v[q] = hist[tid * PER + q]; sum += v[q]; }
-                unsigned incl = sum;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += y; }
-                unsigned run = incl - sum;
-#pragma unroll
-                for (int q = 0; q < PER; ++q) { hist[tid * PER + q] = run; run += v[q]; }
-                if (tid == 31) { *ts.n_items = incl; *ts.item_next = 0u; }
-            }
-            __syncthreads();
-        }
-    }
+// Hand-out list of the tile rasteriser.  Every non-empty (frame, tile) becomes 1, 2, 4 or 8 items (bands of rows) so that
+// no item holds more than about 1/fair of a CTA's fair share of a launch's (pixel, face) pairs, and the rasteriser's
+// persistent CTAs draw the items largest first.  Every frame emits its own items (CTA 0 of its cluster, right after the
+// tile offsets are known) into RT_ITEM_BINS size classes of one global array: a slot is reserved with an integer atomic
+// on the class counter, the rasteriser walks the classes from the largest down.  There is no serial pass over all frames'
+// tiles: an earlier version built a sorted list in the last CTA to finish, a 10 us (16 frames) ... 35 us (128 frames) tail
+// on one SM after every other SM had gone idle.  The price: the fair share is taken from the PREVIOUS launch's pair total
+// (ts.prev_total; the total moves by a fraction of a per cent between optimiser steps; the very first launch uses the
+// minimum item size), and the order inside a class is the order of arrival -- items are independent, so neither changes
+// a result, only the schedule.
+__device__ __forceinline__ unsigned item_size_limit(const TileScratch& ts, int n_ctas) {
+    const unsigned long long a = *(volatile unsigned long long*)ts.prev_total;
+    const unsigned long long share = a / (unsigned long long)((ts.fair > 0 ? ts.fair : RT_FAIR) * n_ctas);
+    const unsigned long long floor_ = (unsigned long long)(ts.min_item > 0 ? ts.min_item : RT_MIN_ITEM);
+    const unsigned long long ceil_ = (unsigned long long)(ts.fair > 0 ? 1u << 30 : RT_MAX_ITEM);      // (an explicit fair share is taken literally)
+    const unsigned long long cm = share < floor_ ? floor_ : (share > ceil_ ? ceil_ : share);
+    return ts.split_len > 0 ? (unsigned)ts.split_len : (unsigned)cm;
+}
+__device__ __forceinline__ void emit_items(const TileScratch& ts, unsigned cmax, unsigned f, unsigned t, unsigned cost, unsigned off, unsigned len) {
+    unsigned lg = 0u;                                   // bands: 1 << lg
+    while (lg < 3u && ((cost >> lg) > cmax || (cost >> lg) > (unsigned)ts.list_cap)) ++lg;     // (and keep the lists in one pass)
+    if (ts.nsub > 0) { lg = 0u; while ((1 << lg) < ts.nsub) ++lg; if (cost <= cmax) lg = 0u; }      // forced (measurements)
+    // size class of one item, class 0 = largest (bands that stay above the limit: they cannot be cut further), then two
+    // classes per octave below it: what the order has to get right is that the launch ENDS with its smallest items (the
+    // last classes are a few hundred pairs wide), not the order among the big ones that are handed out first anyway.
+    // Measured against linear classes and a linear / logarithmic mix at 128, 32 and 16 frames (profiles/r02_ab_experiments.txt).
+    const float r = (float)(cost >> lg) / (float)cmax;
+    const unsigned bin = (r >= 1.f) ? 0u : min(1u + (unsigned)(-2.f * __log2f(fmaxf(r, 1e-6f))), (unsigned)(RT_ITEM_BINS - 1));
+    const unsigned pos = atomicAdd(ts.bin_count + bin, 1u << lg);
+    uint4* dst = ts.items + (size_t)bin * ts.bin_cap + pos;
+    for (unsigned b = 0; b < (1u << lg); ++b) dst[b] = make_uint4((f << 15) | (t << 5) | (b << 2) | lg, off, len, 0u);
 }
 
 
@@ -349,6 +330,13 @@ frame_front_kernel(ModelDev m, Workspace w, TileScratch ts, Params p, int frame0
 
     PHASE_CLOCK_DECL
     frame_pose_forward(S, m, w, p, fr, slot, (w.n_shapes == 1) ? 0 : fr);
+#ifndef NO_POSE_RELOAD
+    if (crank == 0) {                                 // kept for frame_backward of the same step
+        float* ps = w.pose_state + (size_t)fr * POSE_STATE_FLOATS;
+        const float* src = reinterpret_cast<const float*>(&S);
+        for (int i = tid; i < POSE_STATE_FLOATS; i += FRONT_THREADS) ps[i] = src[i];
+    }
+#endif
     PHASE_CLOCK()   /* pose chain */
     const float focal = w.focal ? *w.focal : CAM_F;
 
@@ -439,6 +427,7 @@ frame_front_kernel(ModelDev m, Workspace w, TileScratch ts, Params p, int frame0
     unsigned* cost = cnt + FRONT_WARPS * T;           // [T] (pixel, face) pairs per tile, this CTA's faces
     unsigned* tot = cost + T;                         // [T] entries per tile, then tile offsets
     unsigned* before = tot + T;                       // [T] entries of the CTAs (= face segments) before this one
+    unsigned* tcs = before + T;                       // [T] (pixel, face) pairs per tile, whole frame (CTA 0)
     __shared__ unsigned part[FRONT_THREADS];
 
     const int seg_id = crank * FRONT_WARPS + wid;
@@ -487,7 +476,11 @@ frame_front_kernel(ModelDev m, Workspace w, TileScratch ts, Params p, int frame0
                 cs += rcnt[c][FRONT_WARPS * T + t];
             }
             tot[t] = a; before[t] = b;
-            if (crank == 0) w.tile_cost[(size_t)fr * T + t] = cs;
+            if (crank == 0) {
+                w.tile_cost[(size_t)fr * T + t] = cs;
+                tcs[t] = cs;
+                if (cs) atomicAdd(ts.total_cost, (unsigned long long)cs);      // (integer: order-independent; the next launch's fair share)
+            }
         }
     }
     __syncthreads();
@@ -518,18 +511,38 @@ frame_front_kernel(ModelDev m, Workspace w, TileScratch ts, Params p, int frame0
         const int nq = (T * RPT + FRONT_CTAS - 1) / FRONT_CTAS;
         const int i_hi = min(T * RPT, (crank + 1) * nq);
         const size_t base = (size_t)fr * T * RPT;
-        for (int i = crank * nq + tid; i < i_hi; i += FRONT_THREADS)
-            if (tot[i / RPT] == 0u) w.region_l1[base + i] = w.region_tsum[base + i];
+        for (int i0 = crank * nq + tid; i0 < i_hi; i0 += 4 * FRONT_THREADS) {      // (independent loads first: a cold read each)
+            float v[4];
+            bool e[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k * FRONT_THREADS;
+                e[k] = i < i_hi && tot[i / RPT] == 0u;
+                v[k] = e[k] ? w.region_tsum[base + i] : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (e[k]) w.region_l1[base + i0 + k * FRONT_THREADS] = v[k];
+        }
     }
     cluster.sync();                                   // nobody reads another CTA's counts from here on
     {
         unsigned* toff = w.tile_off + (size_t)fr * (T + 1);
         unsigned run = part[tid];
+        const unsigned cmax_items = (crank == 0) ? item_size_limit(ts, n_ctas) : 0u;
         for (int k = 0; k < per; ++k) {
             const int t = tid * per + k;
             if (t < T) {
                 const unsigned n_t = tot[t];
-                if (crank == 0) toff[t] = run;
+                if (crank == 0) {
+                    toff[t] = run;
+                    // this tile's work items (tiles no face reaches were finished above, unless alpha itself is wanted);
+                    // the tile's slice of the frame's pool is clamped like every reader of tile_off clamps it
+                    if (n_t > 0u || do_bin == 2) {
+                        const unsigned off = min(run, (unsigned)w.pool_cap);
+                        emit_items(ts, cmax_items, (unsigned)blockIdx.y, (unsigned)t, tcs[t], off, min(run + n_t, (unsigned)w.pool_cap) - off);
+                    }
+                }
                 unsigned cur = run + before[t];
 #pragma unroll
                 for (int q = 0; q < FRONT_WARPS; ++q) { const unsigned c = cnt[q * T + t]; cnt[q * T + t] = cur; cur += c; }   // counts -> cursors
@@ -595,30 +608,13 @@ frame_front_kernel(ModelDev m, Workspace w, TileScratch ts, Params p, int frame0
             }
         }
     }
-    PHASE_CLOCK() PHASE_CLOCK_PRINT("frame_front [pose lbs joints sync1 kp count+sync2 scan fill]", blockIdx.y == 0 && crank == 0 && tid == 0)
     if (dropped) atomicAdd(w.counters + 2, (unsigned long long)dropped);
     PHASE_CLOCK()   /* fill */
-    // the last frame to finish its binning builds the rasteriser's hand-out list from every frame's tile costs
-    // (CTA 0 of a cluster wrote its frame's tile_cost; each takes one ticket when it is done)
-    if (crank == 0) {
-        __shared__ bool s_last_frame;
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            s_last_frame = (atomicAdd(ts.front_ticket, 1u) == (unsigned)n_frames - 1u);
-        }
-        __syncthreads();
-        if (s_last_frame) {
-            __threadfence();
-            if (tid == 0) *ts.front_ticket = 0u;
-            build_items_block(w, ts, frame0, n_frames, n_ctas, do_bin == 2);
-        }
-    }
-    PHASE_CLOCK_PRINT("frame_front [pose lbs joints sync1 kp count+sync2 scan fill]", blockIdx.y == 0 && crank == 0 && tid == 0)
+    PHASE_CLOCK_PRINT("frame_front [pose lbs joints sync1 kp count+sync2 scan+items fill]", blockIdx.y == 0 && crank == 0 && tid == 0)
 }
 
 size_t frame_front_smem_bytes(const Workspace& w) {
-    return sizeof(FrameSmem) + (size_t)(FRONT_WARPS + 3) * w.tiles_x * w.tiles_y * sizeof(unsigned);
+    return sizeof(FrameSmem) + (size_t)(FRONT_WARPS + 4) * w.tiles_x * w.tiles_y * sizeof(unsigned);
 }
 
 void launch_frame_front(const ModelDev& m, const Workspace& w, const TileScratch& ts, const Params& p, int frame0, int n, Weights wt,
@@ -668,8 +664,14 @@ namespace smf {
 #ifndef BW_PACK_MIN
 #define BW_PACK_MIN 33          // rectangles of at least this many pixels are swept two pixels per lane (packed FP32)
 #endif
+// One warp per CTA, 32 CTAs per SM (64 registers): a CTA's slot is free again the moment its face is done (8-warp CTAs
+// held theirs until the largest of 8 rectangles was swept: 43.6 of 50 % occupancy achieved), and with the warp index
+// out of the picture the kernel fits 64 registers without the 33 spill loads / stores it had (0.896 -> 0.792 ms).
+#ifndef BW_WARPS
+#define BW_WARPS 1              // warps (= faces) per CTA
+#endif
 #ifndef BW_MIN_CTAS
-#define BW_MIN_CTAS 4           // resident CTAs per SM the register allocation aims for (64 registers: measured best)
+#define BW_MIN_CTAS (32 / BW_WARPS)     // resident CTAs per SM the register allocation aims for (32 warps, 64 registers: measured best)
 #endif
 
 struct BwFace {                 // what a sweep needs beside the prepared face
@@ -751,7 +753,7 @@ __device__ __forceinline__ void bw_sweep2(const FaceSetup& fs, const BwFace& b, 
     }
 }
 
-__global__ void __launch_bounds__(256, BW_MIN_CTAS) raster_backward_kernel(ModelDev m, Workspace w, int frame0) {
+__global__ void __launch_bounds__(32 * BW_WARPS, BW_MIN_CTAS) raster_backward_kernel(ModelDev m, Workspace w, int frame0) {
     grid_dep_wait();
     const int lane = threadIdx.x & 31;
     const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -811,8 +813,8 @@ __global__ void __launch_bounds__(256, BW_MIN_CTAS) raster_backward_kernel(Model
 }
 
 void launch_raster_backward(const ModelDev& m, const Workspace& w, int frame0, int n, cudaStream_t st) {
-    dim3 grid((m.Fp + 7) / 8, n);
-    launch_pdl(raster_backward_kernel, grid, dim3(256), 0, st, m, w, frame0);
+    dim3 grid((m.Fp + BW_WARPS - 1) / BW_WARPS, n);
+    launch_pdl(raster_backward_kernel, grid, dim3(32 * BW_WARPS), 0, st, m, w, frame0);
 }
 
 // ---------------------------------------------------------------------------
@@ -843,7 +845,15 @@ frame_backward_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, We
     FrameSmem* S0 = cluster.map_shared_rank(&S, 0);   // CTA 0's copy: receives the partial results
     PHASE_CLOCK_DECL
 
+#ifndef NO_POSE_RELOAD
+    {                                                 // the pose state frame_front left for this frame (same parameters)
+        const float* ps = w.pose_state + (size_t)fr * POSE_STATE_FLOATS;
+        float* dst = reinterpret_cast<float*>(&S);
+        for (int i = tid; i < POSE_STATE_FLOATS; i += BACK_THREADS) dst[i] = ps[i];
+    }
+#else
     frame_pose_forward(S, m, w, p, fr, slot, (w.n_shapes == 1) ? 0 : fr);
+#endif
     PHASE_CLOCK()   /* pose chain */
     if (tid < NMJ * 3) S.gj[tid] = w.gjoint[(size_t)fr * NMJ * 3 + tid];
     __syncthreads();
@@ -1110,12 +1120,29 @@ shape_backward_kernel(ModelDev m, Workspace w, int frame0, int n_frames, int n_b
     const int fa = (w.n_shapes == 1) ? frame0 : slot, fb = (w.n_shapes == 1) ? frame0 + n_frames : slot + 1;
     float gsum = 0.f;
     if (i < n) {
-        for (int fr = fa; fr < fb; ++fr) gsum += w.dvs[(size_t)fr * n + i];
+        // (frames are summed in order; 16 independent loads in flight per round instead of the compiler's 4)
+        int fr = fa;
+        for (; fr + 16 <= fb; fr += 16) {
+            float q[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) q[k] = w.dvs[(size_t)(fr + k) * n + i];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) gsum += q[k];
+        }
+        for (; fr < fb; ++fr) gsum += w.dvs[(size_t)fr * n + i];
         const int v = i / 3, c = i - v * 3;
         for (int e = m.jregT_ptr[v]; e < m.jregT_ptr[v + 1]; ++e) {
             const int j = m.jregT_joint[e];
             float gj = 0.f;
-            for (int fr = fa; fr < fb; ++fr) gj += w.gJ[(size_t)fr * NJ * 3 + j * 3 + c];
+            int f2 = fa;
+            for (; f2 + 8 <= fb; f2 += 8) {
+                float q[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) q[k] = w.gJ[(size_t)(f2 + k) * NJ * 3 + j * 3 + c];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) gj += q[k];
+            }
+            for (; f2 < fb; ++f2) gj += w.gJ[(size_t)f2 * NJ * 3 + j * 3 + c];
             gsum = fmaf(m.jregT_weight[e], gj, gsum);
         }
     }
@@ -1139,8 +1166,8 @@ __global__ void __launch_bounds__(256)
 finalize_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, int n_frames, Weights wt,
                 int prior_windows, int n_blocks, float* loss_terms) {
     grid_dep_wait();
-    __shared__ float red[40];
-    __shared__ float diff[32], res[32];
+    __shared__ float red[33 * 9];
+    __shared__ float diff[32], res[32], psum[NBETA + NLS];
     __shared__ bool s_last;
     const int tid = threadIdx.x;
     const int pslot = (w.n_shapes == 1) ? 0 : frame0 + blockIdx.x;      // parameter slot / workspace slot, see shape_forward
@@ -1163,10 +1190,22 @@ finalize_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, int n_fr
         }
         __syncthreads();
     }
+    {
+        // the cross-block / cross-frame sums behind dL/dbetas and dL/dlog_beta_scales: a warp per value, lanes strided over
+        // the partials, fixed tree (a serial loop of 128 dependent loads per value was most of this kernel's time)
+        const int lane = tid & 31, fa = (w.n_shapes == 1) ? frame0 : slot, fb = (w.n_shapes == 1) ? frame0 + n_frames : slot + 1;
+        for (int k = tid >> 5; k < NBETA + NLS; k += (int)(blockDim.x >> 5)) {
+            float a = 0.f;
+            if (k < NBETA) { for (int q = lane; q < n_blocks; q += 32) a += w.beta_partial[((size_t)slot * n_blocks + q) * NBETA + k]; }
+            else { for (int fr = fa + lane; fr < fb; fr += 32) a += w.gls[fr * NLS + (k - NBETA)]; }
+            a = warp_sum(a);
+            if (lane == 0) psum[k] = a;
+        }
+        __syncthreads();
+    }
     if (in_range) {
         if (tid < NBETA && g.betas) {
-            float t = 0.f;
-            for (int q = 0; q < n_blocks; ++q) t += w.beta_partial[((size_t)slot * n_blocks + q) * NBETA + tid];
+            float t = psum[tid];
             if (prior) {
                 float a = 0.f;
                 for (int k = 0; k < D; ++k) a = fmaf(m.shape_prec[tid * D + k], res[k], a);
@@ -1176,9 +1215,7 @@ finalize_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, int n_fr
         }
         if (tid >= 32 && tid < 32 + NLS && g.logscale) {
             const int k = tid - 32;
-            const int fa = (w.n_shapes == 1) ? frame0 : slot, fb = (w.n_shapes == 1) ? frame0 + n_frames : slot + 1;
-            float t = 0.f;
-            for (int fr = fa; fr < fb; ++fr) t += w.gls[fr * NLS + k];
+            float t = psum[NBETA + k];
             if (prior && D > NBETA) {       // the log-scale entries live at index 20+k of the 26-d residual
                 float a = 0.f;
                 for (int kk = 0; kk < D; ++kk) a = fmaf(m.shape_prec[(NBETA + k) * D + kk], res[kk], a);
@@ -1207,11 +1244,12 @@ finalize_kernel(ModelDev m, Workspace w, Params p, Grads g, int frame0, int n_fr
         ll += w.frame_loss[fr * 8 + 4];
         if (wt.temp > 0.f) { ltj += w.frame_loss[fr * 8 + 5]; ltg += w.frame_loss[fr * 8 + 6]; ltt += w.frame_loss[fr * 8 + 7]; }
     }
-    if (wt.temp > 0.f) { ltj = block_sum(ltj, red); ltg = block_sum(ltg, red); ltt = block_sum(ltt, red); }
     for (int q = tid; q < (int)gridDim.x; q += blockDim.x) lb += ((volatile float*)w.slot_loss)[(w.n_shapes == 1) ? w.slot0 : frame0 + q];
-    lk = block_sum(lk, red); lp = block_sum(lp, red); lsp = block_sum(lsp, red); lsil = block_sum(lsil, red);
-    lb = block_sum(lb, red);
-    ll = block_sum(ll, red);
+    {
+        float v9[9] = {lk, lp, lsp, lsil, lb, ll, ltj, ltg, ltt};
+        block_sum_n<9>(v9, red);
+        lk = v9[0]; lp = v9[1]; lsp = v9[2]; lsil = v9[3]; lb = v9[4]; ll = v9[5]; ltj = v9[6]; ltg = v9[7]; ltt = v9[8];
+    }
     if (w.gfocal) {          // dL/dfocal: fixed-order sum of the per-frame partials
         float a = 0.f;
         for (int f = tid; f < n_frames; f += blockDim.x) {
@@ -1627,7 +1665,7 @@ cudaError_t configure_kernels(const ModelDev& m) {
     cudaError_t e = cudaFuncSetAttribute(frame_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameSmem));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(frame_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(sizeof(FrameSmem) + (size_t)(FRONT_WARPS + 3) * MAX_TILES * sizeof(unsigned)));
+                             (int)(sizeof(FrameSmem) + (size_t)(FRONT_WARPS + 4) * MAX_TILES * sizeof(unsigned)));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(raster_tile_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_tile_smem_bytes());
 }

@@ -23,7 +23,7 @@ constexpr int RT_PLANE = RT_PITCH * (TILE_H + 1) + 3;      // words per plane (3
 constexpr int RT_BLK = 16;                  // prepared faces per TMA block
 constexpr int RT_BAND_MAX = 2048;           // faces of one warp's range whose positions a band item compacts (longer ranges: streamed whole)
 constexpr int MAX_TILES = 1024;             // 32x32 tiles per frame (image side <= 1024)
-// item-size rule of the tile rasteriser's hand-out list (build_items)
+// item-size rule of the tile rasteriser's work items (emit_items in frame_front)
 constexpr int RT_FAIR = 2;                      // a hand-out item holds at most 1/RT_FAIR of a CTA's fair share of the pairs ...
 constexpr int RT_MAX_ITEM = 64000;              // ... but never more pairs than this: the fragment lists of the items in flight
                                                 // (n_ctas x ~0.6 x 8 B per pair) should fit the 126 MB L2 (measured at 128 frames:
@@ -32,6 +32,8 @@ constexpr int RT_MIN_ITEM = 16000;              // ... and no tile is cut into b
                                                 // measured best at 16 / 32 / 64 frames per GPU: 16 k / 32 k / 48 k pairs)
 
 constexpr int MAX_LEVELS = 16;
+constexpr int RT_ITEM_BINS = 24;              // size classes of the rasteriser's work items (emit_items)
+constexpr int POSE_STATE_FLOATS = NJ * 42 + NLS + 3;   // R, Rw, s, t, J, G, off, theta per joint + log-scales + translation (FrameSmem's head)
 constexpr int SKIN_CHUNK = 96, MAX_SKIN_CHUNKS = 192;
 constexpr float P_SKIP = 2.98023224e-8f;    // 2^-25: below this 1-P rounds to 1.0f in fp32
 
@@ -97,6 +99,7 @@ struct Workspace {
     float* face_grad;           // [N][Fp][8] (gx0,gy0,gx1,gy1,gx2,gy2,-,-)
     float* dvs;                 // [N][V*3]  per-frame dL/dv_shaped
     float* gw;                  // [N][V*3]  per-frame dL/d(world vertices) (frame_backward, read across its cluster)
+    float* pose_state;          // [N][POSE_STATE_FLOATS] rotations, chain and skinning transforms of the frame (frame_front -> frame_backward)
     float* gJ;                  // [N][105]  per-frame dL/dJ(rest joints)
     float* gls;                 // [N][6]    per-frame dL/dlogscale
     float* frame_loss;          // [N][8]    kp, pose, splay, silhouette, joint limit, temporal (joint, global, trans)
@@ -138,9 +141,12 @@ struct TileScratch {        // tile rasteriser: per resident CTA
     int list_cap;           // entries one pass may use before the tile is split into further passes
     int list_stride;        // list_cap + Fp
     unsigned* item_next;    // [1] next item to hand out
-    unsigned* n_items;      // [1]
-    unsigned* front_ticket; // [1] frames whose binning is complete (the last one builds the hand-out list)
-    uint4* items;           // [N * tiles * 8] (frame << 15 | tile << 5 | band << 2 | log2(bands), list offset, list length, -)   (build_items)
+    unsigned* bin_count;    // [RT_ITEM_BINS] items per size class (class 0 = largest), filled by frame_front, cleared by the rasteriser
+    unsigned* exit_ticket;  // [1] rasteriser CTAs that have finished (the last one clears the counters)
+    unsigned long long* total_cost;   // [1] (pixel, face) pairs of the launch, added up tile by tile (integer atomics)
+    unsigned long long* prev_total;   // [1] the previous launch's total: the item-size rule's fair share
+    uint4* items;           // [RT_ITEM_BINS][bin_cap] (frame << 15 | tile << 5 | band << 2 | log2(bands), list offset, list length, -)
+    unsigned bin_cap;       // = frames * tiles * 8: every item of a launch would fit one class
     unsigned short* band_idx;   // [n_ctas][RT_WARPS][RT_BAND_MAX] band items: list positions of the faces that reach the band
     int nsub;               // > 0: force this many bands for every list longer than split_len (measurements)
     int fair;               // > 0: overrides RT_FAIR (and lifts RT_MAX_ITEM)

@@ -5,7 +5,7 @@
 // silhouette term of smal_fitter/smal_fitter.py:172-173.  Outputs: per pixel (coef, depth threshold, tie
 // face id) for raster_backward, per region row sum|alpha - T|, optionally alpha itself.
 //
-// Work item (build_items, run by the last CTA of frame_front) = one 32x32-pixel tile of one frame, or one band of rows
+// Work item (emit_items: every frame's cluster in frame_front emits its own) = one 32x32-pixel tile of one frame, or one band of rows
 // of a tile that holds more than the item-size rule allows (RT_FAIR / RT_MIN_ITEM / RT_MAX_ITEM); items are handed out
 // largest first to persistent CTAs of 8 warps, 3 CTAs per SM.  The tile's face list (frame_front's binning, ascending
 // face id) is split into 8 contiguous ranges of equal cost, one per warp, and every warp is *face-parallel*:
@@ -64,7 +64,8 @@ struct RtSmem {
     unsigned chunk[RT_MAXCHUNK];         // cost of each RT_BLK-entry chunk of the tile list, then its exclusive prefix
     unsigned char cls[RT_PIX];           // pixel class in the current pass
     unsigned cost_total;
-    int item;
+    long long item;                      // index into ts.items of the item being processed, -1: none left
+    unsigned bin_end[RT_ITEM_BINS];      // items of the size classes 0 .. b (inclusive prefix)
     unsigned n_active, total, p2_next;
     unsigned n_mid;                      // listed pixels with RT_SELCAP < c <= RT_MIDCAP: kept at the back of active[]
     int t_f, t_tile, t_len;              // current item (kept here across the sweep, which needs the registers)
@@ -377,14 +378,25 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
     // The hand-out counter is a global atomic (~1 us round trip with the whole CTA waiting) and the item's record one more
     // dependent load.  (Drawing the next item ahead -- at the start of an item in round 1, after its sweep in round 2 -- was
     // measured worse both times, +2 ... +7 %: items reserved by busy CTAs are missing from the tail of the launch.)
-    const unsigned n_items = *ts.n_items;
+    // Items sit in RT_ITEM_BINS size classes, class 0 = largest (emit_items in frame_front): the k-th draw takes the k-th item
+    // of the classes laid end to end.
+    if (threadIdx.x < RT_ITEM_BINS) {
+        unsigned end = 0u;
+        for (int b = 0; b <= (int)threadIdx.x; ++b) end += ts.bin_count[b];
+        sm.bin_end[threadIdx.x] = end;
+    }
     for (;;) {
-        __syncthreads();                 // the previous item's shared state is no longer read
-        if (threadIdx.x == 0) sm.item = (int)atomicAdd(ts.item_next, 1u);
+        __syncthreads();                 // the previous item's shared state is no longer read (first round: bin_end is written)
+        if (threadIdx.x == 0) {
+            const unsigned k = atomicAdd(ts.item_next, 1u);
+            int b = 0;
+            while (b < RT_ITEM_BINS && k >= sm.bin_end[b]) ++b;
+            sm.item = (b < RT_ITEM_BINS) ? (long long)b * ts.bin_cap + (k - (b ? sm.bin_end[b - 1] : 0u)) : -1ll;
+        }
         __syncthreads();
-        const unsigned item = (unsigned)sm.item;
-        if (item >= n_items) break;
-        // item = one tile of one frame, or one band of rows of a tile with a long list (build_items): code, list offset, length
+        const long long item = sm.item;
+        if (item < 0) break;
+        // item = one tile of one frame, or one band of rows of a tile with a long list: code, list offset, length
         const uint4 rec = ts.items[item];
         const unsigned code = rec.x;
         const int f = (int)(code >> 15), fr = frame0 + f, tile = (int)((code >> 5) & 0x3ffu);
@@ -773,9 +785,21 @@ raster_tile_forward_kernel(ModelDev m, Workspace w, TileScratch ts, int frame0, 
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0 && (sm.n_capped | sm.n_big)) {
-        atomicAdd(w.counters + 0, (unsigned long long)sm.n_capped);
-        atomicAdd(w.counters + 1, (unsigned long long)sm.n_big);
+    if (threadIdx.x == 0) {
+        if (sm.n_capped | sm.n_big) {
+            atomicAdd(w.counters + 0, (unsigned long long)sm.n_capped);
+            atomicAdd(w.counters + 1, (unsigned long long)sm.n_big);
+        }
+        // the last CTA to finish clears the hand-out state for the next launch and passes the pair total on
+        __threadfence();
+        if (atomicAdd(ts.exit_ticket, 1u) == gridDim.x - 1u) {
+            __threadfence();
+            for (int b = 0; b < RT_ITEM_BINS; ++b) ts.bin_count[b] = 0u;
+            *ts.item_next = 0u;
+            *ts.exit_ticket = 0u;
+            *ts.prev_total = *(volatile unsigned long long*)ts.total_cost;
+            *ts.total_cost = 0ull;
+        }
     }
 }
 
@@ -783,7 +807,7 @@ size_t raster_tile_smem_bytes() { return sizeof(RtSmem); }
 
 void launch_raster_tile_forward(const ModelDev& m, const Workspace& w, const TileScratch& ts, int frame0, int n, Weights wt,
                                 float* alpha_out, int n_ctas, cudaStream_t st) {
-    // (the hand-out list was built by the last CTA of frame_front)
+    // (the items were emitted by frame_front, frame by frame)
     const long long tiles = (long long)n * w.tiles_x * w.tiles_y;
     const int grid = (int)(tiles < n_ctas ? tiles : n_ctas);
     launch_pdl(raster_tile_forward_kernel, dim3(grid), dim3(RT_THREADS), raster_tile_smem_bytes(), st, m, w, ts, frame0, n, wt, alpha_out);

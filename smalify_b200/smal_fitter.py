@@ -279,15 +279,58 @@ class SMALFitter(nn.Module):
         if from_host:
             torch.cuda.current_stream(self.device).synchronize()     # vis is a temporary host tensor
 
+    def stage_targets(self, sil_u8: torch.Tensor, joints: torch.Tensor, visibility: torch.Tensor, stream: torch.cuda.Stream):
+        """Pipelined upload of the NEXT targets of this fitter's frames (not in the reference, which re-sends its
+        targets inside every forward, smal_fitter.py:118-120): copies them into the library's second set of target buffers
+        on `stream` -- a copy stream, so that the transfer runs under the kernels of the step in flight -- and returns the
+        event that marks the copy.  Tensors: (n, S, S) uint8 {0, 1}, (n, 25, 2) float32 (row, col), (n, 25) uint8 for the
+        frames of `frame_shard`, pinned host memory or device memory; the caller keeps them alive until the event.
+        `swap_targets()` then makes them the targets of every later call."""
+        a, b = self.frame_shard
+        n = b - a
+        if tuple(sil_u8.shape) != (n, self.image_size, self.image_size) or sil_u8.dtype != torch.uint8:
+            raise ValueError(f"stage_targets: masks must be uint8 of shape {(n, self.image_size, self.image_size)}")
+        if tuple(joints.shape) != (n, K.N_KEYPOINTS, 2) or joints.dtype != torch.float32:
+            raise ValueError(f"stage_targets: joints must be float32 of shape {(n, K.N_KEYPOINTS, 2)}")
+        if tuple(visibility.shape) != (n, K.N_KEYPOINTS) or visibility.dtype != torch.uint8:
+            raise ValueError(f"stage_targets: visibility must be uint8 of shape {(n, K.N_KEYPOINTS)}")
+        devs = {t.is_cuda for t in (sil_u8, joints, visibility)}
+        if len(devs) != 1:
+            raise ValueError("stage_targets: all three tensors on the host (pinned) or all on the device")
+        from_host = not sil_u8.is_cuda
+        if from_host and not all(t.is_pinned() for t in (sil_u8, joints, visibility)):
+            raise ValueError("stage_targets: host tensors must be pinned (the copy is asynchronous)")
+        if not all(t.is_contiguous() for t in (sil_u8, joints, visibility)):
+            raise ValueError("stage_targets: tensors must be contiguous")
+        self._handle.stage_targets(a, n, _ptr(sil_u8), _ptr(joints), _ptr(visibility), from_host, ctypes.c_void_p(stream.cuda_stream))
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        return ev
+
+    def swap_targets(self, staged: torch.cuda.Event | None = None) -> int:
+        """Makes the staged targets current (the current stream first waits for `staged`, the event `stage_targets`
+        returned).  Returns the index (0 / 1) of the set now in use; `FusedFit` keeps one CUDA graph per set.  The
+        visibility rows of the new set are the staged ones: `target_visibility` is not re-sent over them."""
+        if staged is not None:
+            torch.cuda.current_stream(self.device).wait_event(staged)
+        idx = self._handle.swap_targets()
+        # the staged rows stand until `target_visibility` changes again (the attributes sil_imgs / target_joints /
+        # target_visibility keep describing the targets the fitter was constructed with)
+        self._vis_sent = (self._vis_key(), {(self.frame_shard[0], self.frame_shard[1] - self.frame_shard[0])})
+        return idx
+
+    def _vis_key(self):
+        tv = self.target_visibility
+        # (host tensor, as the loaders produce: its content is the key -- a rebound tensor can reuse a freed address)
+        return hash(tv.numpy().tobytes()) if tv.device.type == "cpu" else (tv.data_ptr(), tv._version)
+
     def _sync_visibility(self, a, n):
         """The stage loop rewrites target_visibility in place or rebinds it (optimize_to_joints.py:98-110): the rows
         are sent again only when the tensor or its version counter changed since they were last sent."""
-        tv = self.target_visibility
-        # (host tensor, as the loaders produce: its content is the key -- a rebound tensor can reuse a freed address)
-        key = hash(tv.numpy().tobytes()) if tv.device.type == "cpu" else (tv.data_ptr(), tv._version)
+        key = self._vis_key()
         if self._vis_sent is None or self._vis_sent[0] != key:
             self._vis_sent = (key, set())
-        if (a, n) in self._vis_sent[1]:
+        if any(sa <= a and a + n <= sa + sn for sa, sn in self._vis_sent[1]):
             return
         vis = self._vis_u8(a, n).to(self.device, non_blocking=False)
         h = self._handle
@@ -589,6 +632,7 @@ class FusedFit:
         self.step_count = 0
         self._graph = None
         self._graph_key = None
+        self._graphs = {}
         self._warmed = False
         self.peer_error = None
         self.collective = None
@@ -649,7 +693,7 @@ class FusedFit:
         self.step_count = 0
         h = self.f._handle
         h.check(h.lib.smalfit_adam_reset(h.h, _stream(self.f.device)), "smalfit_adam_reset")
-        self._graph = None
+        self._graph, self._graphs = None, {}
 
     def _enqueue(self, weights, w_temp, lr, train, device_step: bool):
         f = self.f
@@ -692,7 +736,11 @@ class FusedFit:
             self._warmed = True
             return
         key = (tuple(float(w) for w in weights), float(w_temp), float(lr), tuple(int(t) for t in train))
-        if self._graph is None or self._graph_key != key:
+        tset = f._handle.target_set                # a graph replays the target buffers it was captured with
+        if self._graph_key != key:
+            self._graphs, self._graph_key = {}, key
+        self._graph = self._graphs.get(tset)
+        if self._graph is None:
             # warm-up on a side stream, then capture
             s = torch.cuda.Stream(device=f.device)
             s.wait_stream(torch.cuda.current_stream(f.device))
@@ -701,7 +749,7 @@ class FusedFit:
                 with torch.cuda.graph(g, stream=s):
                     self._enqueue(weights, w_temp, lr, train, device_step=True)
             torch.cuda.current_stream(f.device).wait_stream(s)
-            self._graph, self._graph_key = g, key
+            self._graph = self._graphs[tset] = g
         self._graph.replay()
 
     def total_loss(self) -> torch.Tensor:

@@ -395,3 +395,63 @@ def test_frame_shard_handle_matches_full_handle(constants, seq):
         assert torch.equal(res[0][1][k], res[1][1][k]), k
     with pytest.raises(_cabi.SmalfitError):
         part([0, 1], STAGE1, 1)
+
+
+def test_staged_targets_equal_serial_uploads(constants, oracle64, seq):
+    """Double-buffered targets (smalfit_stage_targets on a copy stream + smalfit_swap_targets) against the serial
+    smalfit_set_targets of the same target sequence: a fused loop whose targets alternate between two sets every step
+    ends with BIT-IDENTICAL parameters and Adam state either way, eager or graph-replayed (one graph per set), also
+    on a frame-shard handle; swapping with nothing staged is an error."""
+    from smalify_b200 import _cabi
+    from smalify_b200.smal_fitter import FusedFit, SMALFitter, _ptr, _stream
+    data_a, _ = seq
+    data_b, _ = synthetic.make_sequence(constants, N_SMALL, S_SMALL, H.oracle_renderer(oracle64, S_SMALL), seed=3)
+    row = K.STAGE_SCHEDULE[1]
+    w, w_temp, lr = row[:6], row[6], row[8]
+
+    def host_set(data):
+        _, sil, joints, vis = data
+        return ((sil.reshape(N_SMALL, S_SMALL, S_SMALL) > 0.5).to(torch.uint8).contiguous().pin_memory(),
+                joints.reshape(N_SMALL, K.N_KEYPOINTS, 2).float().contiguous().pin_memory(),
+                vis.reshape(N_SMALL, K.N_KEYPOINTS).to(torch.uint8).contiguous().pin_memory())
+    sets = [host_set(data_a), host_set(data_b)]
+    assert not torch.equal(sets[0][0], sets[1][0])
+
+    for shard in (None, (1, 3)):
+        lo, hi = shard or (0, N_SMALL)
+        fa = SMALFitter("cuda", data_a, N_SMALL, 1, True, constants=constants, frame_shard=shard)
+        fb = SMALFitter("cuda", data_a, N_SMALL, 1, True, constants=constants, frame_shard=shard)
+        with pytest.raises(_cabi.SmalfitError):
+            fa.swap_targets()
+        la, lb = FusedFit(fa, N_SMALL, frame_shard=shard), FusedFit(fb, N_SMALL, frame_shard=shard)
+        copy_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        h = fb._handle
+        seen = set()
+        for step in range(8):
+            sil, joints, vis = (t[lo:hi] for t in sets[step & 1])
+            # pipelined: stage on the copy stream (after the step that last read that set), swap, step
+            done = torch.cuda.Event()
+            done.record(main)
+            copy_stream.wait_event(done)
+            ev = fa.stage_targets(sil, joints, vis, copy_stream)
+            seen.add(fa.swap_targets(ev))
+            la.step(w, w_temp, lr, use_graph=(step >= 2))
+            # serial: overwrite the one set in place on the main stream
+            h.check(h.lib.smalfit_set_targets(h.h, lo, hi - lo, _ptr(sil), _ptr(joints), _ptr(vis), 1, _stream(fb.device)), "set_targets")
+            lb.step(w, w_temp, lr, use_graph=(step >= 2))
+            torch.cuda.synchronize()
+            assert torch.equal(la.flat_p, lb.flat_p), (shard, step)
+            assert torch.equal(la.flat_m, lb.flat_m) and torch.equal(la.flat_v, lb.flat_v), (shard, step)
+            assert float(la.total_loss()) == float(lb.total_loss()), (shard, step)
+        assert seen == {0, 1}
+        assert len(la._graphs) == 2 and len(lb._graphs) == 1
+        assert fa._handle.status() == 0
+    # the drop-in surface reads the swapped-in set as well
+    fc = SMALFitter("cuda", data_a, N_SMALL, 1, True, constants=constants)
+    fd = SMALFitter("cuda", data_b, N_SMALL, 1, True, constants=constants)
+    ev = fc.stage_targets(*sets[1], torch.cuda.Stream())
+    fc.swap_targets(ev)
+    la_, _ = fc(list(range(N_SMALL)), STAGE1, 1)
+    lb_, _ = fd(list(range(N_SMALL)), STAGE1, 1)
+    assert float(la_) == float(lb_)

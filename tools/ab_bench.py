@@ -39,7 +39,8 @@ def main():
                 d = json.loads(res.stdout.strip().splitlines()[-1])
                 ph = d["roofline"]["phase_ms"]
                 print(f"{os.path.basename(lib):28s} it/s {d['value']:7.1f}  fwd {ph['raster_forward']:.4f}  bwd {ph['raster_backward']:.4f}  "
-                      f"bin {ph['face_rects']:.4f}  total {ph['total']:.4f}  loss {d['final_loss']}", flush=True)
+                      f"front {ph['pose_forward']:.4f}  fback {ph['frame_backward']:.4f}  shape {ph['shape_backward']:.4f}  total {ph['total']:.4f}  "
+                      f"e2e {d['e2e']['value']:.1f} (serial {d['e2e'].get('serial_value', 0):.1f})  loss {d['final_loss']}", flush=True)
             except Exception as e:  # noqa: BLE001
                 print(os.path.basename(lib), "FAILED", e, res.stderr[-400:], flush=True)
 
