@@ -26,10 +26,14 @@ Pinning status
   ``smal_fitter/p3d_renderer.py:22-39,61-68``; self-consistency is checked by
   fp64 finite differences, hard-coverage limits and hand-computed projections
   in ``tests/test_oracle.py``.
-* Loss terms, temporal term, stage loop: restated from
-  ``smal_fitter/smal_fitter.py:107-190`` and
-  ``smal_fitter/optimize_to_joints.py:90-137`` (that module cannot be imported:
-  it needs pytorch3d / matplotlib / nibabel).
+* Loss terms, temporal term, parameter block: restated from
+  ``smal_fitter/smal_fitter.py:107-190`` and PINNED against the unmodified
+  ``SMALFitter`` itself, imported in the build container with its PyTorch3D
+  ``Renderer`` replaced by a stand-in that renders with this module
+  (``tests/test_fitter_vs_reference.py``: losses bit-identical, gradients 3e-6);
+  the loader's tables for every shape family in ``tests/test_loader_vs_reference.py``.
+  Stage loop: restated from ``smal_fitter/optimize_to_joints.py:90-137`` (its
+  schedule table is compared with ``config.OPT_WEIGHTS`` in the same test).
 """
 from __future__ import annotations
 
