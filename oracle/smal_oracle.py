@@ -32,8 +32,9 @@ Pinning status
   ``Renderer`` replaced by a stand-in that renders with this module
   (``tests/test_fitter_vs_reference.py``: losses bit-identical, gradients 3e-6);
   the loader's tables for every shape family in ``tests/test_loader_vs_reference.py``.
-  Stage loop: restated from ``smal_fitter/optimize_to_joints.py:90-137`` (its
-  schedule table is compared with ``config.OPT_WEIGHTS`` in the same test).
+  Stage loop: restated from ``smal_fitter/optimize_to_joints.py:90-137`` and PINNED
+  the same way: the reference's ``main()`` is run and every optimiser step it takes
+  (trainable set, Adam settings and state, gradients) is checked against this module.
 """
 from __future__ import annotations
 
