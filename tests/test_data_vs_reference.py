@@ -91,3 +91,105 @@ def test_loaders_equal_the_reference_loaders():
     assert out["badja"]["all"]["frames"] == 3 and out["badja"]["range"]["frames"] == 2
     for label, d in out["badja"].items():
         assert (d["rgb"], d["sil"], d["joints"], d["vis"]) == (0.0, 0.0, 0.0, 0.0), (label, d)
+
+
+CHILD_CKPT = r'''
+import json, os, pickle, sys, tempfile, types
+import numpy as np
+import torch
+repo, ref = sys.argv[1], sys.argv[2]
+sys.path.insert(0, repo); sys.path.insert(0, os.path.join(repo, "tests"))
+from smalify_b200 import constants as K, data_io, model_io, synthetic
+from smalify_b200.model_io import _ChStub
+
+def stub(name, **attrs):
+    mod = types.ModuleType(name)
+    for k, v in attrs.items():
+        setattr(mod, k, v)
+    sys.modules[name] = mod
+    return mod
+
+saved = {}
+stub("chumpy", Ch=_ChStub); stub("chumpy.ch", Ch=_ChStub)
+stub("matplotlib"); stub("matplotlib.pyplot"); stub("trimesh", Trimesh=lambda vertices, faces, process: types.SimpleNamespace(export=lambda p: saved.setdefault("ply", []).append((p, np.asarray(vertices), np.asarray(faces)))))
+stub("imageio", imsave=lambda p, a: saved.setdefault("png", []).append((p, a.shape)))
+stub("data_loader", load_badja_sequence=None, load_stanford_sequence=None)
+stub("draw_smal_joints", SMALJointDrawer=type("SMALJointDrawer", (), {}))
+stub("utils", eul_to_axis=lambda e: np.asarray(K.GLOBAL_ROT_INIT, dtype=np.float64))
+stub("p3d_renderer", Renderer=type("Renderer", (torch.nn.Module,), {"__init__": lambda self, s, d: torch.nn.Module.__init__(self)}))
+os.chdir(ref)
+sys.path.insert(0, ref); sys.path.insert(0, os.path.join(ref, "smal_fitter"))
+import warnings
+warnings.simplefilter("ignore")
+from smal_fitter import SMALFitter
+import optimize_to_joints as ref_loop
+
+N, S = 3, 16
+g = torch.Generator().manual_seed(3)
+data = (torch.rand(N, 3, S, S, generator=g), torch.zeros(N, 1, S, S), torch.zeros(N, 25, 2), torch.ones(N, 25))
+names = ["%04d.png" % i for i in range(N)]
+want = {"global_rotation": torch.randn(N, 3, generator=g), "joint_rotations": torch.randn(N, 34, 3, generator=g),
+        "betas": torch.randn(20, generator=g), "log_betascale": torch.randn(6, generator=g), "trans": torch.randn(N, 3, generator=g)}
+
+class Fake:                     # what SMALFitter.export_parameters / vertices of the product return (tests/test_gpu_io.py runs the real one)
+    constants = types.SimpleNamespace(faces=np.array([[0, 1, 2], [2, 1, 3]]))
+    def vertices(self):
+        return torch.arange(N * 4 * 3, dtype=torch.float32).reshape(N, 4, 3)
+    def export_parameters(self, i):
+        return {"global_rotation": want["global_rotation"][i].numpy(), "joint_rotations": want["joint_rotations"][i].numpy(),
+                "betas": want["betas"].numpy(), "log_betascale": want["log_betascale"].numpy(), "trans": want["trans"][i].numpy()}
+
+out = {}
+# 1. the product's exporter writes, the reference's load_checkpoint reads (smal_fitter.py:192-207)
+d1 = tempfile.mkdtemp()
+ex = data_io.ResultExporter(d1, names)
+ex.stage_id, ex.epoch_name = 10, "0"
+ex.export_fitter(Fake())
+model = SMALFitter("cpu", data, N, 1, True)
+with torch.no_grad():                      # (its in-place row writes on leaf parameters need this under current torch)
+    model.load_checkpoint(d1, "st10_ep0")
+out["ref_reads_ours"] = {"global_rotation": float((model.global_rotation.detach() - want["global_rotation"]).abs().max()),
+                         "joint_rotations": float((model.joint_rotations.detach() - want["joint_rotations"]).abs().max()),
+                         "trans": float((model.trans.detach() - want["trans"]).abs().max()),
+                         "betas": float((model.betas.detach() - want["betas"]).abs().max()),
+                         "log_beta_scales": float((model.log_beta_scales.detach() - want["log_betascale"]).abs().max())}
+# 2. the reference's ImageExporter writes (optimize_to_joints.py:25-53), the product's files are compared with it
+d2 = tempfile.mkdtemp()
+rex = ref_loop.ImageExporter(d2, names)
+rex.stage_id, rex.epoch_name = 10, "0"
+verts = Fake().vertices()
+for i in range(N):
+    rex.export(np.zeros((S, S * 5, 3), np.uint8), i, i, Fake().export_parameters(i), verts, Fake.constants.faces)
+    ex.export(np.zeros((S, S * 5, 3), np.uint8), i, i, Fake().export_parameters(i), verts, Fake.constants.faces)
+same_tree = sorted(os.path.relpath(os.path.join(r, f), d2) for r, _, fs in os.walk(d2) for f in fs)
+ours_tree = sorted(os.path.relpath(os.path.join(r, f), d1) for r, _, fs in os.walk(d1) for f in fs)
+out["ref_tree"] = same_tree
+out["ours_tree"] = ours_tree
+pk = []
+for i in range(N):
+    a = pickle.load(open(os.path.join(d2, "%04d" % i, "st10_ep0.pkl"), "rb"))
+    b = pickle.load(open(os.path.join(d1, "%04d" % i, "st10_ep0.pkl"), "rb"))
+    pk.append(sorted(a) == sorted(b) and all(np.array_equal(a[k], b[k]) and a[k].dtype == b[k].dtype and a[k].shape == b[k].shape for k in a))
+out["pkl_equal"] = pk
+out["ref_png_ply_calls"] = [len(saved.get("png", [])), len(saved.get("ply", []))]
+out["ref_ply_paths"] = [os.path.relpath(p, d2) for p, _, _ in saved.get("ply", [])]
+print("RESULT " + json.dumps(out))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "smal_fitter")), reason="needs the SMALify checkout (build container only)")
+def test_checkpoint_wire_format_against_the_reference():
+    """Row 8f-2: the reference's `SMALFitter.load_checkpoint` reads what the product's exporter wrote, and the product's
+    exporter produces the file tree and the parameter pickles of the reference's `ImageExporter.export`."""
+    res = subprocess.run([sys.executable, "-c", CHILD_CKPT, REPO, REF], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("RESULT ")][-1][len("RESULT "):])
+    r = out["ref_reads_ours"]
+    assert r["global_rotation"] == 0.0 and r["joint_rotations"] == 0.0 and r["trans"] == 0.0, r
+    assert r["betas"] <= 1e-6 and r["log_beta_scales"] <= 1e-6, r          # (the reference averages the frames' copies: float32 mean)
+    assert out["pkl_equal"] == [True, True, True]
+    # the reference wrote its pkl files itself; png / ply went through the substituted imageio / trimesh: same names as ours
+    expect = sorted("%04d/st10_ep0.%s" % (i, e) for i in range(3) for e in ("pkl", "png", "ply"))
+    assert out["ours_tree"] == expect
+    assert out["ref_tree"] == sorted(p for p in expect if p.endswith(".pkl"))
+    assert out["ref_png_ply_calls"] == [3, 3] and sorted(out["ref_ply_paths"]) == sorted(p for p in expect if p.endswith(".ply"))
