@@ -193,3 +193,46 @@ def test_checkpoint_wire_format_against_the_reference():
     assert out["ours_tree"] == expect
     assert out["ref_tree"] == sorted(p for p in expect if p.endswith(".pkl"))
     assert out["ref_png_ply_calls"] == [3, 3] and sorted(out["ref_ply_paths"]) == sorted(p for p in expect if p.endswith(".ply"))
+
+
+CHILD_MARKERS = r'''
+import json, os, sys, types
+import numpy as np
+import torch
+repo, ref = sys.argv[1], sys.argv[2]
+sys.path.insert(0, repo)
+from smalify_b200 import constants as K, visualization as V
+for name in ("matplotlib", "matplotlib.pyplot", "torchvision", "torchvision.utils"):
+    sys.modules[name] = types.ModuleType(name)
+sys.modules["torchvision.utils"].make_grid = None
+os.chdir(ref)
+sys.path.insert(0, ref); sys.path.insert(0, os.path.join(ref, "smal_fitter"))
+import config
+from draw_smal_joints import SMALJointDrawer
+g = torch.Generator().manual_seed(5)
+img = torch.rand(3, 3, 96, 96, generator=g)
+lm = torch.randint(0, 96, (3, 25, 2), generator=g)            # integer (row, col): current cv2 rejects the float32 the reference passes
+vis = torch.rand(3, 25, generator=g) > 0.3
+out = {"tables": bool(np.array_equal(np.array(config.MARKER_COLORS), np.array(V.MARKER_COLORS)) and list(config.MARKER_TYPE) == list(V.MARKER_TYPE)),
+       "mesh_color": bool(np.allclose(np.array(config.MESH_COLOR) / 255.0, np.array(V.MESH_COLOR))),
+       "canonical": list(config.CANONICAL_MODEL_JOINTS) == list(K.CANONICAL_MODEL_JOINTS), "torso": list(config.TORSO_JOINTS) == list(K.TORSO_JOINTS),
+       "badja_classes": list(config.BADJA_ANNOTATED_CLASSES) == list(K.BADJA_ANNOTATED_CLASSES),
+       "n_pose_betas": [config.N_POSE == K.N_POSE, config.N_BETAS == K.N_BETAS], "crop_window_vis": [config.CROP_SIZE == K.CROP_SIZE, config.WINDOW_SIZE == K.WINDOW_SIZE, config.VIS_FREQUENCY == K.VIS_FREQUENCY]}
+for label, v in (("with_visibility", vis), ("all_visible", None)):
+    a = SMALJointDrawer.draw_joints(img, lm, visible=v)
+    b = V.draw_joints(img, lm.float(), visible=v)
+    out[label] = float((a - b).abs().max())
+print("RESULT " + json.dumps(out))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "smal_fitter")), reason="needs the SMALify checkout (build container only)")
+def test_joint_markers_and_config_tables_equal_the_reference():
+    """Row 8f-3 (host side) and the constant tables of config.py: marker drawing pixel for pixel, marker / colour tables,
+    joint index lists, sizes."""
+    res = subprocess.run([sys.executable, "-c", CHILD_MARKERS, REPO, REF], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("RESULT ")][-1][len("RESULT "):])
+    assert out["tables"] and out["mesh_color"] and out["canonical"] and out["torso"] and out["badja_classes"], out
+    assert out["n_pose_betas"] == [True, True] and out["crop_window_vis"] == [True, True, True], out
+    assert out["with_visibility"] == 0.0 and out["all_visible"] == 0.0, out
