@@ -455,3 +455,46 @@ def test_staged_targets_equal_serial_uploads(constants, oracle64, seq):
     la_, _ = fc(list(range(N_SMALL)), STAGE1, 1)
     lb_, _ = fd(list(range(N_SMALL)), STAGE1, 1)
     assert float(la_) == float(lb_)
+
+
+def test_cuda_path_matches_reference_smalfitter_golden(constants):
+    """The CUDA path against vectors the UNMODIFIED reference `SMALFitter` produced (tests/golden/fitter_golden.npz, made by
+    tests/golden/make_fitter_golden.py: its forward, get_temporal and torch autograd, with the PyTorch3D renderer replaced by
+    a stand-in that renders with the oracle): initial parameter block, loss terms, temporal terms and every gradient, for
+    three rows of the reference's OPT_WEIGHTS, one of them on a sub-window."""
+    import os
+    from smalify_b200.smal_fitter import SMALFitter
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fitter_golden.npz"))
+    S, N = int(g["S"]), int(g["N"])
+    sil = torch.from_numpy(np.unpackbits(g["sil"])[:N * S * S].reshape(N, 1, S, S).astype(np.float32))
+    data = (torch.zeros(N, 3, S, S), sil, torch.from_numpy(g["joints"]), torch.from_numpy(g["vis"]))
+    f = SMALFitter("cuda", data, N, 1, True, constants=constants)
+    assert np.abs(f.betas.detach().cpu().numpy() - g["init_betas"]).max() <= 1e-7
+    assert np.abs(f.log_beta_scales.detach().cpu().numpy().reshape(-1)[:6] - g["init_log_beta_scales"]).max() <= 1e-7
+    assert np.abs(f.global_rotation.detach().cpu().numpy() - g["init_global_rotation"]).max() <= 1e-6
+    assert float(f.joint_rotations.detach().abs().max()) == 0.0 and float(f.trans.detach().abs().max()) == 0.0
+    names = ("betas", "log_beta_scales", "global_rotation", "joint_rotations", "trans")
+    for stage in range(3):
+        pre = "s%d_" % stage
+        with torch.no_grad():
+            for k in names:
+                getattr(f, k).copy_(torch.from_numpy(g["p_" + k]).to(f.device).reshape(getattr(f, k).shape))
+        for t in f.parameters():
+            t.grad = None
+            t.requires_grad_(True)
+        w = [float(x) for x in g[pre + "weights"]]
+        br = [int(i) for i in g[pre + "batch_range"]]
+        loss, objs = f(br, w[:6], stage)
+        jl, gl, tl = f.get_temporal(w[6])
+        (loss + jl + gl + tl).backward()
+        ref = float(g[pre + "loss"])
+        assert abs(float(loss) - ref) <= 2e-5 * abs(ref) + 1e-6, (stage, float(loss), ref)
+        for k in ("joint", "sil_reproj", "betas", "pose", "splay"):
+            r = float(g[pre + "term_" + k])
+            if not np.isnan(r):
+                assert abs(float(objs[k]) - r) <= 3e-5 * abs(r) + 1e-6, (stage, k, float(objs[k]), r)
+        for a, b in zip((jl, gl, tl), g[pre + "temporal"]):
+            assert abs(float(a) - float(b)) <= 2e-5 * abs(float(b)) + 1e-9, (stage, float(a), float(b))
+        for k in names:
+            r = torch.from_numpy(g[pre + "grad_" + k])
+            assert H.rel_err(getattr(f, k).grad.reshape(r.shape), r) < 1e-4, (stage, k)

@@ -195,3 +195,41 @@ def test_joint_limit_term_matches_reference_golden(constants):
     # without limits the weight is ignored, as in the reference
     total0, objs0 = O.fitter_forward(m, p, sil, torch.zeros(B, 25, 2), torch.zeros(B, 25), range(B), w, 16)
     assert objs0 == {} and float(total0) == 0.0
+
+
+@pytest.mark.parametrize("dtype,ltol,gtol", [(torch.float32, 2e-6, 1e-4), (torch.float64, 2e-5, 1e-4)])
+def test_loss_assembly_matches_reference_smalfitter_golden(constants, dtype, ltol, gtol):
+    """tests/golden/fitter_golden.npz holds what the UNMODIFIED reference `SMALFitter` computed (forward, get_temporal,
+    torch autograd; its PyTorch3D renderer replaced by a stand-in that renders with this oracle -- see
+    tests/golden/make_fitter_golden.py) for three rows of its own OPT_WEIGHTS: initial parameter block, every loss term,
+    the temporal terms and all gradients."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fitter_golden.npz"))
+    S, N = int(g["S"]), int(g["N"])
+    m = O.OracleModel.from_constants(constants, dtype)
+    init = O.FitParams.initial(m, N, K.GLOBAL_ROT_INIT)
+    if dtype == torch.float32:
+        assert np.array_equal(init.betas.numpy(), g["init_betas"]) and np.array_equal(init.log_beta_scales.numpy(), g["init_log_beta_scales"])
+    assert np.abs(init.global_rotation.numpy() - g["init_global_rotation"]).max() < 1e-6
+    sil = torch.from_numpy(np.unpackbits(g["sil"])[:N * S * S].reshape(N, 1, S, S).astype(np.float32))
+    joints, vis = torch.from_numpy(g["joints"]), torch.from_numpy(g["vis"])
+    names = ("betas", "log_beta_scales", "global_rotation", "joint_rotations", "trans")
+    for stage in range(3):
+        pre = "s%d_" % stage
+        p = O.FitParams(**{k: torch.from_numpy(g["p_" + k]).to(dtype).requires_grad_(True) for k in names})
+        w = g[pre + "weights"]
+        br = [int(i) for i in g[pre + "batch_range"]]
+        loss, objs = O.fitter_forward(m, p, sil, joints, vis, br, w[:6], S)
+        jl, gl, tl = O.temporal_terms(p, float(w[6]))
+        (loss + jl + gl + tl).backward()
+        assert abs(float(loss) - float(g[pre + "loss"])) <= ltol * abs(float(g[pre + "loss"])), stage
+        for k in ("joint", "sil_reproj", "betas", "pose", "splay"):
+            ref = float(g[pre + "term_" + k])
+            assert (k in objs) == (not math.isnan(ref)), (stage, k)
+            if k in objs:
+                assert abs(float(objs[k]) - ref) <= ltol * max(abs(ref), 1e-12), (stage, k, float(objs[k]), ref)
+        for a, b in zip((jl, gl, tl), g[pre + "temporal"]):
+            assert abs(float(a) - float(b)) <= ltol * max(abs(float(b)), 1e-12), stage
+        for k in names:
+            ref = torch.from_numpy(g[pre + "grad_" + k]).double()
+            got = getattr(p, k).grad.double()
+            assert float((got - ref).abs().max()) <= gtol * max(float(ref.abs().max()), 1e-12), (stage, k)
