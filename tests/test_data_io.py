@@ -105,3 +105,43 @@ def test_ply_and_exporter_layout(tmp_path):
             q = pickle.load(fh)
         assert set(q) == {"global_rotation", "joint_rotations", "betas", "log_betascale", "trans"} and q["trans"][0] == i
         assert (d / "st10_ep0.ply").exists()
+
+
+def _rle_encode(m: np.ndarray) -> str:
+    """Inverse of the COCO compressed RLE scheme (column-major runs, delta against the run two back, 5-bit groups)."""
+    flat = m.T.reshape(-1)
+    runs, val, cnt = [], 0, 0
+    for b in flat:
+        if b == val:
+            cnt += 1
+        else:
+            runs.append(cnt); cnt = 1; val ^= 1
+    runs.append(cnt)
+    out = []
+    for i, r in enumerate(runs):
+        x = r - runs[i - 2] if i > 2 else r
+        more = True
+        while more:
+            c = x & 0x1F
+            x >>= 5
+            more = not ((x == 0 and not (c & 0x10)) or (x == -1 and (c & 0x10)))
+            if more:
+                c |= 0x20
+            out.append(chr(c + 48))
+    return "".join(out)
+
+
+def test_rle_decode_inverts_the_encoder_on_random_masks():
+    """Property test (hypothesis): any binary mask of any small shape, including empty, full and single-run masks."""
+    from hypothesis import given, settings, strategies as st
+    from hypothesis.extra import numpy as hnp
+
+    @settings(max_examples=150, deadline=None)
+    @given(hnp.arrays(np.uint8, hnp.array_shapes(min_dims=2, max_dims=2, min_side=1, max_side=40), elements=st.integers(0, 1)),
+           st.integers(1, 9))
+    def check(mask, blob):
+        m = np.repeat(np.repeat(mask, blob, axis=0), blob, axis=1)[:64, :64]      # long runs as well as single pixels
+        assert np.array_equal(data_io.decode_coco_rle(_rle_encode(m), m.shape[0], m.shape[1]), m)
+    check()
+    for m in (np.zeros((7, 5), np.uint8), np.ones((7, 5), np.uint8)):
+        assert np.array_equal(data_io.decode_coco_rle(_rle_encode(m), 7, 5), m)
